@@ -1,0 +1,57 @@
+"""CPU, this container only: run the REAL reference (imported from /root/reference) side by side with the numpy
+oracle on fresh random inputs.  Skipped where /root/reference is absent (the GPU box).  Runs in a subprocess
+because the reference must be imported before torch/scipy."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle")
+import ref_import
+tt = ref_import.import_reference()
+import numpy as np
+from oracle import tortto_oracle as O
+rng = np.random.default_rng(1234)
+def rel(a, b): return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))) / max(np.max(np.abs(b)), 1e-30))
+worst = 0.0
+for trial in range(12):
+    n, g = int(rng.integers(1, 4)), int(rng.choice([1, 1, 2]))
+    ci, co = g * int(rng.integers(1, 5)), g * int(rng.integers(1, 5))
+    k = (int(rng.integers(1, 4)), int(rng.integers(1, 4))); s = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+    d = (int(rng.integers(1, 3)), int(rng.integers(1, 3))); p = (int(rng.integers(0, 3)), int(rng.integers(0, 3)))
+    h, w = int(rng.integers(6, 14)), int(rng.integers(6, 14))
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = rng.standard_normal((co, ci // g, *k)).astype(np.float32)
+    b = rng.standard_normal(co).astype(np.float32)
+    xt = tt.tensor(x, requires_grad=True); wtt = tt.tensor(wt, requires_grad=True); bt = tt.tensor(b, requires_grad=True)
+    y = tt.nn.functional.conv2d(xt, wtt, bt, s, p, d, g)
+    dy = rng.standard_normal(y.shape).astype(np.float32)
+    y.backward(tt.tensor(dy))
+    yo = O.conv2d_forward(x, wt, b, s, p, d, g)
+    dxo, dwo, dbo = O.conv2d_backward(x, wt, dy, s, p, d, g, has_bias=True)
+    worst = max(worst, rel(yo, y.data), rel(dxo, xt.grad), rel(dwo, wtt.grad), rel(dbo, bt.grad))
+    # max pool on the same input
+    kk = (int(rng.integers(2, 4)),) * 2; ss = (int(rng.integers(1, 3)),) * 2; pp = (int(rng.integers(0, 2)),) * 2
+    ceil = bool(rng.integers(0, 2))
+    xt2 = tt.tensor(x, requires_grad=True)
+    yp = tt.nn.functional.max_pool2d(xt2, kk, ss, pp, (1, 1), ceil)
+    dyp = rng.standard_normal(yp.shape).astype(np.float32)
+    yp.backward(tt.tensor(dyp))
+    ypo, idx = O.max_pool2d_forward(x, kk, ss, pp, 1, ceil)
+    assert np.array_equal(ypo, yp.data), "pool fwd"
+    assert np.array_equal(O.max_pool2d_backward(dyp, idx, x.shape, kk, ss, pp, 1, ceil), xt2.grad), "pool bwd"
+print("WORST", worst)
+assert worst < 2e-5
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/tortto"), reason="reference not mounted")
+def test_oracle_matches_live_reference():
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "WORST" in r.stdout
