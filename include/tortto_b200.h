@@ -1,0 +1,144 @@
+/*
+ * tortto_b200.h — C ABI of libtortto_b200.so: the B200 (sm_100a) implementation of the conv / BN / ReLU / max-pool
+ * hot path of samrere/pytortto (tortto v1.3.4).
+ *
+ * This is the drop-in boundary: plain C structs, raw device pointers, a CUDA stream handle passed
+ * as void*; the CALLER owns every buffer (inputs, outputs, workspace); each call enqueues work on the given stream
+ * and returns without synchronising; return value 0 = ok, non-zero = error (text via ttb_last_error()).
+ * No exceptions cross the boundary, no torch / cupy types appear in any signature.
+ *
+ * Reference interface each entry point replaces (paths relative to /root/reference/src/tortto/):
+ *   ttb_conv2d_fprop        Convolution.forward            autograd/grad_nn.py:685-715  (_conv2d :595-643)
+ *   ttb_conv2d_dgrad        _conv2d_backward_x             autograd/grad_nn.py:659-682  (also TransposedConvolution.forward :755)
+ *   ttb_conv2d_wgrad        _conv2d_backward_w             autograd/grad_nn.py:646-656
+ *   ttb_bias_grad           gd0.sum((0,2,3))               autograd/grad_nn.py:727-728
+ *   ttb_bn_*                BatchNorm.forward / backward   autograd/grad_nn.py:909-989
+ *   ttb_relu_fwd / _bwd     Relu.forward / backward        autograd/grad_nn.py:50-69
+ *   ttb_maxpool2d_fwd/_bwd  _max_pool2d / _backward        autograd/grad_nn.py:784-826
+ *   ttb_add / ttb_axpy      Add.forward, grad accumulation tensor.py:597-599, autograd/function.py:88-93
+ *   ttb_sgd_step            optim/_functional.py:4-22
+ *   ttb_nchw_to_nhwc etc.   the device-memory layer, xparray.py:44-78 / ToCopy autograd/grad_fcn.py:849-878
+ *
+ * Data layout in HBM: 4-D activations are stored NHWC (channels innermost) as float32; the logical shape seen by
+ * the Python host layer stays (N, C, H, W).  Conv weights are stored "KRSC": [Cout][kh][kw][Cin/groups] float32
+ * (the same bytes as a channels-last view of the reference's (Cout, Cin/g, kh, kw) parameter).
+ */
+#ifndef TORTTO_B200_H
+#define TORTTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* math modes for the convolution contractions */
+enum {
+  TTB_MATH_FP32 = 0, /* CUDA-core FFMA, exact fp32 (generic fallback: any groups / dilation / channel count) */
+  TTB_MATH_TF32 = 1, /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+  TTB_MATH_BF16 = 2  /* tcgen05.mma kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+};
+
+/* One 2-D convolution problem (cross-correlation, zero padding), reference semantics of F.conv2d
+ * (nn/functional.py:80-88).  All sizes in elements. */
+typedef struct ttb_conv_desc {
+  int32_t n, c, h, w;          /* input  x: logical (N, C, H, W)                                        */
+  int32_t k;                   /* output channels                                                       */
+  int32_t r, s;                /* filter height, width                                                  */
+  int32_t stride_h, stride_w;
+  int32_t pad_h, pad_w;
+  int32_t dil_h, dil_w;
+  int32_t groups;
+  int32_t p, q;                /* output y: logical (N, K, P, Q); P = floor((H+2ph-dh(r-1)-1)/sh+1)     */
+  int32_t math_mode;           /* TTB_MATH_*                                                            */
+} ttb_conv_desc;
+
+typedef struct ttb_pool_desc {
+  int32_t n, c, h, w;          /* input                                                                 */
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int32_t p, q;                /* output spatial size (the host computes floor/ceil_mode geometry)      */
+} ttb_pool_desc;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char* ttb_last_error(void);            /* thread-local text of the last failure                    */
+int ttb_version(void);                       /* ABI version, bumps on any signature change               */
+int ttb_device_sm_count(int* out);           /* SM count of the current device                           */
+/* 1 if the tcgen05 tensor path supports this problem in the requested math mode, else 0 (then the FP32 path runs) */
+int ttb_conv2d_tensor_path_supported(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
+
+/* ---- layout --------------------------------------------------------------------------------------------- */
+int ttb_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, void* stream);
+int ttb_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, void* stream);
+
+/* ---- convolution ---------------------------------------------------------------------------------------- */
+size_t ttb_conv2d_workspace_size(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
+/* y[N,P,Q,K] = conv(x[N,H,W,C], w[K,R,S,C/g]) (+ bias[K] if bias != NULL) */
+int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* dx[N,H,W,C] = input gradient; every element of dx is written (zeros where no output touches it) */
+int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* dw[K,R,S,C/g] = weight gradient (overwritten, not accumulated) */
+int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* db[K] = sum over rows of dy[M,K] */
+int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void* stream);
+
+/* ---- batch norm (x viewed as [M = N*H*W rows][C channels]) ---------------------------------------------- */
+/* number of row chunks ttb_bn_stats / ttb_bn_bwd_reduce emit partial sums for */
+int ttb_bn_num_chunks(int64_t m, int c);
+/* partials[chunk][2][C] (double): per-chunk sum(x), sum(x*x) */
+int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chunks, void* stream);
+/* sums[2][C] = sum over chunks (double).  This is the buffer a data-parallel run all-reduces (SyncBN). */
+int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream);
+/* from sums[2][C] over `count` elements per channel: mean, var_eps = biased var + eps, sd = sqrt(var_eps)
+ * (what BatchNorm.forward saves, grad_nn.py:962-963), scale = gamma/sd, shift = beta - mean*scale, and, if
+ * running_mean/var != NULL, running = (1-momentum)*running + momentum*{mean, var*count/(count-1)} (:925-930). */
+int ttb_bn_finalize(const double* sums, int64_t count, int c, float eps, float momentum,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    float* mean, float* var_eps, float* sd, float* scale, float* shift, void* stream);
+/* eval mode / precomputed statistics: fills var_eps, sd, scale, shift from given mean & var */
+int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float eps, const float* gamma,
+                        const float* beta, float* mean, float* var_eps, float* sd, float* scale, float* shift,
+                        void* stream);
+/* y = x*scale[c] + shift[c]; relu != 0 fuses y = max(y, 0) */
+int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale, const float* shift, int relu,
+                 void* stream);
+/* partials[chunk][2][C]: sum(dy), sum(dy*(x-mean)).  If relu_out != NULL dy is first masked by (relu_out > 0)
+ * (fused ReLU backward, grad_nn.py:64-69). */
+int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, int64_t m, int c,
+                      double* partials, int num_chunks, void* stream);
+/* from sums[2][C]: dgamma = sum(dy*(x-mean))/sd, dbeta = sum(dy), and the three per-channel coefficients of
+ * dx = c1*(dy - c2 - (x-mean)*c3)  (grad_nn.py:984-988 re-associated) */
+int ttb_bn_bwd_finalize(const double* sums, int64_t count, int c, const float* gamma, const float* var_eps,
+                        const float* sd, float* dgamma, float* dbeta, float* coef /*[3][C]*/, void* stream);
+int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
+                     float* dx, int64_t m, int c, void* stream);
+
+/* ---- relu / elementwise ---------------------------------------------------------------------------------- */
+int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream);              /* y may alias x (in-place) */
+int ttb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+int ttb_add(const float* a, const float* b, float* out, int64_t n, void* stream); /* out may alias a or b    */
+int ttb_axpy(float alpha, const float* x, float* y, int64_t n, void* stream);     /* y += alpha*x            */
+int ttb_scale(float alpha, float* x, int64_t n, void* stream);                    /* x *= alpha              */
+int ttb_fill(float value, float* x, int64_t n, void* stream);
+/* one SGD update of a flat parameter range (optim/_functional.py:4-22); first_step != 0 means the momentum buffer
+ * is initialised to d_p (buf = d_p) instead of buf = momentum*buf + (1-dampening)*d_p */
+int ttb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                 float dampening, float weight_decay, int nesterov, int first_step, void* stream);
+
+/* ---- max pool --------------------------------------------------------------------------------------------- */
+/* y[N,P,Q,C] = max over window (padding acts as -inf); idx[N,P,Q,C] (uint8) = r*kw+s of the FIRST maximum in
+ * row-major window order (two-stage nanargmax of the reference) */
+int ttb_maxpool2d_fwd(const ttb_pool_desc* d, const float* x, float* y, uint8_t* idx, void* stream);
+/* dx[N,H,W,C]: reference semantics — where several windows selected the same input element the LAST window in
+ * (n, p, q) raster order wins (assignment, not accumulation; grad_nn.py:820).  accumulate != 0 switches to the
+ * PyTorch behaviour (sum). */
+int ttb_maxpool2d_bwd(const ttb_pool_desc* d, const float* dy, const uint8_t* idx, float* dx, int accumulate,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORTTO_B200_H */

@@ -1,0 +1,374 @@
+// BatchNorm2d forward/backward on NHWC activations viewed as [M rows][C channels] (HBM-bound).
+//
+// Reference: BatchNorm.forward/backward, /root/reference/src/tortto/autograd/grad_nn.py:909-989.
+// The reference makes ~8 full-tensor passes forward and ~10 backward; here forward is 2 reads + 1 write
+// (column reduce, then one fused normalise[+ReLU] pass) and backward is 4 reads + 1 write (column reduce of
+// sum(dy), sum(dy*(x-mean)); then one fused dx pass).
+//
+// Column reductions: thread -> fixed channel quad (float4 = 4 channels), rows strided across the block and
+// the grid; per-thread fp32 partials over <= kRowsPerThread rows, block tree in shared memory, one double
+// partial per (chunk, channel) written to HBM, and a tiny second kernel sums chunks in double in a FIXED
+// order (deterministic; no atomics).  The [2][C] double sums are what a data-parallel run all-reduces.
+#include "common.cuh"
+
+namespace ttb {
+
+constexpr int kBnThreads = 256;
+constexpr int kRowsPerThread = 32;  // fp32 accumulation length per thread before widening to double
+
+struct ColGeom {
+  int tx;        // threads along channel quads (power of two <= 256)
+  int ty;        // threads along rows = 256 / tx
+  int qblocks;   // gridDim.x = ceil(cq / tx)
+  int chunks;    // gridDim.y
+  int64_t rows_per_chunk;
+};
+
+static ColGeom col_geom(int64_t m, int c) {
+  ColGeom g;
+  int cq = (c + 3) / 4;
+  int tx = 1;
+  while (tx < cq && tx < kBnThreads) tx <<= 1;
+  g.tx = tx;
+  g.ty = kBnThreads / tx;
+  g.qblocks = (cq + tx - 1) / tx;
+  int64_t rows_per_chunk = (int64_t)g.ty * kRowsPerThread;
+  int64_t chunks = ceil_div(m, rows_per_chunk);
+  // keep the partial buffer and the finalize loop small: at most ~8 CTAs per SM worth of chunks
+  int64_t cap = (int64_t)sm_count() * 8 / g.qblocks;
+  if (cap < 1) cap = 1;
+  if (chunks > cap) {
+    chunks = cap;
+    rows_per_chunk = ceil_div(m, chunks);
+    rows_per_chunk = ceil_div(rows_per_chunk, g.ty) * g.ty;
+    chunks = ceil_div(m, rows_per_chunk);
+  }
+  if (chunks < 1) chunks = 1;
+  g.chunks = (int)chunks;
+  g.rows_per_chunk = rows_per_chunk;
+  return g;
+}
+
+// MODE 0: s0 = sum(a), s1 = sum(a*a)                          (forward statistics; a = x)
+// MODE 1: s0 = sum(g), s1 = sum(g*(b-mean)), g = a or masked  (backward; a = dy, b = x, mask = relu_out > 0)
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(kBnThreads)
+col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
+                  const float* __restrict__ mask, int64_t m, int c, int tx_n, int64_t rows_per_chunk,
+                  double* __restrict__ partials) {
+  extern __shared__ float4 sm[];  // [2][ty][tx]
+  const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = kBnThreads / tx_n;
+  const int quad = blockIdx.x * tx_n + tx;
+  const int ch = quad * 4;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (ch < c) {
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 1) {
+      if (VEC) mu = ld_f4(mean + ch);
+      else {
+        mu.x = mean[ch];
+        if (ch + 1 < c) mu.y = mean[ch + 1];
+        if (ch + 2 < c) mu.z = mean[ch + 2];
+        if (ch + 3 < c) mu.w = mean[ch + 3];
+      }
+    }
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+    int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
+    for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+      const int64_t off = r * c + ch;
+      float4 va, vb = make_float4(0.f, 0.f, 0.f, 0.f), vm = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (VEC) {
+        va = ld_f4_stream(a + off);
+        if (MODE == 1) {
+          vb = ld_f4_stream(b + off);
+          if (mask) vm = ld_f4_stream(mask + off);
+        }
+      } else {
+        va = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* pa = &va.x; float* pb = &vb.x; float* pm = &vm.x;
+        for (int j = 0; j < 4 && ch + j < c; ++j) {
+          pa[j] = a[off + j];
+          if (MODE == 1) {
+            pb[j] = b[off + j];
+            if (mask) pm[j] = mask[off + j];
+          }
+        }
+      }
+      if (MODE == 0) {
+        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
+        s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
+        s1.z = fmaf(va.z, va.z, s1.z); s1.w = fmaf(va.w, va.w, s1.w);
+      } else {
+        if (mask) {
+          va.x = vm.x > 0.f ? va.x : 0.f; va.y = vm.y > 0.f ? va.y : 0.f;
+          va.z = vm.z > 0.f ? va.z : 0.f; va.w = vm.w > 0.f ? va.w : 0.f;
+        }
+        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
+        s1.x = fmaf(va.x, vb.x - mu.x, s1.x); s1.y = fmaf(va.y, vb.y - mu.y, s1.y);
+        s1.z = fmaf(va.z, vb.z - mu.z, s1.z); s1.w = fmaf(va.w, vb.w - mu.w, s1.w);
+      }
+    }
+  }
+  sm[ty * tx_n + tx] = s0;
+  sm[(ty_n + ty) * tx_n + tx] = s1;
+  __syncthreads();
+  // ty == 0 row of threads finishes the block reduction in double, in fixed order
+  if (ty == 0 && ch < c) {
+    double d0[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0};
+    for (int j = 0; j < ty_n; ++j) {
+      float4 p = sm[j * tx_n + tx], q = sm[(ty_n + j) * tx_n + tx];
+      d0[0] += p.x; d0[1] += p.y; d0[2] += p.z; d0[3] += p.w;
+      d1[0] += q.x; d1[1] += q.y; d1[2] += q.z; d1[3] += q.w;
+    }
+    double* out = partials + (int64_t)blockIdx.y * 2 * c;
+    for (int j = 0; j < 4 && ch + j < c; ++j) {
+      out[ch + j] = d0[j];
+      out[c + ch + j] = d1[j];
+    }
+  }
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int c2,
+                                       double* __restrict__ sums) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c2) return;
+  double s = 0.0;
+  for (int k = 0; k < num_chunks; ++k) s += partials[(int64_t)k * c2 + i];
+  sums[i] = s;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int c, float eps, float momentum,
+                                   float one_minus_momentum, float unbias, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   float* mean, float* var_eps, float* sd, float* scale, float* shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double mu = sums[i] / count;
+  double var = sums[c + i] / count - mu * mu;  // biased variance, grad_nn.py:924
+  if (var < 0.0) var = 0.0;
+  float muf = (float)mu, varf = (float)var;
+  if (running_mean) running_mean[i] = __fadd_rn(__fmul_rn(one_minus_momentum, running_mean[i]), __fmul_rn(momentum, muf));
+  if (running_var)
+    running_var[i] = __fadd_rn(__fmul_rn(one_minus_momentum, running_var[i]), __fmul_rn(momentum, __fmul_rn(varf, unbias)));
+  float ve = __fadd_rn(varf, eps);
+  float s = sqrtf(ve);
+  mean[i] = muf;
+  var_eps[i] = ve;
+  sd[i] = s;
+  float g = gamma ? gamma[i] : 1.f;
+  float sc = g / s;
+  scale[i] = sc;
+  shift[i] = (beta ? beta[i] : 0.f) - muf * sc;
+}
+
+__global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const float* __restrict__ var_in, int c,
+                                       float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* mean, float* var_eps, float* sd, float* scale, float* shift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float mu = mean_in[i];
+  float ve = __fadd_rn(var_in[i], eps);
+  float s = sqrtf(ve);
+  mean[i] = mu; var_eps[i] = ve; sd[i] = s;
+  float sc = (gamma ? gamma[i] : 1.f) / s;
+  scale[i] = sc;
+  shift[i] = (beta ? beta[i] : 0.f) - mu * sc;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int c,
+                                       const float* __restrict__ gamma, const float* __restrict__ var_eps,
+                                       const float* __restrict__ sd, float* dgamma, float* dbeta, float* coef) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double sdy = sums[i], sdyx = sums[c + i];
+  if (dbeta) dbeta[i] = (float)sdy;
+  if (dgamma) dgamma[i] = (float)(sdyx / (double)sd[i]);
+  float g = gamma ? gamma[i] : 1.f;
+  coef[i] = g / sd[i];                                      // c1
+  coef[c + i] = (float)(sdy / count);                       // c2
+  coef[2 * c + i] = (float)(sdyx / (count * (double)var_eps[i]));  // c3
+}
+
+// y = x*scale + shift (+ReLU).  One float4 = 4 channels; channel quad = i % cq.
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n4, int cq,
+                const float* __restrict__ scale, const float* __restrict__ shift) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int q = (int)(i % cq);
+    float4 v = ld_f4_stream(x + 4 * i);
+    float4 sc = ld_f4(scale + 4 * q), sh = ld_f4(shift + 4 * q);
+    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    if (RELU) {
+      v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+      v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+    }
+    st_f4(y + 4 * i, v);
+  }
+}
+
+template <bool RELU>
+__global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
+                                       const float* __restrict__ scale, const float* __restrict__ shift) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int ch = (int)(i % c);
+    float v = fmaf(x[i], scale[ch], shift[ch]);
+    if (RELU) v = v < 0.f ? 0.f : v;
+    y[i] = v;
+  }
+}
+
+// dx = c1*(g - c2 - (x-mean)*c3), g = dy (masked by relu_out > 0 when given)
+template <bool MASK>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ mask, const float* __restrict__ coef, float* __restrict__ dx,
+                    int64_t n4, int cq, int c) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int q = (int)(i % cq);
+    float4 g = ld_f4_stream(dy + 4 * i), v = ld_f4_stream(x + 4 * i);
+    if (MASK) {
+      float4 o = ld_f4_stream(mask + 4 * i);
+      g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+      g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+    }
+    float4 mu = ld_f4(mean + 4 * q), c1 = ld_f4(coef + 4 * q), c2 = ld_f4(coef + c + 4 * q),
+           c3 = ld_f4(coef + 2 * c + 4 * q);
+    float4 r;
+    r.x = c1.x * (g.x - c2.x - (v.x - mu.x) * c3.x);
+    r.y = c1.y * (g.y - c2.y - (v.y - mu.y) * c3.y);
+    r.z = c1.z * (g.z - c2.z - (v.z - mu.z) * c3.z);
+    r.w = c1.w * (g.w - c2.w - (v.w - mu.w) * c3.w);
+    st_f4(dx + 4 * i, r);
+  }
+}
+
+template <bool MASK>
+__global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                           const float* __restrict__ mean, const float* __restrict__ mask,
+                                           const float* __restrict__ coef, float* __restrict__ dx, int64_t n, int c) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int ch = (int)(i % c);
+    float g = dy[i];
+    if (MASK) g = mask[i] > 0.f ? g : 0.f;
+    dx[i] = coef[ch] * (g - coef[c + ch] - (x[i] - mean[ch]) * coef[2 * c + ch]);
+  }
+}
+
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE>
+static int launch_col_reduce(const float* a, const float* b, const float* mean, const float* mask, int64_t m, int c,
+                             double* partials, int num_chunks, cudaStream_t st, const char* what) {
+  if (m <= 0 || c <= 0) return 0;
+  ColGeom g = col_geom(m, c);
+  TTB_REQUIRE(num_chunks == g.chunks, "%s: num_chunks=%d but ttb_bn_num_chunks gives %d", what, num_chunks, g.chunks);
+  bool vec = (c % 4 == 0) && a16(a) && (MODE == 0 || (a16(b) && a16(mean) && (!mask || a16(mask))));
+  dim3 grid(g.qblocks, g.chunks);
+  size_t smem = sizeof(float4) * 2 * kBnThreads;
+  if (vec)
+    col_reduce_kernel<MODE, true><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, m, c, g.tx, g.rows_per_chunk, partials);
+  else
+    col_reduce_kernel<MODE, false><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, m, c, g.tx, g.rows_per_chunk, partials);
+  return check_launch(what);
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_bn_num_chunks(int64_t m, int c) {
+  if (m <= 0 || c <= 0) return 1;
+  return col_geom(m, c).chunks;
+}
+
+int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chunks, void* stream) {
+  return launch_col_reduce<0>(x, nullptr, nullptr, nullptr, m, c, partials, num_chunks, as_stream(stream), "bn_stats");
+}
+
+int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
+  if (c2 <= 0) return 0;
+  reduce_partials_kernel<<<(c2 + 127) / 128, 128, 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
+  return check_launch("bn_reduce_partials");
+}
+
+int ttb_bn_finalize(const double* sums, int64_t count, int c, float eps, float momentum, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float* mean, float* var_eps,
+                    float* sd, float* scale, float* shift, void* stream) {
+  if (c <= 0) return 0;
+  TTB_REQUIRE(count > 0, "bn_finalize: count must be positive");
+  // N/(N-1) and (1-momentum) are evaluated in double on the host like the reference's Python floats
+  // (grad_nn.py:927-930), then applied to float32 arrays.
+  float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  float omm = (float)(1.0 - (double)momentum);
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, (double)count, c, eps, momentum, omm, unbias,
+                                                                     gamma, beta, running_mean, running_var, mean,
+                                                                     var_eps, sd, scale, shift);
+  return check_launch("bn_finalize");
+}
+
+int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float eps, const float* gamma,
+                        const float* beta, float* mean, float* var_eps, float* sd, float* scale, float* shift,
+                        void* stream) {
+  if (c <= 0) return 0;
+  bn_prepare_eval_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(mean_in, var_in, c, eps, gamma, beta, mean,
+                                                                         var_eps, sd, scale, shift);
+  return check_launch("bn_prepare_eval");
+}
+
+int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale, const float* shift, int relu,
+                 void* stream) {
+  int64_t n = m * c;
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (c % 4 == 0 && a16(x) && a16(y) && a16(scale) && a16(shift)) {
+    int grid = elementwise_grid(n / 4, 256);
+    if (relu) bn_apply_kernel<true><<<grid, 256, 0, st>>>(x, y, n / 4, c / 4, scale, shift);
+    else bn_apply_kernel<false><<<grid, 256, 0, st>>>(x, y, n / 4, c / 4, scale, shift);
+  } else {
+    int grid = elementwise_grid(n, 256);
+    if (relu) bn_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(x, y, n, c, scale, shift);
+    else bn_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(x, y, n, c, scale, shift);
+  }
+  return check_launch("bn_apply");
+}
+
+int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, int64_t m, int c,
+                      double* partials, int num_chunks, void* stream) {
+  return launch_col_reduce<1>(dy, x, mean, relu_out, m, c, partials, num_chunks, as_stream(stream), "bn_bwd_reduce");
+}
+
+int ttb_bn_bwd_finalize(const double* sums, int64_t count, int c, const float* gamma, const float* var_eps,
+                        const float* sd, float* dgamma, float* dbeta, float* coef, void* stream) {
+  if (c <= 0) return 0;
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, (double)count, c, gamma, var_eps, sd,
+                                                                         dgamma, dbeta, coef);
+  return check_launch("bn_bwd_finalize");
+}
+
+int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
+                     float* dx, int64_t m, int c, void* stream) {
+  int64_t n = m * c;
+  if (n <= 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  bool vec = c % 4 == 0 && a16(dy) && a16(x) && a16(dx) && a16(mean) && a16(coef) && (!relu_out || a16(relu_out));
+  if (vec) {
+    int grid = elementwise_grid(n / 4, 256);
+    if (relu_out) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n / 4, c / 4, c);
+    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n / 4, c / 4, c);
+  } else {
+    int grid = elementwise_grid(n, 256);
+    if (relu_out) bn_bwd_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n, c);
+    else bn_bwd_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n, c);
+  }
+  return check_launch("bn_bwd_apply");
+}
+
+}  // extern "C"

@@ -1,0 +1,212 @@
+// HBM-bound elementwise kernels: ReLU fwd/bwd, add, axpy, scale, fill, SGD, NCHW<->NHWC.
+// All are grid-stride, 128-bit vectorised with a scalar tail; grids are sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace ttb {
+
+constexpr int kThreads = 256;
+
+// Generic vectorised elementwise driver: `Op` gets float4s (vector body) and floats (tail / unaligned).
+template <class F4, class F1>
+__global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, F4 f4, F1 f1, bool vec_ok) {
+  int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    int64_t n4 = n >> 2;
+    // 2x unrolled grid-stride loop: two independent 128-bit accesses in flight per thread
+    int64_t i = tid;
+    for (; i + stride < n4; i += 2 * stride) {
+      f4(i);
+      f4(i + stride);
+    }
+    for (; i < n4; i += stride) f4(i);
+    for (int64_t j = (n4 << 2) + tid; j < n; j += stride) f1(j);
+  } else {
+    for (int64_t j = tid; j < n; j += stride) f1(j);
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <class F4, class F1>
+static int launch_ew(const char* what, int64_t n, bool vec_ok, F4 f4, F1 f1, cudaStream_t st) {
+  if (n <= 0) return 0;
+  int64_t items = vec_ok ? (n + 3) / 4 : n;
+  int grid = elementwise_grid(items, kThreads);
+  ew_kernel<<<grid, kThreads, 0, st>>>(n, f4, f1, vec_ok);
+  return check_launch(what);
+}
+
+__device__ __forceinline__ float relu1(float v) { return v < 0.f ? 0.f : v; }  // NaN propagates like np.maximum
+
+// ---------------------------------------------------------------------------------------------------------
+// NCHW <-> NHWC (per image: [C][HW] <-> [HW][C]) through a 32x33 shared tile, coalesced on both sides.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int rows, int cols, int64_t batch_stride) {
+  // src: [batch][rows][cols] -> dst: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const float* s = src + (int64_t)blockIdx.z * batch_stride;
+  float* d = dst + (int64_t)blockIdx.z * batch_stride;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int r = r0 + ty + j, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + j][tx] = s[(int64_t)r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    int c = c0 + ty + j, r = r0 + tx;
+    if (r < rows && c < cols) d[(int64_t)c * rows + r] = tile[tx][ty + j];
+  }
+}
+
+static int transpose_batched(const float* src, float* dst, int batch, int rows, int cols, cudaStream_t st) {
+  if (batch <= 0 || rows <= 0 || cols <= 0) return 0;
+  int done = 0;
+  while (done < batch) {  // gridDim.z <= 65535
+    int nb = batch - done < 65535 ? batch - done : 65535;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, nb);
+    int64_t off = (int64_t)done * rows * cols;
+    transpose_kernel<<<grid, 256, 0, st>>>(src + off, dst + off, rows, cols, (int64_t)rows * cols);
+    if (check_launch("transpose")) return 1;
+    done += nb;
+  }
+  return 0;
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, void* stream) {
+  return transpose_batched(src, dst, n, c, h * w, as_stream(stream));
+}
+
+int ttb_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, void* stream) {
+  return transpose_batched(src, dst, n, h * w, c, as_stream(stream));
+}
+
+int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream) {
+  bool v = aligned16(x) && aligned16(y);
+  return launch_ew(
+      "relu_fwd", n, v,
+      [=] __device__(int64_t i) {
+        float4 a = ld_f4(x + 4 * i);
+        a.x = relu1(a.x); a.y = relu1(a.y); a.z = relu1(a.z); a.w = relu1(a.w);
+        st_f4(y + 4 * i, a);
+      },
+      [=] __device__(int64_t i) { y[i] = relu1(x[i]); }, as_stream(stream));
+}
+
+int ttb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {
+  bool v = aligned16(dy) && aligned16(y) && aligned16(dx);
+  return launch_ew(
+      "relu_bwd", n, v,
+      [=] __device__(int64_t i) {
+        float4 g = ld_f4(dy + 4 * i), o = ld_f4(y + 4 * i);
+        g.x = o.x > 0.f ? g.x : g.x * 0.f;  // dy * (y > 0): keeps NaN/Inf semantics of the multiply
+        g.y = o.y > 0.f ? g.y : g.y * 0.f;
+        g.z = o.z > 0.f ? g.z : g.z * 0.f;
+        g.w = o.w > 0.f ? g.w : g.w * 0.f;
+        st_f4(dx + 4 * i, g);
+      },
+      [=] __device__(int64_t i) { dx[i] = y[i] > 0.f ? dy[i] : dy[i] * 0.f; }, as_stream(stream));
+}
+
+int ttb_add(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  bool v = aligned16(a) && aligned16(b) && aligned16(out);
+  return launch_ew(
+      "add", n, v,
+      [=] __device__(int64_t i) {
+        float4 p = ld_f4(a + 4 * i), q = ld_f4(b + 4 * i);
+        p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+        st_f4(out + 4 * i, p);
+      },
+      [=] __device__(int64_t i) { out[i] = a[i] + b[i]; }, as_stream(stream));
+}
+
+int ttb_axpy(float alpha, const float* x, float* y, int64_t n, void* stream) {
+  bool v = aligned16(x) && aligned16(y);
+  return launch_ew(
+      "axpy", n, v,
+      [=] __device__(int64_t i) {
+        float4 p = ld_f4(x + 4 * i), q = ld_f4(y + 4 * i);
+        q.x = fmaf(alpha, p.x, q.x); q.y = fmaf(alpha, p.y, q.y);
+        q.z = fmaf(alpha, p.z, q.z); q.w = fmaf(alpha, p.w, q.w);
+        st_f4(y + 4 * i, q);
+      },
+      [=] __device__(int64_t i) { y[i] = fmaf(alpha, x[i], y[i]); }, as_stream(stream));
+}
+
+int ttb_scale(float alpha, float* x, int64_t n, void* stream) {
+  bool v = aligned16(x);
+  return launch_ew(
+      "scale", n, v,
+      [=] __device__(int64_t i) {
+        float4 p = ld_f4(x + 4 * i);
+        p.x *= alpha; p.y *= alpha; p.z *= alpha; p.w *= alpha;
+        st_f4(x + 4 * i, p);
+      },
+      [=] __device__(int64_t i) { x[i] *= alpha; }, as_stream(stream));
+}
+
+int ttb_fill(float value, float* x, int64_t n, void* stream) {
+  bool v = aligned16(x);
+  return launch_ew(
+      "fill", n, v, [=] __device__(int64_t i) { st_f4(x + 4 * i, make_float4(value, value, value, value)); },
+      [=] __device__(int64_t i) { x[i] = value; }, as_stream(stream));
+}
+
+// optim/_functional.py:4-22, one fused pass: d_p = g + wd*p; buf = first ? d_p : mom*buf + (1-damp)*d_p;
+// d_p = nesterov ? d_p + mom*buf : buf; p += -lr*d_p.  Plain (non-fma-contracted) ops in the reference's order.
+__device__ __forceinline__ void sgd1(float& p, float g, float* buf, float lr, float mom, float damp, float wd,
+                                     int nesterov, int first) {
+  float d = g;
+  if (wd != 0.f) d = __fadd_rn(d, __fmul_rn(p, wd));
+  if (mom != 0.f) {
+    float b;
+    if (first) {
+      b = d;
+    } else {
+      b = __fadd_rn(__fmul_rn(*buf, mom), __fmul_rn(d, 1.f - damp));
+    }
+    *buf = b;
+    d = nesterov ? __fadd_rn(d, __fmul_rn(b, mom)) : b;
+  }
+  p = __fadd_rn(p, __fmul_rn(d, -lr));
+}
+
+int ttb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                 float dampening, float weight_decay, int nesterov, int first_step, void* stream) {
+  TTB_REQUIRE(momentum == 0.f || momentum_buf != nullptr, "sgd_step: momentum != 0 needs a momentum buffer");
+  bool v = aligned16(param) && aligned16(grad) && (momentum_buf == nullptr || aligned16(momentum_buf));
+  float* mb = momentum_buf;
+  return launch_ew(
+      "sgd_step", n, v,
+      [=] __device__(int64_t i) {
+        float4 p = ld_f4(param + 4 * i), g = ld_f4(grad + 4 * i);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mb && !first_step) b = ld_f4(mb + 4 * i);
+        sgd1(p.x, g.x, &b.x, lr, momentum, dampening, weight_decay, nesterov, first_step);
+        sgd1(p.y, g.y, &b.y, lr, momentum, dampening, weight_decay, nesterov, first_step);
+        sgd1(p.z, g.z, &b.z, lr, momentum, dampening, weight_decay, nesterov, first_step);
+        sgd1(p.w, g.w, &b.w, lr, momentum, dampening, weight_decay, nesterov, first_step);
+        if (mb) st_f4(mb + 4 * i, b);
+        st_f4(param + 4 * i, p);
+      },
+      [=] __device__(int64_t i) {
+        float p = param[i];
+        float b = (mb && !first_step) ? mb[i] : 0.f;
+        sgd1(p, grad[i], &b, lr, momentum, dampening, weight_decay, nesterov, first_step);
+        if (mb) mb[i] = b;
+        param[i] = p;
+      },
+      as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// MaxPool2d forward (with window-argmax byte index) and backward on NHWC activations (HBM-bound).
+//
+// Reference: _max_pool2d / _max_pool2d_backward, /root/reference/src/tortto/autograd/grad_nn.py:784-826.
+//  * forward: padding behaves as -inf; the selected element is the FIRST maximum in row-major (r, s) window order
+//    (nanargmax over kw, then over kh, :789-805).
+//  * backward: `expanded[pos] = dy` (:820) is an assignment through a fancy index, so when two overlapping windows
+//    chose the same input element the window that comes LAST in (n, p, q) raster order wins - gradients are not
+//    summed.  Implemented here as a gather (each input element searches the windows that cover it, last one
+//    first), so it is deterministic and needs neither atomics nor a zero-fill pass.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ttb {
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(ttb_pool_desc d, const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
+                   int64_t total, int cvec) {
+  // one thread per (n, p, q, channel group of `cvec` channels); cvec is 4 (float4) or 1
+  const int cg = d.c / cvec;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int g = (int)(t % cg);
+    int64_t pix = t / cg;
+    int q = (int)(pix % d.q);
+    int64_t t2 = pix / d.q;
+    int p = (int)(t2 % d.p);
+    int n = (int)(t2 / d.p);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {-1, -1, -1, -1};
+    for (int r = 0; r < d.kh; ++r) {
+      int h = p * d.stride_h - d.pad_h + r * d.dil_h;
+      if (h < 0 || h >= d.h) continue;
+      for (int s = 0; s < d.kw; ++s) {
+        int w = q * d.stride_w - d.pad_w + s * d.dil_w;
+        if (w < 0 || w >= d.w) continue;
+        const float* px = x + (((int64_t)n * d.h + h) * d.w + w) * d.c + g * cvec;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (cvec == 4) {
+          float4 f = ld_f4(px);
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+          v[0] = px[0];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // strict '>' keeps the first maximum; a NaN ranks as -inf (nanargmax ignores NaNs)
+          float key = (v[j] == v[j]) ? v[j] : -INFINITY;
+          if (j < cvec && (bi[j] < 0 || key > best[j])) {
+            best[j] = key;
+            bi[j] = r * d.kw + s;
+          }
+        }
+      }
+    }
+    int64_t o = pix * d.c + g * cvec;
+    for (int j = 0; j < cvec; ++j) {
+      y[o + j] = best[j];
+      idx[o + j] = (uint8_t)(bi[j] < 0 ? 0 : bi[j]);
+    }
+  }
+}
+
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t* __restrict__ idx,
+                   float* __restrict__ dx, int64_t total) {
+  // one thread per input element (n, h, w, c); c fastest -> coalesced
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int c = (int)(t % d.c);
+    int64_t pix = t / d.c;
+    int w = (int)(pix % d.w);
+    int64_t t2 = pix / d.w;
+    int h = (int)(t2 % d.h);
+    int n = (int)(t2 / d.h);
+    float acc = 0.f;
+    bool done = false;
+    // r ascending <=> p descending, s ascending <=> q descending: the first hit is the last writer in raster order
+    for (int r = 0; r < d.kh && !done; ++r) {
+      int hp = h + d.pad_h - r * d.dil_h;
+      if (hp < 0) break;
+      if (hp % d.stride_h) continue;
+      int p = hp / d.stride_h;
+      if (p >= d.p) continue;
+      for (int s = 0; s < d.kw; ++s) {
+        int wq = w + d.pad_w - s * d.dil_w;
+        if (wq < 0) break;
+        if (wq % d.stride_w) continue;
+        int q = wq / d.stride_w;
+        if (q >= d.q) continue;
+        int64_t o = (((int64_t)n * d.p + p) * d.q + q) * d.c + c;
+        if (idx[o] == (uint8_t)(r * d.kw + s)) {
+          if (ACCUM) {
+            acc += dy[o];
+          } else {
+            acc = dy[o];
+            done = true;
+            break;
+          }
+        }
+      }
+    }
+    dx[t] = acc;
+  }
+}
+
+}  // namespace ttb
+
+using namespace ttb;
+
+extern "C" {
+
+int ttb_maxpool2d_fwd(const ttb_pool_desc* d, const float* x, float* y, uint8_t* idx, void* stream) {
+  TTB_REQUIRE(d != nullptr, "maxpool2d_fwd: null descriptor");
+  TTB_REQUIRE(d->kh * d->kw <= 255, "maxpool2d_fwd: window of %dx%d does not fit the byte index", d->kh, d->kw);
+  int cvec = (d->c % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 4 : 1;
+  int64_t total = (int64_t)d->n * d->p * d->q * (d->c / cvec);
+  if (total <= 0) return 0;
+  int grid = elementwise_grid(total, 256);
+  maxpool_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, x, y, idx, total, cvec);
+  return check_launch("maxpool2d_fwd");
+}
+
+int ttb_maxpool2d_bwd(const ttb_pool_desc* d, const float* dy, const uint8_t* idx, float* dx, int accumulate,
+                      void* stream) {
+  TTB_REQUIRE(d != nullptr, "maxpool2d_bwd: null descriptor");
+  int64_t total = (int64_t)d->n * d->h * d->w * d->c;
+  if (total <= 0) return 0;
+  int grid = elementwise_grid(total, 256);
+  if (accumulate) maxpool_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(*d, dy, idx, dx, total);
+  else maxpool_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(*d, dy, idx, dx, total);
+  return check_launch("maxpool2d_bwd");
+}
+
+}  // extern "C"

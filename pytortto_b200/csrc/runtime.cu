@@ -1,0 +1,44 @@
+// Library-level entry points: error text, version, device properties.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ttb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace ttb
+
+extern "C" {
+
+const char* ttb_last_error(void) { return ttb::g_err; }
+
+int ttb_version(void) { return 1; }
+
+int ttb_device_sm_count(int* out) {
+  if (!out) return 2;
+  *out = ttb::sm_count();
+  return 0;
+}
+
+}  // extern "C"
