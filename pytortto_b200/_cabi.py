@@ -1,0 +1,94 @@
+"""ctypes binding of libtortto_b200.so (the C ABI declared in include/tortto_b200.h).
+
+The library is built in-tree by `python -m pytortto_b200.build`.  There is NO fallback: if the shared object is
+missing, or a call returns non-zero, a RuntimeError is raised (the product path never routes through the CPU
+oracle or through library kernels).
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtortto_b200.so")
+
+TTB_MATH_FP32, TTB_MATH_TF32, TTB_MATH_BF16 = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    """struct ttb_conv_desc"""
+    _fields_ = [(n, c_int32) for n in ("n", "c", "h", "w", "k", "r", "s", "stride_h", "stride_w", "pad_h", "pad_w",
+                                       "dil_h", "dil_w", "groups", "p", "q", "math_mode")]
+
+
+class PoolDesc(ctypes.Structure):
+    """struct ttb_pool_desc"""
+    _fields_ = [(n, c_int32) for n in ("n", "c", "h", "w", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w",
+                                       "dil_h", "dil_w", "p", "q")]
+
+
+_F = c_void_p  # device pointers travel as plain integers
+_PROTOS = {
+    "ttb_last_error": (c_char_p, []),
+    "ttb_version": (c_int, []),
+    "ttb_device_sm_count": (c_int, [POINTER(c_int)]),
+    "ttb_conv2d_tensor_path_supported": (c_int, [POINTER(ConvDesc), c_int]),
+    "ttb_nchw_to_nhwc": (c_int, [_F, _F, c_int, c_int, c_int, c_int, c_void_p]),
+    "ttb_nhwc_to_nchw": (c_int, [_F, _F, c_int, c_int, c_int, c_int, c_void_p]),
+    "ttb_conv2d_workspace_size": (c_size_t, [POINTER(ConvDesc), c_int]),
+    "ttb_conv2d_fprop": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_conv2d_dgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_conv2d_wgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_bias_grad": (c_int, [_F, _F, c_int64, c_int, c_void_p]),
+    "ttb_bn_num_chunks": (c_int, [c_int64, c_int]),
+    "ttb_bn_stats": (c_int, [_F, c_int64, c_int, _F, c_int, c_void_p]),
+    "ttb_bn_reduce_partials": (c_int, [_F, c_int, c_int, _F, c_void_p]),
+    "ttb_bn_finalize": (c_int, [_F, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, c_int, c_void_p]),
+    "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
+    "ttb_bn_bwd_finalize": (c_int, [_F, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, c_void_p]),
+    "ttb_relu_fwd": (c_int, [_F, _F, c_int64, c_void_p]),
+    "ttb_relu_bwd": (c_int, [_F, _F, _F, c_int64, c_void_p]),
+    "ttb_add": (c_int, [_F, _F, _F, c_int64, c_void_p]),
+    "ttb_axpy": (c_int, [c_float, _F, _F, c_int64, c_void_p]),
+    "ttb_scale": (c_int, [c_float, _F, c_int64, c_void_p]),
+    "ttb_fill": (c_int, [c_float, _F, c_int64, c_void_p]),
+    "ttb_sgd_step": (c_int, [_F, _F, _F, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, c_void_p]),
+    "ttb_maxpool2d_fwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_void_p]),
+    "ttb_maxpool2d_bwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+launch_count = 0  # kernels-launching C-ABI calls made so far (bench.py reports the per-step delta)
+
+
+def load():
+    """dlopen the library (no CUDA context is created by loading)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m pytortto_b200.build` "
+                               "(there is no CPU / library fallback for the CUDA path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().ttb_last_error().decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise on a non-zero status."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    launch_count += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (status {rc}): {last_error()}")

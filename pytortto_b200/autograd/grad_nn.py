@@ -1,0 +1,261 @@
+"""The hot path: Convolution, TransposedConvolution, BatchNorm, Relu, MaxPool2DWithIndices as autograd Functions
+that call the sm_100a kernels through the C ABI.
+
+Each class keeps the reference's name, `forward(ctx, *inputs, **params)` / `backward(ctx, *grad_outputs)`
+signature, parameter names, saved state and error messages (/root/reference/src/tortto/autograd/grad_nn.py,
+lines cited per class), so `nn.functional` and the modules above it are unchanged callers.  What differs is below
+the boundary: no `x_padded` copy is kept for wgrad (the TMA im2col load zero-fills the halo), dgrad is a gather
+(no zero-inserted `grad_dilated`), BN is two fused passes per direction.
+"""
+import math
+
+from .. import ops
+from ..xparray import cparray
+from .function import Function
+from .helper import build_links, inplace_precheck, inplace_update
+
+prod = math.prod
+
+
+def _require_cuda(name, *arrays):
+    for a in arrays:
+        if a is not None and a.__class__ is not cparray:
+            raise RuntimeError(f"{name}: pytortto_b200 implements the CUDA path only (got a host array); "
+                               f"move tensors and modules with .cuda()")
+
+
+class Relu(Function):
+    """reference grad_nn.py:33-69: y = maximum(x, 0) (NaN-propagating); saves the OUTPUT; dx = dy * (y > 0)."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, = inputs
+        xd0 = xt0.data
+        _require_cuda('relu', xd0)
+        if params['inplace']:
+            inplace_precheck(xt0)
+            ops.relu_fwd(xd0, inplace=True)
+            yt0 = inplace_update(xt0, ctx)
+        else:
+            yt0 = build_links(ops.relu_fwd(xd0), grad_fn=ctx)
+        ctx.save_for_backward(yt0)
+        return yt0
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, = grad_outputs
+        yd0, = ctx.saved_tensors
+        return ops.relu_bwd(gd0, yd0)
+
+
+class Convolution(Function):
+    """reference grad_nn.py:684-734.  inputs = (input, weight, bias|None); params stride/padding/dilation/groups."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, xt1, xt2 = inputs
+        xd0, xd1 = xt0.data, xt1.data
+        xd2 = None if xt2 is None else xt2.data
+        stride = tuple(params['stride'])
+        padding = tuple(params['padding'])
+        dilation = tuple(params['dilation'])
+        groups = params['groups']
+        if xd0.__class__ is not xd1.__class__:
+            raise RuntimeError(f'Input type ({xd0.__class__.__name__}) and weight type ({xd1.__class__.__name__}) '
+                               f'should be the same')
+        if xd2 is not None and xd0.__class__ is not xd2.__class__:
+            raise RuntimeError(f'Input type ({xd0.__class__.__name__}) and bias type ({xd2.__class__.__name__}) '
+                               f'should be the same')
+        if xd0.ndim != 4:
+            raise RuntimeError(f'Expected 3D (unbatched) or 4D (batched) input to conv2d, '
+                               f'but got input of size: {xd0.shape}')
+        if groups * xd1.shape[-3] != xd0.shape[-3]:
+            raise RuntimeError(f'Given groups={groups}, weight of size {xd1.shape}, '
+                               f'expected input{xd0.shape} to have {groups * xd1.shape[-3]} channels, '
+                               f'but got {xd0.shape[-3]} channels instead')
+        _require_cuda('conv2d', xd0)
+        d = ops.conv_desc(xd0.shape, xd1.shape, stride, padding, dilation, groups)
+        yd0 = ops.conv2d_fprop(xd0, xd1, xd2, d)
+        yt0 = build_links(yd0, grad_fn=ctx)
+        ctx.save_for_backward(xt0, xt1)
+        ctx.params['desc'] = d
+        return yt0
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, = grad_outputs
+        xd0, xd1 = ctx.saved_tensors
+        d = ctx.params['desc']
+        grad0, grad1, grad2 = None, None, None
+        if ctx.needs_input_grad[2]:
+            grad2 = ops.bias_grad(gd0)
+        if ctx.needs_input_grad[1]:
+            grad1 = ops.conv2d_wgrad(xd0, gd0, d)
+        if ctx.needs_input_grad[0]:
+            grad0 = ops.conv2d_dgrad(gd0, xd1, d)
+        return grad0, grad1, grad2
+
+
+class TransposedConvolution(Function):
+    """reference grad_nn.py:737-779: forward IS the dgrad of a convolution whose 'output' is this op's input
+    (:755); backward: wgrad with roles swapped (:776), input gradient = plain convolution of dy (:778).
+    weight is (Cin, Cout/groups, kh, kw)."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, xt1, xt2 = inputs
+        xd0, xd1 = xt0.data, xt1.data
+        stride = tuple(params['stride'])
+        padding = tuple(params['padding'])
+        dilation = tuple(params['dilation'])
+        groups = params['groups']
+        output_padding = params['output_padding']
+        if xd0.ndim != 4:
+            raise RuntimeError(f'Expected 3D (unbatched) or 4D (batched) input to conv_transpose2d, '
+                               f'but got input of size: {xd0.shape}')
+        if xd1.shape[-4] != xd0.shape[-3]:
+            raise RuntimeError(f'Given transposed=1, weight of size {xd1.shape}, '
+                               f'expected input {xd0.shape} to have {xd1.shape[-4]} channels, '
+                               f'but got {xd0.shape[-3]} channels instead')
+        _require_cuda('conv_transpose2d', xd0, xd1)
+        op = tuple(output_padding) if hasattr(output_padding, '__len__') else (output_padding,)
+        hop = op[0]
+        wop = hop if len(op) == 1 else op[1]  # grad_nn.py:675-676
+        n, cin, hi, wi = xd0.shape
+        _, cog, kh, kw = xd1.shape
+        ho = (hi - 1) * stride[0] - 2 * padding[0] + dilation[0] * (kh - 1) + hop + 1
+        wo = (wi - 1) * stride[1] - 2 * padding[1] + dilation[1] * (kw - 1) + wop + 1
+        # the underlying convolution maps (n, cog*groups, ho, wo) -> (n, cin, hi, wi)
+        d = ops.conv_desc((n, cog * groups, ho, wo), xd1.shape, stride, padding, dilation, groups, out_hw=(hi, wi))
+        yd0 = ops.conv2d_dgrad(xd0, xd1, d)
+        if xt2 is not None:
+            ops.add_bias_(yd0, xt2.data)
+        yt0 = build_links(yd0, grad_fn=ctx)
+        ctx.save_for_backward(xt0, xt1)
+        ctx.params['desc'] = d
+        return yt0
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, = grad_outputs
+        xd0, xd1 = ctx.saved_tensors
+        d = ctx.params['desc']
+        grad0, grad1, grad2 = None, None, None
+        if ctx.needs_input_grad[2]:
+            grad2 = ops.bias_grad(gd0)
+        if ctx.needs_input_grad[1]:
+            grad1 = ops.conv2d_wgrad(gd0, xd0, d)
+        if ctx.needs_input_grad[0]:
+            grad0 = ops.conv2d_fprop(gd0, xd1, None, d)
+        return grad0, grad1, grad2
+
+
+class MaxPool2DWithIndices(Function):
+    """reference grad_nn.py:828-864.  The saved 'pos' is a byte index (r*kw+s) per output element instead of the
+    reference's six broadcast index arrays; backward keeps the reference's last-writer-wins overlap semantics."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, = inputs
+        xd0 = xt0.data
+        kernel_size = tuple(params['kernel_size'])
+        stride = tuple(params['stride'])
+        padding = tuple(params['padding'])
+        dilation = tuple(params['dilation'])
+        ceil_mode = params['ceil_mode']
+        return_indices = params['return_indices']
+        if padding[0] * 2 > kernel_size[0] or padding[1] * 2 > kernel_size[1]:
+            raise RuntimeError(f'pad should be smaller than or equal to half of kernel size, '
+                               f'but got padW = {padding[1]}, padH = {padding[0]}, kW = {kernel_size[1]}, '
+                               f'kH = {kernel_size[0]}')
+        if xd0.ndim != 3 and xd0.ndim != 4:
+            raise RuntimeError('non-empty 3D or 4D (batch mode) tensor expected for input')
+        _require_cuda('max_pool2d', xd0)
+        low_dim = xd0.ndim == 3
+        if low_dim:
+            xd0 = xd0.reshape((1,) + tuple(xd0.shape))
+        d = ops.pool_desc(xd0.shape, kernel_size, stride, padding, dilation, ceil_mode)
+        yd0, pos = ops.maxpool2d_fwd(xd0, d)
+        if low_dim:
+            yd0 = yd0.reshape(tuple(yd0.shape)[1:])
+        yt0 = build_links(yd0, grad_fn=ctx)
+        ctx.save_for_backward(xt0)
+        ctx.params['pos'] = pos
+        ctx.params['desc'] = d
+        ctx.params['low_dim'] = low_dim
+        return (yt0, pos) if return_indices else yt0
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, *_ = grad_outputs
+        d = ctx.params['desc']
+        if ctx.params['low_dim']:
+            gd0 = gd0.reshape((1,) + tuple(gd0.shape))
+        grad0 = ops.maxpool2d_bwd(gd0, ctx.params['pos'], d, accumulate=_POOL_ACCUMULATE[0])
+        if ctx.params['low_dim']:
+            grad0 = grad0.reshape(tuple(grad0.shape)[1:])
+        return grad0
+
+
+_POOL_ACCUMULATE = [False]  # reference semantics by default; set_maxpool_backward_accumulate(True) = PyTorch's
+
+
+def set_maxpool_backward_accumulate(flag):
+    _POOL_ACCUMULATE[0] = bool(flag)
+
+
+def _verify_batch_size(size):
+    size_prods = size[0]
+    for i in range(len(size) - 2):
+        size_prods *= size[i + 2]
+    if size_prods == 1:
+        raise ValueError(f'Expected more than 1 value per channel when training, got input size {size}')
+
+
+class BatchNorm(Function):
+    """reference grad_nn.py:907-989.  inputs = (input, weight|None, bias|None); params running_mean, running_var
+    (Tensors or None), training, momentum, eps.  Training: batch mean / BIASED variance normalise, running stats get
+    the UNBIASED variance (:923-930).  Saves input + weight and keeps mean, var+eps, sd for backward (:962-963);
+    backward always uses those saved statistics, also in eval mode (:967-989).
+
+    Under `pytortto_b200.distributed` with sync_bn the per-channel sums are all-reduced (forward: sum x, sum x^2;
+    backward: sum dy, sum dy*(x-mean)), which makes a k-GPU run equal the single-process global batch."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, xt1, xt2 = inputs
+        xd0 = xt0.data
+        running_mean = ctx.params['running_mean']
+        running_var = ctx.params['running_var']
+        training = ctx.params['training']
+        momentum = ctx.params['momentum']
+        eps = ctx.params['eps']
+        _require_cuda('batch_norm', xd0)
+        gamma = None if xt1 is None else xt1.data
+        beta = None if xt2 is None else xt2.data
+        from .. import distributed as dist
+        hook = dist.bn_forward_hook() if training else None
+        if training:
+            _verify_batch_size(xd0.shape)
+            track = running_mean is not None and running_var is not None
+            yd0, stats, count = ops.bn_forward_train(xd0, gamma, beta, running_mean.data if track else None,
+                                                     running_var.data if track else None, momentum, eps,
+                                                     reduce_hook=hook)
+        elif running_mean is not None and running_var is not None:
+            yd0, stats, count = ops.bn_forward_eval(xd0, gamma, beta, running_mean.data, running_var.data, eps)
+        else:
+            yd0, stats, count = ops.bn_forward_train(xd0, gamma, beta, None, None, None, eps)
+        yt0 = build_links(yd0, grad_fn=ctx)
+        ctx.save_for_backward(xt0, xt1)
+        ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None}
+        return yt0
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, = grad_outputs
+        xd0, xd1 = ctx.saved_tensors
+        from .. import distributed as dist
+        hook = dist.bn_backward_hook() if ctx.params['synced'] else None
+        return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'],
+                               need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
+                               need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook)

