@@ -92,10 +92,11 @@ int ttb_bn_num_chunks(int64_t m, int c);
 int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chunks, void* stream);
 /* sums[2][C] = sum over chunks (double).  This is the buffer a data-parallel run all-reduces (SyncBN). */
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream);
-/* from sums[2][C] over `count` elements per channel: mean, var_eps = biased var + eps, sd = sqrt(var_eps)
+/* from sums[num_chunks][2][C] (per-chunk partials, summed here in fixed order; num_chunks = 1 for an already reduced /
+ * all-reduced buffer) over `count` elements per channel: mean, var_eps = biased var + eps, sd = sqrt(var_eps)
  * (what BatchNorm.forward saves, grad_nn.py:962-963), scale = gamma/sd, shift = beta - mean*scale, and, if
  * running_mean/var != NULL, running = (1-momentum)*running + momentum*{mean, var*count/(count-1)} (:925-930). */
-int ttb_bn_finalize(const double* sums, int64_t count, int c, float eps, float momentum,
+int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, float eps, float momentum,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
                     float* mean, float* var_eps, float* sd, float* scale, float* shift, void* stream);
 /* eval mode / precomputed statistics: fills var_eps, sd, scale, shift from given mean & var */
@@ -109,9 +110,9 @@ int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale,
  * (fused ReLU backward, grad_nn.py:64-69). */
 int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, int64_t m, int c,
                       double* partials, int num_chunks, void* stream);
-/* from sums[2][C]: dgamma = sum(dy*(x-mean))/sd, dbeta = sum(dy), and the three per-channel coefficients of
- * dx = c1*(dy - c2 - (x-mean)*c3)  (grad_nn.py:984-988 re-associated) */
-int ttb_bn_bwd_finalize(const double* sums, int64_t count, int c, const float* gamma, const float* var_eps,
+/* from sums[num_chunks][2][C]: dgamma = sum(dy*(x-mean))/sd, dbeta = sum(dy), and the three per-channel
+ * coefficients of dx = c1*(dy - c2 - (x-mean)*c3)  (grad_nn.py:984-988 re-associated) */
+int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef /*[3][C]*/, void* stream);
 int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
                      float* dx, int64_t m, int c, void* stream);
@@ -127,6 +128,12 @@ int ttb_fill(float value, float* x, int64_t n, void* stream);
  * is initialised to d_p (buf = d_p) instead of buf = momentum*buf + (1-dampening)*d_p */
 int ttb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                  float dampening, float weight_decay, int nesterov, int first_step, void* stream);
+
+/* the same update for `n_tensors` parameter tensors in as few launches as possible (HOST arrays of device pointers,
+ * sizes in elements, per-tensor first_step flags; bufs may be NULL when momentum == 0) */
+int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* bufs,
+                       const int64_t* sizes, const unsigned char* first_step, float lr, float momentum, float dampening,
+                       float weight_decay, int nesterov, void* stream);
 
 /* ---- max pool --------------------------------------------------------------------------------------------- */
 /* y[N,P,Q,C] = max over window (padding acts as -inf); idx[N,P,Q,C] (uint8) = r*kw+s of the FIRST maximum in

@@ -42,11 +42,11 @@ _PROTOS = {
     "ttb_bn_num_chunks": (c_int, [c_int64, c_int]),
     "ttb_bn_stats": (c_int, [_F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_reduce_partials": (c_int, [_F, c_int, c_int, _F, c_void_p]),
-    "ttb_bn_finalize": (c_int, [_F, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_finalize": (c_int, [_F, c_int, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, c_int, c_void_p]),
     "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
-    "ttb_bn_bwd_finalize": (c_int, [_F, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_bwd_finalize": (c_int, [_F, c_int, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, c_void_p]),
     "ttb_relu_fwd": (c_int, [_F, _F, c_int64, c_void_p]),
     "ttb_relu_bwd": (c_int, [_F, _F, _F, c_int64, c_void_p]),
@@ -55,6 +55,8 @@ _PROTOS = {
     "ttb_scale": (c_int, [c_float, _F, c_int64, c_void_p]),
     "ttb_fill": (c_int, [c_float, _F, c_int64, c_void_p]),
     "ttb_sgd_step": (c_int, [_F, _F, _F, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, c_void_p]),
+    "ttb_sgd_step_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
+                                   c_float, c_int, c_void_p]),
     "ttb_maxpool2d_fwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_void_p]),
     "ttb_maxpool2d_bwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_int, c_void_p]),
 }

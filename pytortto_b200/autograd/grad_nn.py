@@ -212,18 +212,12 @@ def _verify_batch_size(size):
         raise ValueError(f'Expected more than 1 value per channel when training, got input size {size}')
 
 
-class BatchNorm(Function):
-    """reference grad_nn.py:907-989.  inputs = (input, weight|None, bias|None); params running_mean, running_var
-    (Tensors or None), training, momentum, eps.  Training: batch mean / BIASED variance normalise, running stats get
-    the UNBIASED variance (:923-930).  Saves input + weight and keeps mean, var+eps, sd for backward (:962-963);
-    backward always uses those saved statistics, also in eval mode (:967-989).
+class _BatchNormBase(Function):
+    """shared implementation of BatchNorm and the fused BatchNorm+ReLU node"""
+    _fuse_relu = False
 
-    Under `pytortto_b200.distributed` with sync_bn the per-channel sums are all-reduced (forward: sum x, sum x^2;
-    backward: sum dy, sum dy*(x-mean)), which makes a k-GPU run equal the single-process global batch."""
-
-    @staticmethod
-    def forward(ctx, *inputs, **params):
-        xt0, xt1, xt2 = inputs
+    @classmethod
+    def _forward(cls, ctx, xt0, xt1, xt2):
         xd0 = xt0.data
         running_mean = ctx.params['running_mean']
         running_var = ctx.params['running_var']
@@ -235,27 +229,66 @@ class BatchNorm(Function):
         beta = None if xt2 is None else xt2.data
         from .. import distributed as dist
         hook = dist.bn_forward_hook() if training else None
+        relu = cls._fuse_relu
         if training:
             _verify_batch_size(xd0.shape)
             track = running_mean is not None and running_var is not None
             yd0, stats, count = ops.bn_forward_train(xd0, gamma, beta, running_mean.data if track else None,
-                                                     running_var.data if track else None, momentum, eps,
+                                                     running_var.data if track else None, momentum, eps, relu=relu,
                                                      reduce_hook=hook)
         elif running_mean is not None and running_var is not None:
-            yd0, stats, count = ops.bn_forward_eval(xd0, gamma, beta, running_mean.data, running_var.data, eps)
+            yd0, stats, count = ops.bn_forward_eval(xd0, gamma, beta, running_mean.data, running_var.data, eps, relu=relu)
         else:
-            yd0, stats, count = ops.bn_forward_train(xd0, gamma, beta, None, None, None, eps)
+            yd0, stats, count = ops.bn_forward_train(xd0, gamma, beta, None, None, None, eps, relu=relu)
         yt0 = build_links(yd0, grad_fn=ctx)
-        ctx.save_for_backward(xt0, xt1)
+        if relu:
+            ctx.save_for_backward(xt0, xt1, yt0)
+        else:
+            ctx.save_for_backward(xt0, xt1)
         ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None}
         return yt0
 
-    @staticmethod
-    def backward(ctx, *grad_outputs):
-        gd0, = grad_outputs
-        xd0, xd1 = ctx.saved_tensors
+    @classmethod
+    def _backward(cls, ctx, gd0):
+        saved = ctx.saved_tensors
+        xd0, xd1 = saved[0], saved[1]
+        relu_out = saved[2] if cls._fuse_relu else None
         from .. import distributed as dist
         hook = dist.bn_backward_hook() if ctx.params['synced'] else None
-        return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'],
+        return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'], relu_out=relu_out,
                                need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
                                need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook)
+
+
+class BatchNormRelu(_BatchNormBase):
+    """BatchNorm immediately followed by ReLU as ONE node (what `nn.Sequential(BatchNorm2d, ReLU)` lowers to):
+    forward writes max(bn(x), 0) in the normalise pass; backward masks dy with (y > 0) inside the two BN backward
+    kernels (Relu.backward, reference grad_nn.py:64-69, folded in).  Saves 1 read + 1 write forward and 2 reads +
+    1 write backward per element against separate nodes; numerically identical to BatchNorm -> Relu."""
+    _fuse_relu = True
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        return BatchNormRelu._forward(ctx, *inputs)
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        return BatchNormRelu._backward(ctx, grad_outputs[0])
+
+
+class BatchNorm(_BatchNormBase):
+    """reference grad_nn.py:907-989.  inputs = (input, weight|None, bias|None); params running_mean, running_var
+    (Tensors or None), training, momentum, eps.  Training: batch mean / BIASED variance normalise, running stats get
+    the UNBIASED variance (:923-930).  Saves input + weight and keeps mean, var+eps, sd for backward (:962-963);
+    backward always uses those saved statistics, also in eval mode (:967-989).
+
+    Under `pytortto_b200.distributed` with sync_bn the per-channel sums are all-reduced (forward: sum x, sum x^2;
+    backward: sum dy, sum dy*(x-mean)), which makes a k-GPU run equal the single-process global batch."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        return BatchNorm._forward(ctx, *inputs)
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        return BatchNorm._backward(ctx, grad_outputs[0])

@@ -35,7 +35,7 @@ static ColGeom col_geom(int64_t m, int c) {
   int64_t rows_per_chunk = (int64_t)g.ty * kRowsPerThread;
   int64_t chunks = ceil_div(m, rows_per_chunk);
   // keep the partial buffer and the finalize loop small: at most ~8 CTAs per SM worth of chunks
-  int64_t cap = (int64_t)sm_count() * 8 / g.qblocks;
+  int64_t cap = (int64_t)sm_count() * 4 / g.qblocks;
   if (cap < 1) cap = 1;
   if (chunks > cap) {
     chunks = cap;
@@ -128,23 +128,42 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
   }
 }
 
-__global__ void reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int c2,
-                                       double* __restrict__ sums) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c2) return;
+// Sum of the per-chunk partials of one value: blockDim = (32 values, 8 chunk lanes); fixed order => deterministic.
+// Returns the total in threads with threadIdx.y == 0.
+__device__ __forceinline__ double chunk_sum(const double* __restrict__ partials, int num_chunks, int stride, int idx,
+                                            bool valid, double (*sm)[33]) {
   double s = 0.0;
-  for (int k = 0; k < num_chunks; ++k) s += partials[(int64_t)k * c2 + i];
-  sums[i] = s;
+  if (valid)
+    for (int k = threadIdx.y; k < num_chunks; k += 8) s += partials[(int64_t)k * stride + idx];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.y == 0)
+    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+  __syncthreads();
+  return t;
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int c, float eps, float momentum,
-                                   float one_minus_momentum, float unbias, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean, float* running_var,
-                                   float* mean, float* var_eps, float* sd, float* scale, float* shift) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  double mu = sums[i] / count;
-  double var = sums[c + i] / count - mu * mu;  // biased variance, grad_nn.py:924
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int c2, double* __restrict__ sums) {
+  __shared__ double sm[8][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  double t = chunk_sum(partials, num_chunks, c2, i, i < c2, sm);
+  if (threadIdx.y == 0 && i < c2) sums[i] = t;
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c, float eps, float momentum,
+                   float one_minus_momentum, float unbias, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                   float* mean, float* var_eps, float* sd, float* scale, float* shift) {
+  __shared__ double sm[8][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  double s0 = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
+  double s1 = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
+  if (threadIdx.y != 0 || i >= c) return;
+  double mu = s0 / count;
+  double var = s1 / count - mu * mu;  // biased variance, grad_nn.py:924
   if (var < 0.0) var = 0.0;
   float muf = (float)mu, varf = (float)var;
   if (running_mean) running_mean[i] = __fadd_rn(__fmul_rn(one_minus_momentum, running_mean[i]), __fmul_rn(momentum, muf));
@@ -175,12 +194,15 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const 
   shift[i] = (beta ? beta[i] : 0.f) - mu * sc;
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, int c,
-                                       const float* __restrict__ gamma, const float* __restrict__ var_eps,
-                                       const float* __restrict__ sd, float* dgamma, float* dbeta, float* coef) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  double sdy = sums[i], sdyx = sums[c + i];
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c,
+                       const float* __restrict__ gamma, const float* __restrict__ var_eps,
+                       const float* __restrict__ sd, float* dgamma, float* dbeta, float* coef) {
+  __shared__ double sm[8][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  double sdy = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
+  double sdyx = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
+  if (threadIdx.y != 0 || i >= c) return;
   if (dbeta) dbeta[i] = (float)sdy;
   if (dgamma) dgamma[i] = (float)(sdyx / (double)sd[i]);
   float g = gamma ? gamma[i] : 1.f;
@@ -295,11 +317,11 @@ int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chu
 
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
   if (c2 <= 0) return 0;
-  reduce_partials_kernel<<<(c2 + 127) / 128, 128, 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
+  reduce_partials_kernel<<<(c2 + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
   return check_launch("bn_reduce_partials");
 }
 
-int ttb_bn_finalize(const double* sums, int64_t count, int c, float eps, float momentum, const float* gamma,
+int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, float eps, float momentum, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float* mean, float* var_eps,
                     float* sd, float* scale, float* shift, void* stream) {
   if (c <= 0) return 0;
@@ -308,9 +330,10 @@ int ttb_bn_finalize(const double* sums, int64_t count, int c, float eps, float m
   // (grad_nn.py:927-930), then applied to float32 arrays.
   float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
   float omm = (float)(1.0 - (double)momentum);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, (double)count, c, eps, momentum, omm, unbias,
-                                                                     gamma, beta, running_mean, running_var, mean,
-                                                                     var_eps, sd, scale, shift);
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count, c,
+                                                                           eps, momentum, omm, unbias, gamma, beta,
+                                                                           running_mean, running_var, mean, var_eps, sd,
+                                                                           scale, shift);
   return check_launch("bn_finalize");
 }
 
@@ -345,11 +368,11 @@ int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const 
   return launch_col_reduce<1>(dy, x, mean, relu_out, m, c, partials, num_chunks, as_stream(stream), "bn_bwd_reduce");
 }
 
-int ttb_bn_bwd_finalize(const double* sums, int64_t count, int c, const float* gamma, const float* var_eps,
+int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef, void* stream) {
   if (c <= 0) return 0;
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, (double)count, c, gamma, var_eps, sd,
-                                                                         dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count,
+                                                                               c, gamma, var_eps, sd, dgamma, dbeta, coef);
   return check_launch("bn_bwd_finalize");
 }
 

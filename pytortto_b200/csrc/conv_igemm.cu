@@ -16,6 +16,7 @@
 // warps 2-5 epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128 B row-segment stores).
 // A ring of NSTAGES {A,B} stages is handed over with full/empty mbarriers; tcgen05.commit releases stages.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -61,13 +62,14 @@ static int load_driver_fns() {
 }
 
 // 2-D row-major fp32 matrix [rows][cols] -> tiled map with box [box_rows][32 floats], 128B swizzle, zero OOB fill
-static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * sizeof(float)};
   cuuint32_t box[2] = {kKBlock, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r, (unsigned long long)rows,
@@ -80,14 +82,15 @@ static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint
 // NHWC fp32 activation [n][h][w][c] -> im2col map: `pixels` base pixels x 32 channels per load, traversal strides
 // (tw, th), bounding-box corners in W/H order, 128B swizzle, zero fill outside the image.
 static int make_im2col_4d(CUtensorMap* tm, const float* base, int n, int h, int w, int c, int lower_w, int lower_h,
-                          int upper_w, int upper_h, int tw, int th, uint32_t pixels) {
+                          int upper_w, int upper_h, int tw, int th, uint32_t pixels,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)tw, (cuuint32_t)th, 1};
   CUresult r = g_encodeIm2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, lower, upper,
-                              kKBlock, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              kKBlock, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d) nhwc=%d,%d,%d,%d lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)", (int)r, n,
@@ -134,6 +137,7 @@ struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B =
   int steps_per_split;
   int p_dim, q_dim;        // output pixel grid (for decomposing the pixel index of a step)
   int base_w, base_h, trav_w, trav_h;
+  uint32_t desc_lbo, desc_sbo, desc_layout;  // UMMA smem-descriptor fields for the MN-major operands
   uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
 };
 
@@ -379,8 +383,10 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         const uint32_t sb = sa + kABytes;
 #pragma unroll
         for (int k = 0; k < KP / 8; ++k) {  // 8 pixels (= one 8-row swizzle atom of every slab) per MMA
-          uint64_t da = ptx::umma_desc_sw128(sa + k * 1024, kSlabBytes, 1024);
-          uint64_t db = ptx::umma_desc_sw128(sb + k * 1024, kSlabBytes, 1024);
+          // MN-major fp32 operands must use the 128B-span / 32B-atom swizzle: 4-row K groups (512 B apart),
+          // 32-channel slabs kSlabBytes apart
+          uint64_t da = ptx::umma_desc(sa + k * 1024, P.desc_lbo, P.desc_sbo, P.desc_layout);
+          uint64_t db = ptx::umma_desc(sb + k * 1024, P.desc_lbo, P.desc_sbo, P.desc_layout);
           ptx::mma_tf32(tmem_base, da, db, idesc, (s | k) != 0);
         }
         ptx::mma_commit(&empty_bar[stage]);
@@ -506,9 +512,18 @@ static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_p
   const int64_t m = (int64_t)d->n * d->p * d->q;
   const int total = (int)ceil_div(m, KP);
   const int64_t tiles = ceil_div(d->k, kTileM) * ceil_div(ncols, *bn);
-  int64_t sp = ceil_div(2 * (int64_t)sm_count(), tiles);
-  if (sp > total / 8) sp = total / 8;  // at least 8 pipeline steps per CTA
-  if (sp < 1) sp = 1;
+  // one CTA per SM is resident (the stage ring takes most of the shared memory), so size the grid to whole waves:
+  // the largest split count with tiles*splits <= waves*SMs, for the smallest wave count that gives >= 8 steps per CTA
+  const int64_t sms = sm_count();
+  int64_t sp = 1;
+  for (int waves = 1; waves <= 2; ++waves) {
+    int64_t cand = (waves * sms) / tiles;
+    if (cand < 1) cand = 1;
+    if (cand > total / 8) cand = total / 8;
+    if (cand < 1) cand = 1;
+    sp = cand;
+    if (tiles * cand >= (waves * sms * 3) / 4 || tiles > sms) break;  // this wave count is filled well enough
+  }
   if (sp > 512) sp = 512;
   int sps = (int)ceil_div(total, sp);
   sp = ceil_div(total, sps);
@@ -680,10 +695,20 @@ int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* 
   WgradParams P;
   memset(&P, 0, sizeof(P));
   const int64_t m = (int64_t)d->n * d->p * d->q;
+  // MN-major fp32 operands: 128B-span / 32B-atom swizzle (TMA) <-> UMMA layout type 1, 4-row K groups 512 B apart,
+  // 32-channel slabs KP*128 B apart.  (TTB_WGRAD_* env overrides exist for bring-up experiments only.)
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  P.desc_lbo = (uint32_t)KP * 128;
+  P.desc_sbo = 512;
+  P.desc_layout = 1;
+  if (const char* e = getenv("TTB_WGRAD_SWIZZLE")) swz = (CUtensorMapSwizzle)atoi(e);
+  if (const char* e = getenv("TTB_WGRAD_LBO")) P.desc_lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("TTB_WGRAD_SBO")) P.desc_sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("TTB_WGRAD_LAYOUT")) P.desc_layout = (uint32_t)atoi(e);
   // dY as a [pixels][K] matrix; box = KP pixel rows x 32 channels
-  if (make_tiled_2d(&P.tmDy, dy, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP)) return 1;
+  if (make_tiled_2d(&P.tmDy, dy, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
   const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
-  if (make_im2col_4d(&P.tmX, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP))
+  if (make_im2col_4d(&P.tmX, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP, swz))
     return 1;
   const int ncols = d->r * d->s * d->c;
   P.o.out = splits > 1 ? reinterpret_cast<float*>(ws) : dw;

@@ -77,11 +77,118 @@ static int transpose_batched(const float* src, float* dst, int batch, int rows, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// multi-tensor SGD: one launch updates up to kMultiMax parameter tensors (pointer table passed by value)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMultiMax = 48;
+constexpr int kMultiChunk = 2048;  // elements per CTA (256 threads x 2 float4)
+
+struct SgdMulti {
+  float* p[kMultiMax];
+  const float* g[kMultiMax];
+  float* b[kMultiMax];
+  int64_t n[kMultiMax];
+  int block_start[kMultiMax + 1];
+  unsigned char first[kMultiMax];
+  int count;
+  float lr, momentum, dampening, weight_decay;
+  int nesterov;
+};
+
+__device__ __forceinline__ void sgd_elem(float& p, float g, float& b, bool has_buf, bool first, float lr, float mom,
+                                         float damp, float wd, int nesterov) {
+  float d = g;
+  if (wd != 0.f) d = __fadd_rn(d, __fmul_rn(p, wd));
+  if (mom != 0.f) {
+    b = first ? d : __fadd_rn(__fmul_rn(b, mom), __fmul_rn(d, 1.f - damp));
+    d = nesterov ? __fadd_rn(d, __fmul_rn(b, mom)) : b;
+  }
+  p = __fadd_rn(p, __fmul_rn(d, -lr));
+  (void)has_buf;
+}
+
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ SgdMulti A) {
+  // locate the tensor this CTA works on
+  int t = 0;
+  while (t + 1 < A.count && (int)blockIdx.x >= A.block_start[t + 1]) ++t;
+  const int64_t base = (int64_t)(blockIdx.x - A.block_start[t]) * kMultiChunk;
+  const int64_t n = A.n[t];
+  float* __restrict__ p = A.p[t];
+  const float* __restrict__ g = A.g[t];
+  float* __restrict__ b = A.b[t];
+  const bool first = A.first[t] != 0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < kMultiChunk / (256 * 4); ++it) {
+      int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
+      if (i + 3 < n) {
+        float4 pv = ld_f4(p + i), gv = ld_f4(g + i);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b && !first) bv = ld_f4(b + i);
+        sgd_elem(pv.x, gv.x, bv.x, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+        sgd_elem(pv.y, gv.y, bv.y, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+        sgd_elem(pv.z, gv.z, bv.z, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+        sgd_elem(pv.w, gv.w, bv.w, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+        if (b) st_f4(b + i, bv);
+        st_f4(p + i, pv);
+      } else {
+        for (int64_t j = i; j < n && j < i + 4; ++j) {
+          float pv = p[j], bv = (b && !first) ? b[j] : 0.f;
+          sgd_elem(pv, g[j], bv, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+          if (b) b[j] = bv;
+          p[j] = pv;
+        }
+      }
+    }
+  } else {
+    for (int64_t j = base + threadIdx.x; j < n && j < base + kMultiChunk; j += 256) {
+      float pv = p[j], bv = (b && !first) ? b[j] : 0.f;
+      sgd_elem(pv, g[j], bv, b != nullptr, first, A.lr, A.momentum, A.dampening, A.weight_decay, A.nesterov);
+      if (b) b[j] = bv;
+      p[j] = pv;
+    }
+  }
+}
+
 }  // namespace ttb
 
 using namespace ttb;
 
 extern "C" {
+
+int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* bufs,
+                       const int64_t* sizes, const unsigned char* first_step, float lr, float momentum, float dampening,
+                       float weight_decay, int nesterov, void* stream) {
+  TTB_REQUIRE(n_tensors >= 0 && params && grads && sizes, "sgd_step_multi: null table");
+  cudaStream_t st = as_stream(stream);
+  int done = 0;
+  while (done < n_tensors) {
+    SgdMulti A;
+    A.count = 0;
+    A.lr = lr; A.momentum = momentum; A.dampening = dampening; A.weight_decay = weight_decay; A.nesterov = nesterov;
+    int blocks = 0;
+    while (done < n_tensors && A.count < kMultiMax) {
+      if (sizes[done] > 0) {
+        TTB_REQUIRE(momentum == 0.f || (bufs && bufs[done]), "sgd_step_multi: momentum != 0 needs momentum buffers");
+        int i = A.count++;
+        A.p[i] = params[done];
+        A.g[i] = grads[done];
+        A.b[i] = bufs ? bufs[done] : nullptr;
+        A.n[i] = sizes[done];
+        A.first[i] = first_step ? first_step[done] : 0;
+        A.block_start[i] = blocks;
+        blocks += (int)ceil_div(sizes[done], kMultiChunk);
+      }
+      ++done;
+    }
+    if (A.count == 0) break;
+    A.block_start[A.count] = blocks;
+    sgd_multi_kernel<<<blocks, 256, 0, st>>>(A);
+    if (check_launch("sgd_step_multi")) return 1;
+  }
+  return 0;
+}
 
 int ttb_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, void* stream) {
   return transpose_batched(src, dst, n, c, h * w, as_stream(stream));

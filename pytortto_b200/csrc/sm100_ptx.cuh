@@ -130,6 +130,30 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// Same, layout type 1 (SWIZZLE_128B_BASE32B: 32-byte chunks swizzled within a 128-byte span, pattern period 4 rows).
+// This is the only swizzled layout tcgen05 accepts for MN-major 32-bit (tf32) operands; it matches TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = bytes between 128 B-wide MN slabs, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_sw128_atom32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// generic form (layout type: 0 none, 1 128B/32B-atom, 2 128B, 4 64B, 6 32B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7) << 61;
+  return d;
+}
+
 // Instruction descriptor: fp32 accumulate, A/B format (2 = tf32, 1 = bf16, 0 = f16), majors (0 = K, 1 = MN), M, N
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t a_mn_major, uint32_t b_mn_major, uint32_t m,
                                                   uint32_t n) {

@@ -1,7 +1,7 @@
 """`tortto.nn.functional` for the conv-net path - the entry points kept verbatim from the reference
 (/root/reference/src/tortto/nn/functional.py:6-11, 54-63, 80-121): same names, argument order, defaults."""
 from ..autograd.grad_fcn import (BinaryCrossEntropyWithLogits, LogSoftmax, NllLoss, View)
-from ..autograd.grad_nn import BatchNorm, Convolution, MaxPool2DWithIndices, Relu, TransposedConvolution
+from ..autograd.grad_nn import BatchNorm, BatchNormRelu, Convolution, MaxPool2DWithIndices, Relu, TransposedConvolution
 from ..VariableFunctions import matmul
 
 
@@ -48,6 +48,12 @@ def max_pool2d(input, kernel_size, stride=(1, 1), padding=(0, 0), dilation=(1, 1
 def batch_norm(input, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
     return BatchNorm.apply(input, weight, bias, running_mean=running_mean, running_var=running_var,
                            training=training, momentum=momentum, eps=eps)
+
+
+def batch_norm_relu(input, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
+    """relu(batch_norm(...)) as one fused node; `nn.Sequential` calls this for a BatchNorm module followed by ReLU."""
+    return BatchNormRelu.apply(input, weight, bias, running_mean=running_mean, running_var=running_var,
+                               training=training, momentum=momentum, eps=eps)
 
 
 def linear(input, weight, bias):

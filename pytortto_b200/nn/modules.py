@@ -299,9 +299,27 @@ class Sequential(Module):
         return Sequential(*vals[idx]) if isinstance(idx, slice) else vals[idx]
 
     def forward(self, x):
-        for m in self._modules.values():
-            x = m(x)
+        mods = list(self._modules.values())
+        i, n = 0, len(mods)
+        while i < n:
+            m = mods[i]
+            # peephole: BatchNorm immediately followed by ReLU inside one Sequential is a single fused node
+            # (same values, same gradients; the intermediate is not observable from outside the container)
+            if i + 1 < n and isinstance(m, _BatchNorm) and type(mods[i + 1]) is ReLU and _FUSE_BN_RELU[0]:
+                x = m(x, fuse_relu=True)
+                i += 2
+            else:
+                x = m(x)
+                i += 1
         return x
+
+
+_FUSE_BN_RELU = [True]
+
+
+def set_bn_relu_fusion(flag):
+    """Enable / disable the Sequential(BatchNorm, ReLU) -> fused node peephole (on by default)."""
+    _FUSE_BN_RELU[0] = bool(flag)
 
 
 class ModuleList(Module):
@@ -561,7 +579,7 @@ class _BatchNorm(Module):
         return (f'{self.num_features}, eps={self.eps}, momentum={self.momentum}, affine={self.affine}, '
                 f'track_running_stats={self.track_running_stats}')
 
-    def forward(self, inpt):
+    def forward(self, inpt, fuse_relu=False):
         self._check_input_dim(inpt)
         if self.training and self.track_running_stats:
             # host-side step counter: the reference bumps a float32 device scalar and reads it back with .item()
@@ -574,7 +592,8 @@ class _BatchNorm(Module):
         else:
             factor = None
         bn_training = True if self.training else (self.running_mean is None and self.running_var is None)
-        return F.batch_norm(inpt,
+        fn = F.batch_norm_relu if fuse_relu else F.batch_norm
+        return fn(inpt,
                             self.running_mean if not self.training or self.track_running_stats else None,
                             self.running_var if not self.training or self.track_running_stats else None,
                             self.weight, self.bias, bn_training, factor, self.eps)
@@ -593,4 +612,5 @@ class BatchNorm1d(_BatchNorm):
 
 
 __all__ = ['Module', 'Sequential', 'ModuleList', 'Identity', 'ReLU', 'LogSoftmax', 'NLLLoss', 'BCEWithLogitsLoss',
-           'Linear', 'Conv2d', 'ConvTranspose2d', 'MaxPool2d', 'BatchNorm2d', 'BatchNorm1d', 'Parameter']
+           'Linear', 'Conv2d', 'ConvTranspose2d', 'MaxPool2d', 'BatchNorm2d', 'BatchNorm1d', 'Parameter',
+           'set_bn_relu_fusion']

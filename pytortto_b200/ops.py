@@ -121,29 +121,30 @@ def _rows_channels(x):
 
 
 def bn_sums(x, reduce_hook=None):
-    """[2][C] double: per-channel sum(x), sum(x^2).  `reduce_hook(t)` may all-reduce the torch tensor in place."""
+    """per-channel sum(x), sum(x^2) as double partials [chunks][2][C] -> (buffer, chunks, count).  Without a hook
+    the per-chunk partials go straight to the finalize kernel (which sums them in fixed order); with a hook
+    (SyncBN) they are first collapsed to [2][C] and `reduce_hook(t, count)` all-reduces that tensor in place."""
     m, c = _rows_channels(x)
     chunks = _cabi.load().ttb_bn_num_chunks(m, c)
     partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
     st = current_stream_ptr()
     _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
-    if reduce_hook is None and chunks == 1:
-        return partials, m
+    if reduce_hook is None:
+        return partials, chunks, m
     sums = torch.empty((2, c), dtype=torch.float64, device=x.t.device)
     _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
-    if reduce_hook is not None:
-        m = reduce_hook(sums, m)
-    return sums, m
+    m = reduce_hook(sums, m)
+    return sums, 1, m
 
 
 def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, relu=False, reduce_hook=None):
     m, c = _rows_channels(x)
-    sums, count = bn_sums(x, reduce_hook)
+    sums, nchunks, count = bn_sums(x, reduce_hook)
     stats = new_f32((5, c))  # rows: mean, var+eps, sd, scale, shift
     base = stats.t.data_ptr()
     row = c * 4
     st = current_stream_ptr()
-    _cabi.call("ttb_bn_finalize", sums.data_ptr(), count, c, eps, 0.0 if momentum is None else momentum, _ptr(gamma),
+    _cabi.call("ttb_bn_finalize", sums.data_ptr(), nchunks, count, c, eps, 0.0 if momentum is None else momentum, _ptr(gamma),
                _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row, base + 3 * row,
                base + 4 * row, st)
     y = cparray(empty_device(x.shape))
@@ -174,17 +175,16 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     chunks = _cabi.load().ttb_bn_num_chunks(m, c)
     partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
     _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), m, c, partials.data_ptr(), chunks, st)
-    if chunks == 1 and reduce_hook is None:
-        sums = partials
+    if reduce_hook is None:
+        sums, nchunks = partials, chunks
     else:
-        sums = torch.empty((2, c), dtype=torch.float64, device=x.t.device)
+        sums, nchunks = torch.empty((2, c), dtype=torch.float64, device=x.t.device), 1
         _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
-        if reduce_hook is not None:
-            reduce_hook(sums, m)
+        reduce_hook(sums, m)
     dgamma = new_f32((c,)) if need_dgamma else None
     dbeta = new_f32((c,)) if need_dbeta else None
     coef = new_f32((3, c))
-    _cabi.call("ttb_bn_bwd_finalize", sums.data_ptr(), count, c, _ptr(gamma), base + row, base + 2 * row,
+    _cabi.call("ttb_bn_bwd_finalize", sums.data_ptr(), nchunks, count, c, _ptr(gamma), base + row, base + 2 * row,
                _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
     dx = None
     if need_dx:
@@ -225,6 +225,20 @@ def axpy_(alpha, x, y):
 def sgd_step_(param, grad, buf, lr, momentum, dampening, weight_decay, nesterov, first_step):
     _cabi.call("ttb_sgd_step", _ptr(param), _ptr(grad), _ptr(buf), param.size, float(lr), float(momentum),
                float(dampening), float(weight_decay), int(bool(nesterov)), int(bool(first_step)), current_stream_ptr())
+
+
+def sgd_step_multi_(params, grads, bufs, first_flags, lr, momentum, dampening, weight_decay, nesterov):
+    """Fused update of many parameter tensors (lists of cparrays; bufs entries may be None when momentum == 0)."""
+    n = len(params)
+    if n == 0:
+        return
+    P = (ctypes.c_void_p * n)(*[p.t.data_ptr() for p in params])
+    G = (ctypes.c_void_p * n)(*[g.t.data_ptr() for g in grads])
+    B = (ctypes.c_void_p * n)(*[None if b is None else b.t.data_ptr() for b in bufs])
+    S = (ctypes.c_int64 * n)(*[p.size for p in params])
+    F = (ctypes.c_ubyte * n)(*[1 if f else 0 for f in first_flags])
+    _cabi.call("ttb_sgd_step_multi", n, P, G, B, S, F, float(lr), float(momentum), float(dampening),
+               float(weight_decay), int(bool(nesterov)), current_stream_ptr())
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 """SGD with momentum / dampening / weight decay / Nesterov (reference optim/sgd.py:5-59 + _functional.py:4-22).
-The per-parameter chain of 3-5 array expressions becomes ONE fused kernel per parameter (ttb_sgd_step):
+The per-parameter chain of 3-5 array expressions becomes ONE fused multi-tensor launch per 48 parameters
+(ttb_sgd_step_multi):
 d_p = g + wd*p; buf = d_p (first step) | mom*buf + (1-damp)*d_p; p += -lr * (nesterov ? d_p + mom*buf : buf)."""
 from .. import ops
 from ..xparray import cparray, new_f32
@@ -22,6 +23,7 @@ class SGD(Optimizer):
     def step(self):
         for group in self.param_groups:
             lr, momentum = group['lr'], group['momentum']
+            params, grads, bufs, firsts = [], [], [], []
             for p in group['params']:
                 g = p.grad
                 if g is None:
@@ -36,5 +38,9 @@ class SGD(Optimizer):
                         buf = new_f32(p.data.shape)
                         st['momentum_buffer'] = buf
                         first = True
-                ops.sgd_step_(p.data, g, buf, lr, momentum, group['dampening'], group['weight_decay'],
-                              group['nesterov'], first)
+                params.append(p.data)
+                grads.append(g)
+                bufs.append(buf)
+                firsts.append(first)
+            ops.sgd_step_multi_(params, grads, bufs, firsts, lr, momentum, group['dampening'], group['weight_decay'],
+                                group['nesterov'])

@@ -69,7 +69,7 @@ class cparray:
         a = np.asarray(a)
         if dtype is not None:
             a = a.astype(dtype, copy=False)
-        a = np.ascontiguousarray(a)
+        a = np.require(a, requirements='C')  # keeps 0-d arrays 0-d (ascontiguousarray would make them 1-d)
         if a.dtype not in _NP_TO_TORCH:
             raise TypeError(f"unsupported dtype {a.dtype}")
         host = torch.from_numpy(a.view(np.ndarray))

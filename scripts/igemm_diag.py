@@ -93,7 +93,35 @@ def main():
                     np.savez_compressed(os.path.join(OUT, f"diag_fail_{which}_{'_'.join(map(str, case))}.npz"), got=got,
                                         ref=ref, x=x.get(), w=w.get(), dy=dy.get())
     print("FAILED passes:", failed)
+    if failed:
+        wgrad_variants()
     return 1 if failed else 0
+
+
+def wgrad_variants():
+    """bring-up aid: try the MN-major descriptor / swizzle variants on one small wgrad problem"""
+    case = (4, 64, 16, 16, 64, 3, 1, 1, 1)
+    n, ci, h, w_, co, k, s, p, d = case
+    rng = np.random.default_rng(1)
+    x = cparray.from_numpy(rng.standard_normal((n, ci, h, w_)).astype(np.float32))
+    w = cparray.from_numpy((rng.standard_normal((co, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32))
+    ho, wo = ops.conv_out_hw(h, w_, k, k, (s, s), (p, p), (d, d))
+    dy = cparray.from_numpy(rng.standard_normal((n, co, ho, wo)).astype(np.float32))
+    ref, _ = run_pass("fp32", "wgrad", x, w, dy, s, p, d)
+    for swz in (4, 3):            # CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B = 4, _128B = 3
+        for layout in (1, 2):
+            for lbo, sbo in ((4096, 512), (512, 4096), (4096, 1024), (1024, 4096), (4096, 256)):
+                os.environ.update(TTB_WGRAD_SWIZZLE=str(swz), TTB_WGRAD_LAYOUT=str(layout), TTB_WGRAD_LBO=str(lbo),
+                                  TTB_WGRAD_SBO=str(sbo))
+                try:
+                    got, _ = run_pass("tf32", "wgrad", x, w, dy, s, p, d)
+                    rel = float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
+                    print(f"  variant swz={swz} layout={layout} lbo={lbo} sbo={sbo}: rel={rel:.3e} nonzero={np.mean(got != 0):.3f}", flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print(f"  variant swz={swz} layout={layout} lbo={lbo} sbo={sbo}: EXC {e}", flush=True)
+                    return
+    for k_ in ("TTB_WGRAD_SWIZZLE", "TTB_WGRAD_LAYOUT", "TTB_WGRAD_LBO", "TTB_WGRAD_SBO"):
+        os.environ.pop(k_, None)
 
 
 if __name__ == "__main__":
