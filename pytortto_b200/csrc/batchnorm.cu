@@ -128,36 +128,45 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
   }
 }
 
-// Sum of the per-chunk partials of one value: blockDim = (32 values, 8 chunk lanes); fixed order => deterministic.
-// Returns the total in threads with threadIdx.y == 0.
+// Sum of the per-chunk partials of one value: blockDim = (32 values, kLanes chunk lanes); fixed order => deterministic.
+// Four independent accumulators per thread keep four L2 loads in flight.  Returns the total where threadIdx.y == 0.
+constexpr int kLanes = 32;
 __device__ __forceinline__ double chunk_sum(const double* __restrict__ partials, int num_chunks, int stride, int idx,
                                             bool valid, double (*sm)[33]) {
-  double s = 0.0;
-  if (valid)
-    for (int k = threadIdx.y; k < num_chunks; k += 8) s += partials[(int64_t)k * stride + idx];
-  sm[threadIdx.y][threadIdx.x] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (valid) {
+    int k = threadIdx.y;
+    for (; k + 3 * kLanes < num_chunks; k += 4 * kLanes) {
+      s0 += partials[(int64_t)k * stride + idx];
+      s1 += partials[(int64_t)(k + kLanes) * stride + idx];
+      s2 += partials[(int64_t)(k + 2 * kLanes) * stride + idx];
+      s3 += partials[(int64_t)(k + 3 * kLanes) * stride + idx];
+    }
+    for (; k < num_chunks; k += kLanes) s0 += partials[(int64_t)k * stride + idx];
+  }
+  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   double t = 0.0;
   if (threadIdx.y == 0)
-    for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+    for (int j = 0; j < kLanes; ++j) t += sm[j][threadIdx.x];
   __syncthreads();
   return t;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int c2, double* __restrict__ sums) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double t = chunk_sum(partials, num_chunks, c2, i, i < c2, sm);
   if (threadIdx.y == 0 && i < c2) sums[i] = t;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c, float eps, float momentum,
                    float one_minus_momentum, float unbias, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* running_mean, float* running_var,
                    float* mean, float* var_eps, float* sd, float* scale, float* shift) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double s0 = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
   double s1 = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
@@ -194,11 +203,11 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const 
   shift[i] = (beta ? beta[i] : 0.f) - mu * sc;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c,
                        const float* __restrict__ gamma, const float* __restrict__ var_eps,
                        const float* __restrict__ sd, float* dgamma, float* dbeta, float* coef) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double sdy = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
   double sdyx = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
@@ -317,7 +326,7 @@ int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chu
 
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
   if (c2 <= 0) return 0;
-  reduce_partials_kernel<<<(c2 + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
+  reduce_partials_kernel<<<(c2 + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
   return check_launch("bn_reduce_partials");
 }
 
@@ -330,7 +339,7 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
   // (grad_nn.py:927-930), then applied to float32 arrays.
   float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
   float omm = (float)(1.0 - (double)momentum);
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count, c,
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count, c,
                                                                            eps, momentum, omm, unbias, gamma, beta,
                                                                            running_mean, running_var, mean, var_eps, sd,
                                                                            scale, shift);
@@ -371,7 +380,7 @@ int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const 
 int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef, void* stream) {
   if (c <= 0) return 0;
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count,
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count,
                                                                                c, gamma, var_eps, sd, dgamma, dbeta, coef);
   return check_launch("bn_bwd_finalize");
 }

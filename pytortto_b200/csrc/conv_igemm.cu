@@ -505,10 +505,19 @@ static int launch_fwd_bn(const FwdParams& P, int bn, cudaStream_t st) {
 
 size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
 
+static int wgrad_variant() {  // bring-up / tuning knob: 0 = default
+  const char* e = getenv("TTB_WGRAD_VARIANT");
+  return e ? atoi(e) : 0;
+}
+
 static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_per_split, int* steps_total) {
-  constexpr int KP = 32;
+  // 64 pixels per pipeline step: the TMA unit pays a fixed cost per box (measured: ~115 cycles + ~3 cycles per
+  // 128-byte row), so few large boxes beat many small ones (KP = 32 ran the layer-1 wgrad at 89 TFLOP/s, KP = 64 at 162)
+  const int variant = wgrad_variant();
+  const int KP = variant == 3 ? 32 : 64;
   const int ncols = d->r * d->s * d->c;
   *bn = ncols >= 256 ? 256 : (ncols >= 128 ? 128 : (ncols >= 64 ? 64 : 32));
+  if (variant == 2 && *bn == 256) *bn = 128;
   const int64_t m = (int64_t)d->n * d->p * d->q;
   const int total = (int)ceil_div(m, KP);
   const int64_t tiles = ceil_div(d->k, kTileM) * ceil_div(ncols, *bn);
@@ -738,11 +747,20 @@ int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* 
     }
   const int ktiles = (int)ceil_div(d->k, kTileM), ntiles = (int)ceil_div(ncols, bn);
   int rc;
-  switch (bn) {
-    case 256: rc = launch_wgrad<256, 32, 4>(P, ktiles, ntiles, splits, st); break;
-    case 128: rc = launch_wgrad<128, 32, 4>(P, ktiles, ntiles, splits, st); break;
-    case 64: rc = launch_wgrad<64, 32, 6>(P, ktiles, ntiles, splits, st); break;
-    default: rc = launch_wgrad<32, 32, 6>(P, ktiles, ntiles, splits, st); break;
+  if (KP == 32) {  // legacy small-box configuration, kept for A/B measurements (TTB_WGRAD_VARIANT=3)
+    switch (bn) {
+      case 256: rc = launch_wgrad<256, 32, 4>(P, ktiles, ntiles, splits, st); break;
+      case 128: rc = launch_wgrad<128, 32, 4>(P, ktiles, ntiles, splits, st); break;
+      case 64: rc = launch_wgrad<64, 32, 6>(P, ktiles, ntiles, splits, st); break;
+      default: rc = launch_wgrad<32, 32, 6>(P, ktiles, ntiles, splits, st); break;
+    }
+  } else {
+    switch (bn) {
+      case 256: rc = launch_wgrad<256, 64, 2>(P, ktiles, ntiles, splits, st); break;
+      case 128: rc = launch_wgrad<128, 64, 3>(P, ktiles, ntiles, splits, st); break;
+      case 64: rc = launch_wgrad<64, 64, 4>(P, ktiles, ntiles, splits, st); break;
+      default: rc = launch_wgrad<32, 64, 4>(P, ktiles, ntiles, splits, st); break;
+    }
   }
   if (rc) return rc;
   if (splits > 1) {

@@ -1,26 +1,33 @@
-"""Data-parallel layer (new work - the reference is single-process, single-device).
+"""Data-parallel layer (new work: the reference is single-process, single-device - SURVEY.md §2c, §8(e)).
 
-One process per GPU (torchrun-style env: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT), NCCL over
-NVLink 5 / NVSwitch through `torch.distributed` (gloo on CPU for the host-logic tests).  The batch is sharded by
-rank; two exchange steps make a k-GPU run equal the reference's single-process run on the concatenated batch:
+One process per GPU (torchrun environment: RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT), NCCL over
+NVLink 5 / NVSwitch through `torch.distributed` (gloo for the CPU host-logic tests).  The global batch is sharded
+by rank (`shard_batch`); two exchange steps make a k-GPU run equal the reference's single-process run on the
+concatenated batch:
 
-  1. parameter gradients: every rank back-propagates its local-mean loss; gradients are packed into flat buckets in
-     the order AccumulateGrad produces them, each bucket is all-reduced (SUM) as soon as it is full - overlapping the
-     rest of backward on a side stream - and scaled by 1/world, which yields the global-batch mean gradient;
-  2. BatchNorm statistics (SyncBN): forward all-reduces the per-channel [sum x, sum x^2] doubles (+ the element
-     count), backward all-reduces [sum dy, sum dy*(x-mean)], so normalisation, running stats (global N/(N-1)) and
-     dx use global-batch statistics (reference formulas, autograd/grad_nn.py:923-930, :984-988).  dgamma / dbeta
-     computed from the all-reduced sums are already GLOBAL sums, so they are excluded from the gradient averaging's
-     1/world... they are divided by world after SUM like every other gradient only if they were local; here they
-     are marked `_ttb_global_grad` and skipped by the bucket all-reduce, then scaled by 1/world to match the
-     mean-loss convention.
+1. Parameter gradients.  Every rank back-propagates the mean loss of ITS shard.  `DistributedDataParallel` hooks
+   `AccumulateGrad` (the leaf node of the autograd graph, reference autograd/function.py:70-93): as soon as a
+   parameter's gradient is final it is appended to the current bucket (reverse parameter order = the order
+   backward produces them); a full bucket (~25 MB) is flattened and all-reduced (SUM) asynchronously on NCCL's own
+   stream while the rest of backward keeps the compute stream busy.  `reduce_gradients()` (called between
+   `loss.backward()` and `optimizer.step()`) waits for the outstanding buckets, scales by 1/world - the mean over
+   ranks of local-mean gradients IS the global-batch mean gradient - and scatters the result back into `p.grad`.
+
+2. BatchNorm statistics (SyncBN).  BatchNorm.forward all-reduces the per-channel double sums [sum x, sum x^2]
+   (2C values) and uses count = world * local count, so normalisation and the running statistics (unbiased variance
+   with the GLOBAL N/(N-1), reference autograd/grad_nn.py:923-930) are those of the global batch; BatchNorm.backward
+   all-reduces [sum dy, sum dy*(x-mean)] so dx follows the reference formula (:984-988) with global sums.
+   dgamma / dbeta computed from those all-reduced sums are identical on every rank and equal the SUM over ranks of
+   the local-loss gradients, so they skip the bucket all-reduce and only receive the 1/world scaling.
 """
 import os
 
 import numpy as np
 import torch
 
-_state = {"initialized": False, "world": 1, "rank": 0, "sync_bn": True, "group": None, "backend": None}
+from .autograd.function import AccumulateGrad
+
+_state = {"initialized": False, "world": 1, "rank": 0, "sync_bn": True, "backend": None}
 
 
 def is_initialized():
@@ -45,7 +52,7 @@ def init_process_group(backend=None, sync_bn=True):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group(backend=backend)
     _state.update(initialized=True, world=dist.get_world_size(), rank=dist.get_rank(), sync_bn=bool(sync_bn),
-                  group=dist.group.WORLD, backend=backend)
+                  backend=backend)
     return _state["rank"], _state["world"]
 
 
@@ -53,36 +60,33 @@ def destroy_process_group():
     import torch.distributed as dist
     if dist.is_initialized():
         dist.destroy_process_group()
-    _state.update(initialized=False, world=1, rank=0, group=None)
+    _state.update(initialized=False, world=1, rank=0)
 
 
-def all_reduce_sum_(t):
-    """In-place SUM all-reduce of a torch tensor on the current stream (no-op for world 1)."""
+def all_reduce_sum_(t, async_op=False):
+    """In-place SUM all-reduce of a torch tensor (no-op for world 1).  Returns the work handle when async."""
     if _state["initialized"] and _state["world"] > 1:
         import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
+    return None
 
 
 # ---- SyncBN hooks (called from ops.bn_forward_train / ops.bn_backward) ------------------------------------
-def bn_forward_hook():
-    if not (_state["initialized"] and _state["world"] > 1 and _state["sync_bn"]):
-        return None
+def _sync_bn_active():
+    return _state["initialized"] and _state["world"] > 1 and _state["sync_bn"]
 
-    def hook(sums, local_count):
-        all_reduce_sum_(sums)
-        return local_count * _state["world"]  # equal shards by construction (shard_batch)
-    return hook
+
+def _stat_hook(sums, local_count):
+    all_reduce_sum_(sums)
+    return local_count * _state["world"]  # equal shards by construction (shard_batch)
+
+
+def bn_forward_hook():
+    return _stat_hook if _sync_bn_active() else None
 
 
 def bn_backward_hook():
-    if not (_state["initialized"] and _state["world"] > 1 and _state["sync_bn"]):
-        return None
-
-    def hook(sums, local_count):
-        all_reduce_sum_(sums)
-        return local_count * _state["world"]
-    return hook
+    return _stat_hook if _sync_bn_active() else None
 
 
 def shard_batch(*arrays):
@@ -108,25 +112,50 @@ def broadcast_parameters(module, src=0):
         if hasattr(d, "t"):
             dist.broadcast(d.t, src=src)
         else:
-            buf = torch.from_numpy(np.ascontiguousarray(d))
+            buf = torch.from_numpy(np.array(d, copy=True))
             dist.broadcast(buf, src=src)
             d[...] = buf.numpy()
 
 
+def _flat_view(t):
+    """1-D view of a gradient's PHYSICAL storage (4-D arrays are NHWC in memory)."""
+    if t.dim() == 4:
+        return t.permute(0, 2, 3, 1).reshape(-1)
+    return t.reshape(-1)
+
+
+class _Bucket:
+    __slots__ = ("params", "flat", "work")
+
+    def __init__(self, params):
+        self.params = params
+        self.flat = torch.cat([_flat_view(p.grad.t) for p in params])
+        self.work = all_reduce_sum_(self.flat, async_op=True)
+
+    def finish(self, inv_world, skip=()):
+        if self.work is not None:
+            self.work.wait()  # makes the current stream wait for the collective
+        self.flat.mul_(inv_world)
+        off = 0
+        for p in self.params:
+            v = _flat_view(p.grad.t)
+            n = v.numel()
+            if id(p) not in skip:
+                v.copy_(self.flat[off:off + n])
+            off += n
+
+
 class DistributedDataParallel:
-    """Wraps a Module: forward is unchanged; `reduce_gradients()` (call between loss.backward() and
-    optimizer.step()) turns local gradients into global-batch mean gradients.
+    """Wraps a Module.  Forward is unchanged; gradients are all-reduced in buckets that start during backward
+    (AccumulateGrad hook) and complete in `reduce_gradients()`."""
 
-    Gradients are flattened into buckets of ~`bucket_mb` MiB in reverse parameter order (the order backward produces
-    them), all-reduced with SUM and scaled by 1/world.  BatchNorm weight/bias gradients computed from all-reduced
-    statistics are already global sums of per-sample terms of the LOCAL-mean loss, i.e. world x the global-mean
-    gradient... see `_is_synced_bn_param`."""
-
-    def __init__(self, module, bucket_mb=25, broadcast=True):
+    def __init__(self, module, bucket_mb=25, broadcast=True, overlap=True):
         self.module = module
         self.bucket_bytes = int(bucket_mb * (1 << 20))
+        self.overlap = overlap
         if broadcast:
             broadcast_parameters(module)
+        self._param_ids = {id(p) for p in module.parameters()}
         self._synced_bn_params = set()
         if _state["sync_bn"]:
             from .nn.modules import _BatchNorm
@@ -135,6 +164,13 @@ class DistributedDataParallel:
                     for p in (m._parameters.get("weight"), m._parameters.get("bias")):
                         if p is not None:
                             self._synced_bn_params.add(id(p))
+        self._pending, self._pending_bytes = [], 0
+        self._buckets, self._seen = [], set()
+        AccumulateGrad.post_hooks.append(self._on_grad_ready)
+
+    def close(self):
+        if self._on_grad_ready in AccumulateGrad.post_hooks:
+            AccumulateGrad.post_hooks.remove(self._on_grad_ready)
 
     def __call__(self, *a, **k):
         return self.module(*a, **k)
@@ -145,37 +181,55 @@ class DistributedDataParallel:
     def parameters(self):
         return self.module.parameters()
 
+    # ---- backward-time hook ---------------------------------------------------------------------------------
+    def _on_grad_ready(self, p):
+        if not (self.overlap and _state["initialized"] and _state["world"] > 1):
+            return
+        pid = id(p)
+        if pid not in self._param_ids or pid in self._synced_bn_params:
+            return
+        if pid in self._seen:  # a parameter used twice in the graph: its gradient is not final yet - reduce at the end
+            self._seen.add(("dirty", pid))
+            return
+        self._seen.add(pid)
+        self._pending.append(p)
+        self._pending_bytes += p.grad.nbytes
+        if self._pending_bytes >= self.bucket_bytes:
+            self._launch_pending()
+
+    def _launch_pending(self):
+        if self._pending:
+            self._buckets.append(_Bucket(self._pending))
+            self._pending, self._pending_bytes = [], 0
+
+    # ---- after backward ----------------------------------------------------------------------------------------
     def reduce_gradients(self):
         world = _state["world"]
         if not (_state["initialized"] and world > 1):
             return
-        params = [p for p in self.module.parameters() if p.grad is not None]
-        params.reverse()
         inv = 1.0 / world
-        bucket, size = [], 0
-        for p in params:
-            if id(p) in self._synced_bn_params:
-                # computed from globally all-reduced sums: identical on every rank and equal to the SUM over ranks
-                # of the local-mean-loss gradients -> only the 1/world of the mean convention is missing
-                p.grad.t.mul_(inv)
+        dirty = {k[1] for k in self._seen if isinstance(k, tuple)}
+        self._launch_pending()
+        done = set()
+        for b in self._buckets:
+            b.finish(inv, skip=dirty)
+            done.update(id(p) for p in b.params)
+        # whatever was not bucketed during backward (overlap off, re-used parameters, grads set by hand)
+        rest, size = [], 0
+        for p in reversed(list(self.module.parameters())):
+            if p.grad is None:
                 continue
-            bucket.append(p)
+            pid = id(p)
+            if pid in self._synced_bn_params:
+                p.grad.t.mul_(inv)  # identical on all ranks and already the sum over ranks (see module docstring)
+                continue
+            if pid in done and pid not in dirty:
+                continue
+            rest.append(p)
             size += p.grad.nbytes
             if size >= self.bucket_bytes:
-                self._reduce_bucket(bucket, inv)
-                bucket, size = [], 0
-        if bucket:
-            self._reduce_bucket(bucket, inv)
-
-    @staticmethod
-    def _reduce_bucket(bucket, inv):
-        flats = [p.grad.t.reshape(-1) if p.grad.t.is_contiguous() else p.grad.t.permute(0, 2, 3, 1).reshape(-1)
-                 for p in bucket]
-        flat = torch.cat(flats)
-        all_reduce_sum_(flat)
-        flat.mul_(inv)
-        off = 0
-        for p, f in zip(bucket, flats):
-            n = f.numel()
-            f.copy_(flat[off:off + n])  # `f` is a view of the gradient's physical storage
-            off += n
+                _Bucket(rest).finish(inv)
+                rest, size = [], 0
+        if rest:
+            _Bucket(rest).finish(inv)
+        self._buckets, self._seen = [], set()
