@@ -260,7 +260,8 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel-family device time (CUDA events around every C-ABI call) on a few extra steps
-    prof = profile_families(step, x_dev, y_dev, steps=min(5, args.steps)) if rank == 0 else None
+    # (every rank runs it: the step contains collectives)
+    prof = profile_families(step, x_dev, y_dev, steps=min(5, args.steps))
 
     if rank != 0:
         return

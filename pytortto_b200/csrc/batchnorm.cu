@@ -74,7 +74,41 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     }
     int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
-    for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+    auto accumulate = [&](float4 va, float4 vb, float4 vm) {
+      if (MODE == 0) {
+        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
+        s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
+        s1.z = fmaf(va.z, va.z, s1.z); s1.w = fmaf(va.w, va.w, s1.w);
+      } else {
+        if (mask) {
+          va.x = vm.x > 0.f ? va.x : 0.f; va.y = vm.y > 0.f ? va.y : 0.f;
+          va.z = vm.z > 0.f ? va.z : 0.f; va.w = vm.w > 0.f ? va.w : 0.f;
+        }
+        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
+        s1.x = fmaf(va.x, vb.x - mu.x, s1.x); s1.y = fmaf(va.y, vb.y - mu.y, s1.y);
+        s1.z = fmaf(va.z, vb.z - mu.z, s1.z); s1.w = fmaf(va.w, vb.w - mu.w, s1.w);
+      }
+    };
+    int64_t r = r0 + ty;
+    if (VEC) {
+      // 4 rows per iteration: all loads of the batch are issued before the first use (memory-level parallelism)
+      constexpr int U = 4;
+      for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
+        float4 va[U], vb[U], vm[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = (r + u * ty_n) * c + ch;
+          va[u] = ld_f4_stream(a + off);
+          if (MODE == 1) {
+            vb[u] = ld_f4_stream(b + off);
+            if (mask) vm[u] = ld_f4_stream(mask + off);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(va[u], vb[u], vm[u]);
+      }
+    }
+    for (; r < r1; r += ty_n) {
       const int64_t off = r * c + ch;
       float4 va, vb = make_float4(0.f, 0.f, 0.f, 0.f), vm = make_float4(1.f, 1.f, 1.f, 1.f);
       if (VEC) {
@@ -94,19 +128,7 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
           }
         }
       }
-      if (MODE == 0) {
-        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
-        s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
-        s1.z = fmaf(va.z, va.z, s1.z); s1.w = fmaf(va.w, va.w, s1.w);
-      } else {
-        if (mask) {
-          va.x = vm.x > 0.f ? va.x : 0.f; va.y = vm.y > 0.f ? va.y : 0.f;
-          va.z = vm.z > 0.f ? va.z : 0.f; va.w = vm.w > 0.f ? va.w : 0.f;
-        }
-        s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
-        s1.x = fmaf(va.x, vb.x - mu.x, s1.x); s1.y = fmaf(va.y, vb.y - mu.y, s1.y);
-        s1.z = fmaf(va.z, vb.z - mu.z, s1.z); s1.w = fmaf(va.w, vb.w - mu.w, s1.w);
-      }
+      accumulate(va, vb, vm);
     }
   }
   sm[ty * tx_n + tx] = s0;
@@ -220,24 +242,34 @@ bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, doub
   coef[2 * c + i] = (float)(sdyx / (count * (double)var_eps[i]));  // c3
 }
 
-// y = x*scale + shift (+ReLU).  One float4 = 4 channels; channel quad = i % cq.
+// y = x*scale + shift (+ReLU).  One float4 = 4 channels; channel quad = i % cq.  Two independent float4 streams per
+// thread per iteration (grid-stride, 2x unrolled) keep more loads in flight.
+template <bool RELU>
+__device__ __forceinline__ float4 bn_apply4(float4 v, const float* __restrict__ scale, const float* __restrict__ shift, int q) {
+  float4 sc = ld_f4(scale + 4 * q), sh = ld_f4(shift + 4 * q);
+  v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+  v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+  if (RELU) {
+    v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+    v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+  }
+  return v;
+}
+
 template <bool RELU>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n4, int cq,
                 const float* __restrict__ scale, const float* __restrict__ shift) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    int q = (int)(i % cq);
-    float4 v = ld_f4_stream(x + 4 * i);
-    float4 sc = ld_f4(scale + 4 * q), sh = ld_f4(shift + 4 * q);
-    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-    if (RELU) {
-      v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
-      v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
-    }
-    st_f4(y + 4 * i, v);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    float4 a = ld_f4_stream(x + 4 * i), b = ld_f4_stream(x + 4 * (i + stride));
+    a = bn_apply4<RELU>(a, scale, shift, (int)(i % cq));
+    b = bn_apply4<RELU>(b, scale, shift, (int)((i + stride) % cq));
+    st_f4(y + 4 * i, a);
+    st_f4(y + 4 * (i + stride), b);
   }
+  for (; i < n4; i += stride) st_f4(y + 4 * i, bn_apply4<RELU>(ld_f4_stream(x + 4 * i), scale, shift, (int)(i % cq)));
 }
 
 template <bool RELU>
