@@ -329,7 +329,57 @@ def gen_step():
     print("preact_step.npz", len(names), "params")
 
 
+def _example_models():
+    """the SAME model source the B200 package uses (pytortto_b200/examples.py), instantiated on the reference"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ttb_examples", os.path.join(os.path.dirname(HERE), "pytortto_b200",
+                                                                              "examples.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.make_models(tt)
+
+
+def gen_models():
+    """Whole-model forward/backward of the other BASELINE configurations at reduced size, from the real reference:
+    UNet (conv+bias, BN, ReLU, MaxPool2d(2,2), ConvTranspose2d(k2,s2), cat, BCEWithLogits - config 4) and a
+    bottleneck ResNet with the 7x7/s2 stem and the overlapping MaxPool2d(3,2,1) (config 3)."""
+    M = _example_models()
+    out = {}
+    # ---- UNet ----
+    tt.manual_seed(21)
+    net = M["UNet"](3, 1, [32, 64])
+    rng = np.random.default_rng(21)
+    x = f32(rng.standard_normal((2, 3, 16, 16)))
+    target = f32(rng.integers(0, 2, (2, 1, 16, 16)))
+    net.train()
+    logits = net(tt.tensor(x))
+    loss = nn.BCEWithLogitsLoss()(logits, tt.tensor(target))
+    loss.backward()
+    out["unet/x"], out["unet/target"] = x, target
+    out["unet/logits"], out["unet/loss"] = f32(logits.data), f32(loss.data)
+    out["unet/param_names"] = np.array([k for k, _ in net.named_parameters()])
+    for k, p in net.named_parameters():
+        out[f"unet/grad/{k}"] = f32(p.grad)
+    # ---- bottleneck ResNet with stem + overlapping max-pool ----
+    tt.manual_seed(22)
+    net = M["ResNet"](M["Bottleneck"], [1, 1, 1, 1], [8, 8, 16, 16])
+    x = f32(rng.standard_normal((4, 3, 32, 32)))
+    lab = rng.integers(0, 10, 4).astype(np.int64)
+    net.train()
+    logp = net(tt.tensor(x))
+    loss = nn.NLLLoss()(logp, tt.tensor(lab, dtype=np.int64))
+    loss.backward()
+    out["resnet/x"], out["resnet/labels"] = x, lab
+    out["resnet/logp"], out["resnet/loss"] = f32(logp.data), f32(loss.data)
+    out["resnet/param_names"] = np.array([k for k, _ in net.named_parameters()])
+    for k, p in net.named_parameters():
+        out[f"resnet/grad/{k}"] = f32(p.grad)
+    np.savez_compressed(os.path.join(OUT, "models.npz"), **out)
+    print("models.npz")
+
+
 if __name__ == "__main__":
+    gen_models()
     gen_conv()
     gen_convt()
     gen_bn()

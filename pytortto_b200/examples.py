@@ -137,34 +137,36 @@ def make_models(tt):
             return self.conv(x)
 
     class UNet(nn.Module):
-        def __init__(self, in_channels=3, out_channels=1, features=(32, 64, 128, 256)):
+        """examples/unet/UNet.ipynb cell 12 (attribute names kept: down, up, pool, bottle_neck, out)"""
+
+        def __init__(self, in_channels, out_channels, features):
             super().__init__()
-            self.downs = nn.ModuleList()
-            self.ups = nn.ModuleList()
-            self.pool = nn.MaxPool2d(kernel_size=2, stride=2)
-            c = in_channels
+            self.down = nn.ModuleList()
+            self.up = nn.ModuleList()
+            self.pool = nn.MaxPool2d(2, 2)
             for f in features:
-                self.downs.append(DoubleConv(c, f))
-                c = f
+                self.down.append(DoubleConv(in_channels, f))
+                in_channels = f
+            self.bottle_neck = DoubleConv(f, 2 * f)
             for f in reversed(features):
-                self.ups.append(nn.ConvTranspose2d(f * 2, f, kernel_size=2, stride=2))
-                self.ups.append(DoubleConv(f * 2, f))
-            self.bottleneck = DoubleConv(features[-1], features[-1] * 2)
-            self.final_conv = nn.Conv2d(features[0], out_channels, kernel_size=1)
+                self.up.append(nn.ConvTranspose2d(2 * f, f, kernel_size=2, stride=2))
+                self.up.append(DoubleConv(2 * f, f))
+            self.out = nn.Conv2d(f, out_channels, kernel_size=1)
 
         def forward(self, x):
-            skips = []
-            for down in self.downs:
-                x = down(x)
-                skips.append(x)
+            skip_connections = []
+            for m in self.down:
+                x = m(x)
+                skip_connections.append(x)
                 x = self.pool(x)
-            x = self.bottleneck(x)
-            skips = skips[::-1]
-            for i in range(0, len(self.ups), 2):
-                x = self.ups[i](x)
-                x = tt.cat((skips[i // 2], x), dim=1)
-                x = self.ups[i + 1](x)
-            return self.final_conv(x)
+            x = self.bottle_neck(x)
+            skip_connections = skip_connections[::-1]
+            for i in range(0, len(self.up), 2):
+                skip_connection = skip_connections[i // 2]
+                x = self.up[i](x, output_size=skip_connection.shape[-2:])
+                x = tt.cat([skip_connections[i // 2], x], dim=1)
+                x = self.up[i + 1](x)
+            return self.out(x)
 
     return {"BasicBlock": BasicBlock, "PreactResNet": PreactResNet, "preact_resnet18": preact_resnet18,
             "small_preact_resnet110": small_preact_resnet110, "Bottleneck": Bottleneck, "ResNet": ResNet,

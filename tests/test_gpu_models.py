@@ -1,0 +1,115 @@
+"""GPU: whole-model forward/backward of the other BASELINE configurations (reduced size) against fixtures produced
+by the REAL reference (oracle/make_golden.py::gen_models, tests/golden/models.npz):
+  * UNet (config 4): Conv2d with bias -> BN -> ReLU, MaxPool2d(2,2), ConvTranspose2d(k2,s2), cat, BCEWithLogitsLoss
+  * bottleneck ResNet (config 3): 7x7/s2 3-channel stem, overlapping MaxPool2d(3,2,1) (last-writer-wins backward),
+    1x1 / 3x3 / strided convs with narrow channel counts (mixed tensor / exact paths), NLL loss.
+The same model source (pytortto_b200/examples.py) was instantiated on the reference to make the fixture; the same
+seed gives bit-identical initial parameters here."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from gpu_util import assert_close, report, require_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    require_gpu()
+
+
+def _models(tt):
+    from pytortto_b200.examples import make_models
+    return make_models(tt)
+
+
+@pytest.mark.parametrize("mode,tol_out,tol_grad", [("fp32", 2e-5, 5e-4), ("tf32", 2e-3, 0.1)])
+def test_unet_golden(mode, tol_out, tol_grad):
+    import pytortto_b200 as tt
+    tt.set_math_mode(mode)
+    g = load_golden("models.npz")
+    tt.manual_seed(21)
+    net = _models(tt)["UNet"](3, 1, [32, 64])
+    names = [str(n) for n in g["unet/param_names"]]
+    assert [k for k, _ in net.named_parameters()] == names
+    net.cuda().train()
+    logits = net(tt.tensor(g["unet/x"]).cuda())
+    loss = tt.nn.BCEWithLogitsLoss()(logits, tt.tensor(g["unet/target"]).cuda())
+    loss.backward()
+    assert_close("unet logits", logits.data.get(), g["unet/logits"], tol_out * (1 if mode == "fp32" else 5))
+    assert abs(loss.item() - float(g["unet/loss"])) <= max(tol_out, 1e-5) * max(1.0, abs(float(g["unet/loss"])))
+    worst = 0.0
+    for k, p in net.named_parameters():
+        msg, rel = report(f"unet grad {k}", p.grad.get(), g[f"unet/grad/{k}"])
+        worst = max(worst, rel)
+        assert rel <= tol_grad, msg
+    print(f"[{mode}] UNet worst gradient rel-err {worst:.3e}")
+
+
+@pytest.mark.parametrize("mode,tol_out,tol_grad", [("fp32", 2e-5, 5e-4), ("tf32", 2e-3, 0.1)])
+def test_bottleneck_resnet_golden(mode, tol_out, tol_grad):
+    import pytortto_b200 as tt
+    tt.set_math_mode(mode)
+    g = load_golden("models.npz")
+    tt.manual_seed(22)
+    M = _models(tt)
+    net = M["ResNet"](M["Bottleneck"], [1, 1, 1, 1], [8, 8, 16, 16])
+    names = [str(n) for n in g["resnet/param_names"]]
+    assert [k for k, _ in net.named_parameters()] == names
+    net.cuda().train()
+    logp = net(tt.tensor(g["resnet/x"]).cuda())
+    loss = tt.nn.NLLLoss()(logp, tt.tensor(g["resnet/labels"], dtype=np.int64).cuda())
+    loss.backward()
+    assert_close("resnet logp", logp.data.get(), g["resnet/logp"], tol_out * (1 if mode == "fp32" else 5))
+    worst = 0.0
+    for k, p in net.named_parameters():
+        msg, rel = report(f"resnet grad {k}", p.grad.get(), g[f"resnet/grad/{k}"])
+        worst = max(worst, rel)
+        assert rel <= tol_grad, msg
+    print(f"[{mode}] bottleneck ResNet worst gradient rel-err {worst:.3e}")
+
+
+def test_small_preact_resnet110_runs():
+    """BASELINE config 1 network (16/32/64 channels, 111 convs) at batch 8: finite, TF32 path vs exact path."""
+    import pytortto_b200 as tt
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((8, 3, 32, 32)).astype(np.float32)
+    lab = rng.integers(0, 10, 8).astype(np.int64)
+    losses = {}
+    for mode in ("tf32", "fp32"):
+        tt.set_math_mode(mode)
+        tt.manual_seed(1)
+        net = _models(tt)["small_preact_resnet110"]().cuda()
+        loss = tt.nn.NLLLoss()(net(tt.tensor(x).cuda()), tt.tensor(lab, dtype=np.int64).cuda())
+        loss.backward()
+        assert all(np.isfinite(p.grad.get()).all() for p in net.parameters())
+        losses[mode] = loss.item()
+    assert abs(losses["tf32"] - losses["fp32"]) < 5e-3 * abs(losses["fp32"])
+
+
+def test_adam_step_and_eval_mode():
+    """UNet's optimizer (Adam) and eval-mode BN (running statistics) on the device array."""
+    import pytortto_b200 as tt
+    tt.set_math_mode("tf32")
+    tt.manual_seed(5)
+    net = _models(tt)["UNet"](3, 1, [32]).cuda()
+    opt = tt.optim.Adam(net.parameters(), lr=1e-3)
+    rng = np.random.default_rng(5)
+    x = tt.tensor(rng.standard_normal((2, 3, 8, 8)).astype(np.float32)).cuda()
+    t = tt.tensor(rng.integers(0, 2, (2, 1, 8, 8)).astype(np.float32)).cuda()
+    first = None
+    for _ in range(5):
+        opt.zero_grad()
+        loss = tt.nn.BCEWithLogitsLoss()(net(x), t)
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+    assert loss.item() < first
+    net.eval()
+    with tt.no_grad():
+        y1 = net(x).data.get()
+        y2 = net(x).data.get()
+    np.testing.assert_array_equal(y1, y2)  # eval mode: no statistics update, deterministic
+    sd = net.state_dict()
+    assert float(sd["down.0.conv.1.num_batches_tracked"]) == 5.0
