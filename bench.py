@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="preact_resnet18", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--math", default="tf32", choices=["tf32", "bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

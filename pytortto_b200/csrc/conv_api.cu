@@ -1,5 +1,14 @@
 // C-ABI entry points for convolution: validation + dispatch between the tcgen05 implicit-GEMM kernels
 // (conv_igemm.cu) and the generic exact-fp32 direct kernels (conv_direct.cu).
+//
+// The ABI always takes fp32 NHWC activations and fp32 [K][R][S][C] weights.  Operand staging for the tensor path:
+//   TF32, channels % 32 == 0 : none - TMA reads the caller's buffers directly.
+//   TF32, other channel count : fprop / wgrad run over a zero-padded fp32 copy (C -> round_up(C, 32)); this is how
+//                               the 3-channel network stems reach the tensor cores.
+//   BF16                      : operands are converted (and padded to a multiple of 64 channels) to bf16 copies in
+//                               the workspace; accumulation and all outputs stay fp32.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ttb {
@@ -9,34 +18,47 @@ int direct_fprop(const ttb_conv_desc* d, const float* x, const float* w, const f
 int direct_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
 int direct_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                  cudaStream_t st);
-// conv_igemm.cu
+// conv_igemm.cu (operands in the element type of d->math_mode: fp32 for TF32, bf16 for BF16)
 bool igemm_supported(const ttb_conv_desc* d, int pass);
+int igemm_channel_block(const ttb_conv_desc* d);
 size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
-int igemm_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* ws,
+int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* ws,
                 size_t ws_bytes, cudaStream_t st);
-int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
+int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
                 cudaStream_t st);
-int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 
-// ---- channel padding: problems whose input-channel count is not a multiple of 32 (network stems with C = 3, narrow
-// stages with C = 16 ...) run on the tensor path over a zero-padded copy [rows][Cp], Cp = round_up(C, 32).  The
-// zero channels contribute nothing; for the 3-channel CIFAR stem this replaces the CUDA-core direct kernels.
+// [rows][c] fp32 -> [rows][cp] OutT (zero-filled channels c..cp-1); 4 output channels per thread
+template <class OutT>
 __global__ void __launch_bounds__(256)
-pad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int c, int cp) {
+stage_channels_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int64_t rows, int c, int cp) {
   const int q = cp / 4;
-  int64_t total = rows * q;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t total = rows * q;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    int64_t r = t / q;
-    int c0 = (int)(t % q) * 4;
+    const int64_t r = t / q;
+    const int c0 = (int)(t % q) * 4;
     const float* ps = src + r * c;
     float4 v;
-    v.x = c0 + 0 < c ? ps[c0 + 0] : 0.f;
-    v.y = c0 + 1 < c ? ps[c0 + 1] : 0.f;
-    v.z = c0 + 2 < c ? ps[c0 + 2] : 0.f;
-    v.w = c0 + 3 < c ? ps[c0 + 3] : 0.f;
-    *reinterpret_cast<float4*>(dst + r * cp + c0) = v;
+    if (vec && c0 + 3 < c) {
+      v = ld_f4_stream(ps + c0);
+    } else {
+      v.x = c0 + 0 < c ? ps[c0 + 0] : 0.f;
+      v.y = c0 + 1 < c ? ps[c0 + 1] : 0.f;
+      v.z = c0 + 2 < c ? ps[c0 + 2] : 0.f;
+      v.w = c0 + 3 < c ? ps[c0 + 3] : 0.f;
+    }
+    if constexpr (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + r * cp + c0) = v;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 packed;
+      packed.x = *reinterpret_cast<uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + r * cp + c0) = packed;
+    }
   }
 }
 
@@ -51,16 +73,53 @@ unpad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, in
   }
 }
 
-static inline int padded_c(const ttb_conv_desc* d) { return (d->c + 31) / 32 * 32; }
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// true when pass 0 (fprop) / 2 (wgrad) should run on the tensor path over channel-padded operands
-static bool pad_path(const ttb_conv_desc* d, int pass, ttb_conv_desc* padded) {
-  if (d->math_mode == TTB_MATH_FP32 || d->groups != 1 || d->c % 32 == 0 || pass == 1) return false;
-  ttb_conv_desc p = *d;
-  p.c = padded_c(d);
-  if (!igemm_supported(&p, pass)) return false;
-  if (padded) *padded = p;
+static int stage(const float* src, void* dst, int64_t rows, int c, int cp, bool bf16, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  int grid = elementwise_grid(rows * (cp / 4), 256);
+  if (bf16) stage_channels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, c, cp);
+  else stage_channels_kernel<float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), rows, c, cp);
+  return check_launch("stage_channels");
+}
+
+// How a pass runs on the tensor path.  `p` is the problem the igemm kernels see (channel count padded).
+struct TensorPlan {
+  ttb_conv_desc p;
+  bool bf16;        // operands are staged as bf16
+  bool stage_ops;   // operands need a staged copy (conversion and / or channel padding)
+  size_t a_bytes;   // staged activation-like operand #1 (x for fprop/wgrad, dy for dgrad)
+  size_t b_bytes;   // staged operand #2 (w for fprop/dgrad, dy for wgrad in bf16 mode)
+  size_t c_bytes;   // wgrad only: padded fp32 dw when the channel count was padded
+  size_t inner;     // workspace of the igemm pass itself
+};
+
+static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
+  if (d->math_mode == TTB_MATH_FP32 || d->groups != 1) return false;
+  t->p = *d;
+  t->bf16 = d->math_mode == TTB_MATH_BF16;
+  const int blk = igemm_channel_block(d);
+  if (pass != 1) t->p.c = (d->c + blk - 1) / blk * blk;  // dgrad has no padded variant (needs K % blk == 0)
+  if (!igemm_supported(&t->p, pass)) return false;
+  const bool padded = t->p.c != d->c;
+  t->stage_ops = t->bf16 || padded;
+  const size_t es = t->bf16 ? 2 : 4;
+  t->a_bytes = t->b_bytes = t->c_bytes = 0;
+  if (t->stage_ops) {
+    const size_t xrows = (size_t)d->n * d->h * d->w, yrows = (size_t)d->n * d->p * d->q, wrows = (size_t)d->k * d->r * d->s;
+    if (pass == 0) {
+      t->a_bytes = align256(xrows * t->p.c * es);
+      t->b_bytes = align256(wrows * t->p.c * es);
+    } else if (pass == 1) {
+      t->a_bytes = align256(yrows * d->k * es);
+      t->b_bytes = align256(wrows * d->c * es);
+    } else {
+      t->a_bytes = align256(xrows * t->p.c * es);
+      t->b_bytes = t->bf16 ? align256(yrows * d->k * es) : 0;
+      t->c_bytes = padded ? align256(wrows * t->p.c * sizeof(float)) : 0;
+    }
+  }
+  t->inner = align256(igemm_workspace_size(&t->p, pass));
   return true;
 }
 
@@ -72,6 +131,7 @@ static int validate(const ttb_conv_desc* d, const char* what) {
   TTB_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0 && d->pad_h >= 0 && d->pad_w >= 0,
               "%s: bad stride/dilation/padding", what);
   TTB_REQUIRE(d->p >= 0 && d->q >= 0, "%s: bad output size", what);
+  TTB_REQUIRE(d->math_mode >= TTB_MATH_FP32 && d->math_mode <= TTB_MATH_BF16, "%s: unknown math mode %d", what, d->math_mode);
   return 0;
 }
 }  // namespace ttb
@@ -81,74 +141,86 @@ using namespace ttb;
 extern "C" {
 
 int ttb_conv2d_tensor_path_supported(const ttb_conv_desc* d, int pass) {
-  if (!d || d->math_mode == TTB_MATH_FP32) return 0;
-  return (igemm_supported(d, pass) || pad_path(d, pass, nullptr)) ? 1 : 0;
+  if (!d) return 0;
+  TensorPlan t;
+  return plan_tensor(d, pass, &t) ? 1 : 0;
 }
 
 size_t ttb_conv2d_workspace_size(const ttb_conv_desc* d, int pass) {
   if (!d) return 0;
-  if (d->math_mode != TTB_MATH_FP32 && igemm_supported(d, pass)) return igemm_workspace_size(d, pass);
-  ttb_conv_desc p;
-  if (pad_path(d, pass, &p)) {
-    const size_t xb = align256((size_t)d->n * d->h * d->w * p.c * sizeof(float));
-    const size_t wb = align256((size_t)d->k * d->r * d->s * p.c * sizeof(float));
-    return xb + wb + align256(igemm_workspace_size(&p, pass));
-  }
+  TensorPlan t;
+  if (plan_tensor(d, pass, &t)) return t.a_bytes + t.b_bytes + t.c_bytes + t.inner;
   return direct_workspace_size(d, pass);
 }
 
 int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
                      void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate(d, "conv2d_fprop")) return rc;
-  if (d->math_mode != TTB_MATH_FP32 && igemm_supported(d, 0))
-    return igemm_fprop(d, x, w, bias, y, workspace, workspace_bytes, as_stream(stream));
-  ttb_conv_desc p;
-  if (pad_path(d, 0, &p)) {
-    cudaStream_t st = as_stream(stream);
-    const int64_t xrows = (int64_t)d->n * d->h * d->w, wrows = (int64_t)d->k * d->r * d->s;
-    const size_t xb = align256((size_t)xrows * p.c * sizeof(float)), wb = align256((size_t)wrows * p.c * sizeof(float));
-    TTB_REQUIRE(workspace != nullptr && workspace_bytes >= xb + wb, "conv2d_fprop: workspace of %zu bytes needed, %zu given",
-                xb + wb, workspace_bytes);
-    float* xp = reinterpret_cast<float*>(workspace);
-    float* wp = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + xb);
-    pad_channels_kernel<<<elementwise_grid(xrows * p.c / 4, 256), 256, 0, st>>>(x, xp, xrows, d->c, p.c);
-    pad_channels_kernel<<<elementwise_grid(wrows * p.c / 4, 256), 256, 0, st>>>(w, wp, wrows, d->c, p.c);
-    if (check_launch("pad_channels")) return 1;
-    return igemm_fprop(&p, xp, wp, bias, y, reinterpret_cast<char*>(workspace) + xb + wb, workspace_bytes - xb - wb, st);
+  cudaStream_t st = as_stream(stream);
+  TensorPlan t;
+  if (!plan_tensor(d, 0, &t)) return direct_fprop(d, x, w, bias, y, st);
+  const size_t need = t.a_bytes + t.b_bytes + t.c_bytes + t.inner;
+  TTB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
+              "conv2d_fprop: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+  char* ws = reinterpret_cast<char*>(workspace);
+  const void *xa = x, *wa = w;
+  if (t.stage_ops) {
+    if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
+    if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, t.p.c, t.bf16, st)) return 1;
+    xa = ws;
+    wa = ws + t.a_bytes;
   }
-  return direct_fprop(d, x, w, bias, y, as_stream(stream));
+  return igemm_fprop(&t.p, xa, wa, bias, y, ws ? ws + t.a_bytes + t.b_bytes : nullptr, t.inner, st);
 }
 
 int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
                      size_t workspace_bytes, void* stream) {
   if (int rc = validate(d, "conv2d_dgrad")) return rc;
-  if (d->math_mode != TTB_MATH_FP32 && igemm_supported(d, 1))
-    return igemm_dgrad(d, dy, w, dx, workspace, workspace_bytes, as_stream(stream));
-  return direct_dgrad(d, dy, w, dx, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  TensorPlan t;
+  if (!plan_tensor(d, 1, &t)) return direct_dgrad(d, dy, w, dx, st);
+  const size_t need = t.a_bytes + t.b_bytes + t.c_bytes + t.inner;
+  TTB_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d_dgrad: workspace of %zu bytes needed, %zu given",
+              need, workspace_bytes);
+  char* ws = reinterpret_cast<char*>(workspace);
+  const void *dya = dy, *wa = w;
+  if (t.stage_ops) {  // bf16 only (dgrad has no channel padding)
+    if (stage(dy, ws, (int64_t)d->n * d->p * d->q, d->k, d->k, t.bf16, st)) return 1;
+    if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, d->c, t.bf16, st)) return 1;
+    dya = ws;
+    wa = ws + t.a_bytes;
+  }
+  return igemm_dgrad(&t.p, dya, wa, dx, ws + t.a_bytes + t.b_bytes, t.inner, st);
 }
 
 int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
                      size_t workspace_bytes, void* stream) {
   if (int rc = validate(d, "conv2d_wgrad")) return rc;
-  if (d->math_mode != TTB_MATH_FP32 && igemm_supported(d, 2))
-    return igemm_wgrad(d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
-  ttb_conv_desc p;
-  if (pad_path(d, 2, &p)) {
-    cudaStream_t st = as_stream(stream);
-    const int64_t xrows = (int64_t)d->n * d->h * d->w, wrows = (int64_t)d->k * d->r * d->s;
-    const size_t xb = align256((size_t)xrows * p.c * sizeof(float)), wb = align256((size_t)wrows * p.c * sizeof(float));
-    TTB_REQUIRE(workspace != nullptr && workspace_bytes >= xb + wb, "conv2d_wgrad: workspace of %zu bytes needed, %zu given",
-                xb + wb, workspace_bytes);
-    float* xp = reinterpret_cast<float*>(workspace);
-    float* dwp = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + xb);
-    pad_channels_kernel<<<elementwise_grid(xrows * p.c / 4, 256), 256, 0, st>>>(x, xp, xrows, d->c, p.c);
-    if (check_launch("pad_channels")) return 1;
-    if (int rc = igemm_wgrad(&p, xp, dy, dwp, reinterpret_cast<char*>(workspace) + xb + wb, workspace_bytes - xb - wb, st))
-      return rc;
-    unpad_channels_kernel<<<elementwise_grid(wrows * d->c, 256), 256, 0, st>>>(dwp, dw, wrows, d->c, p.c);
+  cudaStream_t st = as_stream(stream);
+  TensorPlan t;
+  if (!plan_tensor(d, 2, &t)) return direct_wgrad(d, x, dy, dw, workspace, workspace_bytes, st);
+  const size_t need = t.a_bytes + t.b_bytes + t.c_bytes + t.inner;
+  TTB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
+              "conv2d_wgrad: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+  char* ws = reinterpret_cast<char*>(workspace);
+  const void *xa = x, *dya = dy;
+  float* dwa = dw;
+  if (t.stage_ops) {
+    if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
+    xa = ws;
+    if (t.bf16) {
+      if (stage(dy, ws + t.a_bytes, (int64_t)d->n * d->p * d->q, d->k, d->k, true, st)) return 1;
+      dya = ws + t.a_bytes;
+    }
+    if (t.c_bytes) dwa = reinterpret_cast<float*>(ws + t.a_bytes + t.b_bytes);
+  }
+  if (int rc = igemm_wgrad(&t.p, xa, dya, dwa, ws ? ws + t.a_bytes + t.b_bytes + t.c_bytes : nullptr, t.inner, st)) return rc;
+  if (t.c_bytes) {
+    const int64_t wrows = (int64_t)d->k * d->r * d->s;
+    unpad_channels_kernel<<<elementwise_grid(wrows * d->c, 256), 256, 0, st>>>(dwa, dw, wrows, d->c, t.p.c);
     return check_launch("unpad_channels");
   }
-  return direct_wgrad(d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
+  return 0;
 }
 
 }  // extern "C"

@@ -26,7 +26,17 @@ namespace ttb {
 
 constexpr int kMaxTaps = 64;
 constexpr int kTileM = 128;          // UMMA M (rows of the accumulator = TMEM lanes)
-constexpr int kKBlock = 32;          // fp32 elements per 128-byte swizzle row
+
+// operand element type of one launch: fp32 read as TF32 (32 per 128-byte swizzle row) or bf16 (64 per row)
+struct Elem {
+  bool bf16;
+  int size;    // bytes
+  int per_row; // elements per 128-byte row = channels per K-block / per MN slab
+  CUtensorMapDataType dt;
+};
+static inline Elem elem_of(bool bf16) {
+  return bf16 ? Elem{true, 2, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16} : Elem{false, 4, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32};
+}
 constexpr int kThreadsIgemm = 192;
 constexpr int kStagePitch = 36;      // floats per staged epilogue row (32 + 4 pad: conflict-free float4 access)
 
@@ -61,14 +71,14 @@ static int load_driver_fns() {
   return 0;
 }
 
-// 2-D row-major fp32 matrix [rows][cols] -> tiled map with box [box_rows][32 floats], 128B swizzle, zero OOB fill
-static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+// 2-D row-major matrix [rows][cols] -> tiled map with box [box_rows][128 bytes], 128B swizzle, zero OOB fill
+static int make_tiled_2d(CUtensorMap* tm, const void* base, Elem el, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(float)};
-  cuuint32_t box[2] = {kKBlock, box_rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)el.size};
+  cuuint32_t box[2] = {(cuuint32_t)el.per_row, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = g_encodeTiled(tm, el.dt, 2, (void*)base, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -79,18 +89,19 @@ static int make_tiled_2d(CUtensorMap* tm, const float* base, uint64_t rows, uint
   return 0;
 }
 
-// NHWC fp32 activation [n][h][w][c] -> im2col map: `pixels` base pixels x 32 channels per load, traversal strides
+// NHWC activation [n][h][w][c] -> im2col map: `pixels` base pixels x 128 bytes of channels per load, traversal strides
 // (tw, th), bounding-box corners in W/H order, 128B swizzle, zero fill outside the image.
-static int make_im2col_4d(CUtensorMap* tm, const float* base, int n, int h, int w, int c, int lower_w, int lower_h,
+static int make_im2col_4d(CUtensorMap* tm, const void* base, Elem el, int n, int h, int w, int c, int lower_w, int lower_h,
                           int upper_w, int upper_h, int tw, int th, uint32_t pixels,
                           CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  const cuuint64_t es = (cuuint64_t)el.size;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)c * es, (cuuint64_t)w * c * es, (cuuint64_t)h * w * c * es};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)tw, (cuuint32_t)th, 1};
-  CUresult r = g_encodeIm2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, lower, upper,
-                              kKBlock, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+  CUresult r = g_encodeIm2col(tm, el.dt, 4, (void*)base, dims, strides, lower, upper,
+                              (cuuint32_t)el.per_row, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d) nhwc=%d,%d,%d,%d lower=(%d,%d) upper=(%d,%d) stride=(%d,%d)", (int)r, n,
@@ -101,7 +112,7 @@ static int make_im2col_4d(CUtensorMap* tm, const float* base, int n, int h, int 
   // descriptor word must be cleared (same workaround CUTLASS applies, cute/atom/copy_traits_sm90_im2col.hpp).
   int drv = 0;
   cudaDriverGetVersion(&drv);
-  if (drv <= 13010 && (uint64_t)n * h * w * c * 4 < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  if (drv <= 13010 && (uint64_t)n * h * w * c * es < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
   return 0;
 }
 
@@ -194,9 +205,9 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_base, float* stage_
 // ------------------------------------------------------------------------------------------------------------
 // fprop / dgrad kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int NSTAGES>
-__global__ void __launch_bounds__(kThreadsIgemm)
-igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
+template <int BN, int NSTAGES, bool BF16>
+__device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
+  constexpr int kElems = BF16 ? 64 : 32;  // channels per K-block (one 128-byte swizzle row)
   constexpr uint32_t kABytes = kTileM * 128;
   constexpr uint32_t kBBytes = BN * 128;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
@@ -253,8 +264,8 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
-          ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kKBlock, cw, ch, n, ow, oh);
-          ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kKBlock, n0);
+          ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
+          ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -262,7 +273,7 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 0, 0, kTileM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1 /*bf16*/ : 2 /*tf32*/, 0, 0, kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -271,10 +282,11 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
         const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < kKBlock / 8; ++k) {
+        for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
           uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
           uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
-          ptx::mma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
+          if (BF16) ptx::mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+          else ptx::mma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
         if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -293,15 +305,40 @@ igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
   if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+template <int BN, int NSTAGES, bool BF16>
+__global__ void __launch_bounds__(kThreadsIgemm)
+igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
+  igemm_fwd_body<BN, NSTAGES, BF16>(P);
+}
+
+// Up to kMaxMulti independent problems of the same shape class in one launch (blockIdx.z selects): the stride-parity
+// classes of a strided dgrad run concurrently instead of as 4 small back-to-back grids.
+constexpr int kMaxMulti = 4;
+struct FwdParamsMulti {
+  FwdParams p[kMaxMulti];
+};
+
+template <int BN, int NSTAGES, bool BF16>
+__global__ void __launch_bounds__(kThreadsIgemm)
+igemm_fwd_multi_kernel(const __grid_constant__ FwdParamsMulti PM) {
+  const FwdParams& P = PM.p[blockIdx.z];
+  if ((int)blockIdx.x * kTileM >= P.o.m_total) return;  // classes can differ by one tile; whole CTA leaves
+  igemm_fwd_body<BN, NSTAGES, BF16>(P);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // wgrad kernel: D[k (128 lanes), (tap,c) (BN columns)] += dY[pixels, k]^T * A[pixels, (tap,c)]
 // ------------------------------------------------------------------------------------------------------------
-template <int BN, int KP, int NSTAGES>
+template <int BN, int KP, int NSTAGES, bool BF16>
 __global__ void __launch_bounds__(kThreadsIgemm)
 igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
-  constexpr uint32_t kSlabBytes = KP * 128;          // KP pixel rows x 32 channels
-  constexpr uint32_t kABytes = 4 * kSlabBytes;       // 128 output channels = 4 slabs
-  constexpr uint32_t kBBytes = (BN / 32) * kSlabBytes;
+  constexpr int kSlabCh = BF16 ? 64 : 32;            // channels per 128-byte-wide MN slab
+  constexpr int kASlabs = kTileM / kSlabCh;          // 128 output channels
+  constexpr int kMmaRows = BF16 ? 16 : 8;            // pixels (K) consumed per MMA
+  static_assert(BN % kSlabCh == 0, "N tile must be whole slabs");
+  constexpr uint32_t kSlabBytes = KP * 128;          // KP pixel rows x 128 bytes of channels
+  constexpr uint32_t kABytes = kASlabs * kSlabBytes;
+  constexpr uint32_t kBBytes = (BN / kSlabCh) * kSlabBytes;
   constexpr uint32_t kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static_assert(NSTAGES * kStageBytes >= 4 * 32 * kStagePitch * 4, "epilogue staging must fit in the pipeline smem");
@@ -319,8 +356,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   const int step0 = split * P.steps_per_split;
   int steps = P.pixel_steps_total - step0;
   if (steps > P.steps_per_split) steps = P.steps_per_split;
-  const int ncol = P.o.n_total - n0 < BN ? P.o.n_total - n0 : BN;  // valid columns (multiple of 32)
-  const int nslab = ncol / 32;
+  const int ncol = P.o.n_total - n0 < BN ? P.o.n_total - n0 : BN;  // valid columns (whole slabs)
+  const int nslab = ncol / kSlabCh;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&P.tmDy);
@@ -359,10 +396,10 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         uint8_t* sa = smem + stage * kStageBytes;
         ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl)  // dY[pix0 .. pix0+KP, k0+32*sl ..+32]  (rows past the tensor are zero-filled)
-          ptx::tma_load_2d(sa + sl * kSlabBytes, &P.tmDy, &full_bar[stage], k0 + sl * 32, pix0);
+        for (int sl = 0; sl < kASlabs; ++sl)  // dY[pix0 .. pix0+KP, k0 + slab]  (rows past the tensor are zero-filled)
+          ptx::tma_load_2d(sa + sl * kSlabBytes, &P.tmDy, &full_bar[stage], k0 + sl * kSlabCh, pix0);
         for (int sl = 0; sl < nslab; ++sl) {
-          const int col = n0 + sl * 32;
+          const int col = n0 + sl * kSlabCh;
           const int tap = col / P.c;
           const int c0 = col - tap * P.c;
           ptx::tma_load_im2col_4d(sa + kABytes + sl * kSlabBytes, &P.tmX, &full_bar[stage], c0, cw, ch, n,
@@ -373,7 +410,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 1, 1, kTileM, BN);
+      constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1 /*bf16*/ : 2 /*tf32*/, 1, 1, kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 0; s < steps; ++s) {
@@ -382,12 +419,13 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < KP / 8; ++k) {  // 8 pixels (= one 8-row swizzle atom of every slab) per MMA
-          // MN-major fp32 operands must use the 128B-span / 32B-atom swizzle: 4-row K groups (512 B apart),
-          // 32-channel slabs kSlabBytes apart
-          uint64_t da = ptx::umma_desc(sa + k * 1024, P.desc_lbo, P.desc_sbo, P.desc_layout);
-          uint64_t db = ptx::umma_desc(sb + k * 1024, P.desc_lbo, P.desc_sbo, P.desc_layout);
-          ptx::mma_tf32(tmem_base, da, db, idesc, (s | k) != 0);
+        for (int k = 0; k < KP / kMmaRows; ++k) {  // 8 (tf32) / 16 (bf16) pixel rows of every slab per MMA
+          // MN-major operands: fp32 must use the 128B-span / 32B-atom swizzle (4-row K groups 512 B apart), bf16 the
+          // plain 128B swizzle (8-row K groups 1024 B apart); 128-byte-wide slabs are kSlabBytes apart
+          uint64_t da = ptx::umma_desc(sa + k * (kMmaRows * 128), P.desc_lbo, P.desc_sbo, P.desc_layout);
+          uint64_t db = ptx::umma_desc(sb + k * (kMmaRows * 128), P.desc_lbo, P.desc_sbo, P.desc_layout);
+          if (BF16) ptx::mma_bf16(tmem_base, da, db, idesc, (s | k) != 0);
+          else ptx::mma_tf32(tmem_base, da, db, idesc, (s | k) != 0);
         }
         ptx::mma_commit(&empty_bar[stage]);
         if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -410,7 +448,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
 // small helper kernels
 // ------------------------------------------------------------------------------------------------------------
 // w[K][T][C] -> wt[C][T][K]   (T = R*S taps)
-__global__ void repack_krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt, int K, int T, int C) {
+template <class T_>
+__global__ void repack_krsc_to_crsk_kernel(const T_* __restrict__ w, T_* __restrict__ wt, int K, int T, int C) {
   int64_t total = (int64_t)K * T * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -437,7 +476,7 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
 static bool in_corner_range(int v) { return v >= -128 && v <= 127; }
 
 static bool common_ok(const ttb_conv_desc* d) {
-  if (d->math_mode != TTB_MATH_TF32) return false;  // bf16 operand staging is a later round
+  if (d->math_mode != TTB_MATH_TF32 && d->math_mode != TTB_MATH_BF16) return false;
   if (d->groups != 1) return false;
   if (d->r * d->s > kMaxTaps) return false;
   if (d->n <= 0 || d->p <= 0 || d->q <= 0) return false;
@@ -447,13 +486,17 @@ static bool common_ok(const ttb_conv_desc* d) {
   return true;
 }
 
+// channels per K-block / MN slab in the math mode of the descriptor (32 for TF32, 64 for BF16)
+int igemm_channel_block(const ttb_conv_desc* d) { return d->math_mode == TTB_MATH_BF16 ? 64 : 32; }
+
 bool igemm_supported(const ttb_conv_desc* d, int pass) {
   if (!common_ok(d)) return false;
+  const int blk = igemm_channel_block(d);
   const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
   if (pass == 0 || pass == 2) {
     // the traversal box must reproduce exactly (P, Q): true for the reference's floor formula when the
     // bottom/right remainder is smaller than the stride
-    if (d->c % kKBlock != 0 || d->k % 8 != 0) return false;
+    if (d->c % blk != 0 || d->k % 8 != 0) return false;
     if (!in_corner_range(-d->pad_h) || !in_corner_range(-d->pad_w) || !in_corner_range(up_h) || !in_corner_range(up_w))
       return false;
     if ((d->h + up_h + d->pad_h - 1) / d->stride_h + 1 != d->p) return false;
@@ -462,17 +505,17 @@ bool igemm_supported(const ttb_conv_desc* d, int pass) {
     return true;
   }
   // dgrad: reduction over output channels k, output columns = input channels c
-  if (d->k % kKBlock != 0 || d->c % 8 != 0) return false;
+  if (d->k % blk != 0 || d->c % 8 != 0) return false;
   if (d->pad_h + (d->r - 1) * d->dil_h > 100 || d->pad_w + (d->s - 1) * d->dil_w > 100) return false;
   return true;
 }
 
-template <int BN, int NSTAGES>
+template <int BN, int NSTAGES, bool BF16>
 static int launch_fwd(const FwdParams& P, cudaStream_t st) {
   constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, NSTAGES, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return 1;
@@ -480,7 +523,7 @@ static int launch_fwd(const FwdParams& P, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(P.o.m_total, kTileM), (unsigned)ceil_div(P.o.n_total, BN));
-  igemm_fwd_kernel<BN, NSTAGES><<<grid, kThreadsIgemm, smem, st>>>(P);
+  igemm_fwd_kernel<BN, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(P);
   return check_launch("igemm_fwd_kernel");
 }
 
@@ -494,16 +537,59 @@ static int pick_bn(int64_t m_total, int n_total) {
   return 32;
 }
 
-static int launch_fwd_bn(const FwdParams& P, int bn, cudaStream_t st) {
+static int launch_fwd_bn(const FwdParams& P, int bn, bool bf16, cudaStream_t st) {
+  if (bf16) {
+    switch (bn) {
+      case 256: return launch_fwd<256, 4, true>(P, st);
+      case 128: return launch_fwd<128, 3, true>(P, st);
+      case 64: return launch_fwd<64, 4, true>(P, st);
+      default: return launch_fwd<32, 4, true>(P, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch_fwd<256, 4>(P, st);
-    case 128: return launch_fwd<128, 3>(P, st);
-    case 64: return launch_fwd<64, 4>(P, st);
-    default: return launch_fwd<32, 4>(P, st);
+    case 256: return launch_fwd<256, 4, false>(P, st);
+    case 128: return launch_fwd<128, 3, false>(P, st);
+    case 64: return launch_fwd<64, 4, false>(P, st);
+    default: return launch_fwd<32, 4, false>(P, st);
   }
 }
 
-size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
+template <int BN, int NSTAGES, bool BF16>
+static int launch_fwd_multi(const FwdParamsMulti& PM, int count, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_multi_kernel<BN, NSTAGES, BF16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  int m_max = 0;
+  for (int i = 0; i < count; ++i) m_max = PM.p[i].o.m_total > m_max ? PM.p[i].o.m_total : m_max;
+  dim3 grid((unsigned)ceil_div(m_max, kTileM), (unsigned)ceil_div(PM.p[0].o.n_total, BN), (unsigned)count);
+  igemm_fwd_multi_kernel<BN, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(PM);
+  return check_launch("igemm_fwd_multi_kernel");
+}
+
+static int launch_fwd_multi_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
+  if (bf16) {
+    switch (bn) {
+      case 256: return launch_fwd_multi<256, 4, true>(PM, count, st);
+      case 128: return launch_fwd_multi<128, 3, true>(PM, count, st);
+      case 64: return launch_fwd_multi<64, 4, true>(PM, count, st);
+      default: return launch_fwd_multi<32, 4, true>(PM, count, st);
+    }
+  }
+  switch (bn) {
+    case 256: return launch_fwd_multi<256, 4, false>(PM, count, st);
+    case 128: return launch_fwd_multi<128, 3, false>(PM, count, st);
+    case 64: return launch_fwd_multi<64, 4, false>(PM, count, st);
+    default: return launch_fwd_multi<32, 4, false>(PM, count, st);
+  }
+}
 
 static int wgrad_variant() {  // bring-up / tuning knob: 0 = default
   const char* e = getenv("TTB_WGRAD_VARIANT");
@@ -514,7 +600,8 @@ static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_p
   // 64 pixels per pipeline step: the TMA unit pays a fixed cost per box (measured: ~115 cycles + ~3 cycles per
   // 128-byte row), so few large boxes beat many small ones (KP = 32 ran the layer-1 wgrad at 89 TFLOP/s, KP = 64 at 162)
   const int variant = wgrad_variant();
-  const int KP = variant == 3 ? 32 : 64;
+  const bool bf16 = d->math_mode == TTB_MATH_BF16;
+  const int KP = (variant == 3 && !bf16) ? 32 : 64;
   const int ncols = d->r * d->s * d->c;
   *bn = ncols >= 256 ? 256 : (ncols >= 128 ? 128 : (ncols >= 64 ? 64 : 32));
   if (variant == 2 && *bn == 256) *bn = 128;
@@ -542,22 +629,25 @@ static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_p
   return KP;
 }
 
+// workspace of the igemm passes themselves (operands already in the element type of the math mode)
 size_t igemm_workspace_size(const ttb_conv_desc* d, int pass) {
-  const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * sizeof(float);
+  const size_t welems = (size_t)d->k * d->r * d->s * d->c;
   if (pass == 0) return 0;
-  if (pass == 1) return wbytes;  // repacked weights [C][R][S][K]
+  if (pass == 1) return welems * (d->math_mode == TTB_MATH_BF16 ? 2 : 4);  // repacked weights [C][R][S][K]
   int bn, splits, sps, total;
   wgrad_plan(d, &bn, &splits, &sps, &total);
-  return splits > 1 ? (size_t)splits * wbytes : 0;
+  return splits > 1 ? (size_t)splits * welems * sizeof(float) : 0;
 }
 
-int igemm_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, void* /*ws*/,
+// x, w: operands in the element type of d->math_mode (fp32 for TF32, bf16 for BF16); y, bias: fp32
+int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* /*ws*/,
                 size_t /*ws_bytes*/, cudaStream_t st) {
   if (load_driver_fns()) return 1;
+  const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   FwdParams P;
   memset(&P, 0, sizeof(P));
   const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
-  if (make_im2col_4d(&P.tmA, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, kTileM))
+  if (make_im2col_4d(&P.tmA, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, kTileM))
     return 1;
   P.o.out = y;
   P.o.n_stride = (int64_t)d->p * d->q * d->k;
@@ -569,7 +659,7 @@ int igemm_fprop(const ttb_conv_desc* d, const float* x, const float* w, const fl
   P.o.m_total = d->n * d->p * d->q;
   P.o.n_total = d->k;
   P.bias = bias;
-  P.c_blocks = d->c / kKBlock;
+  P.c_blocks = d->c / el.per_row;
   P.num_taps = d->r * d->s;
   P.base_w = -d->pad_w;
   P.base_h = -d->pad_h;
@@ -584,27 +674,37 @@ int igemm_fprop(const ttb_conv_desc* d, const float* x, const float* w, const fl
     }
   // weight matrix [K rows][R*S*C cols]; the TMA box height is the kernel's N tile
   const int bn = pick_bn(P.o.m_total, P.o.n_total);
-  if (make_tiled_2d(&P.tmB, w, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
-  return launch_fwd_bn(P, bn, st);
+  if (make_tiled_2d(&P.tmB, w, el, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
+  return launch_fwd_bn(P, bn, el.bf16, st);
 }
 
-int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, void* ws, size_t ws_bytes,
+int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
   if (load_driver_fns()) return 1;
-  const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * sizeof(float);
+  const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
+  const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * el.size;
   TTB_REQUIRE(ws != nullptr && ws_bytes >= wbytes, "conv2d_dgrad: workspace of %zu bytes needed, %zu given", wbytes, ws_bytes);
-  float* wt = reinterpret_cast<float*>(ws);
   const int T = d->r * d->s;
   {
     int64_t total = (int64_t)d->k * T * d->c;
-    repack_krsc_to_crsk_kernel<<<elementwise_grid(total, 256), 256, 0, st>>>(w, wt, d->k, T, d->c);
+    if (el.bf16)
+      repack_krsc_to_crsk_kernel<uint16_t><<<elementwise_grid(total, 256), 256, 0, st>>>(
+          reinterpret_cast<const uint16_t*>(w), reinterpret_cast<uint16_t*>(ws), d->k, T, d->c);
+    else
+      repack_krsc_to_crsk_kernel<float><<<elementwise_grid(total, 256), 256, 0, st>>>(
+          reinterpret_cast<const float*>(w), reinterpret_cast<float*>(ws), d->k, T, d->c);
     if (check_launch("repack_krsc_to_crsk")) return 1;
   }
+  const void* wt = ws;
   // Stride-parity classes: input rows h = a + sh*i only receive taps r with (a + ph - r*dh) % sh == 0, from output
   // row p = i + (a + ph - r*dh)/sh.  Each class is a stride-1 gather over dY - no zero insertion, no wasted MACs.
   bool need_zero = false;
   struct Cls { int a, b, nr, ns; int rr[kMaxTaps], ro[kMaxTaps], ss[kMaxTaps], so[kMaxTaps]; };
   static thread_local Cls cls;
+  static thread_local FwdParamsMulti PM;
+  int n_multi = 0;
+  int64_t m_all = 0;
+  const bool multi = d->stride_h * d->stride_w > 1 && d->stride_h * d->stride_w <= kMaxMulti;
   for (int pass = 0; pass < 2; ++pass) {
     for (int a = 0; a < d->stride_h; ++a)
       for (int b = 0; b < d->stride_w; ++b) {
@@ -634,9 +734,10 @@ int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* 
         const int up_h = ha - d->p + lo_h, up_w = wb - d->q + lo_w;
         TTB_REQUIRE(in_corner_range(lo_h) && in_corner_range(lo_w) && in_corner_range(up_h) && in_corner_range(up_w),
                     "conv2d_dgrad: traversal box out of TMA range");
-        FwdParams P;
+        FwdParams Pone;
+        FwdParams& P = multi ? PM.p[n_multi] : Pone;
         memset(&P, 0, sizeof(P));
-        if (make_im2col_4d(&P.tmA, dy, d->n, d->p, d->q, d->k, lo_w, lo_h, up_w, up_h, 1, 1, kTileM)) return 1;
+        if (make_im2col_4d(&P.tmA, dy, el, d->n, d->p, d->q, d->k, lo_w, lo_h, up_w, up_h, 1, 1, kTileM)) return 1;
         P.o.out = dx;
         P.o.n_stride = (int64_t)d->h * d->w * d->c;
         P.o.h_stride = (int64_t)d->stride_h * d->w * d->c;
@@ -647,7 +748,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* 
         P.o.m_total = d->n * ha * wb;
         P.o.n_total = d->c;
         P.bias = nullptr;
-        P.c_blocks = d->k / kKBlock;
+        P.c_blocks = d->k / el.per_row;
         P.num_taps = cls.nr * cls.ns;
         P.base_w = lo_w;
         P.base_h = lo_h;
@@ -659,10 +760,21 @@ int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* 
             P.off_h[t] = (uint16_t)(cls.ro[i] - lo_h);
             P.off_w[t] = (uint16_t)(cls.so[j] - lo_w);
           }
+        if (multi) {  // launched together below; the N tile is chosen for the combined grid
+          m_all += P.o.m_total;
+          ++n_multi;
+          continue;
+        }
         const int bn = pick_bn(P.o.m_total, P.o.n_total);
-        if (make_tiled_2d(&P.tmB, wt, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-        if (launch_fwd_bn(P, bn, st)) return 1;
+        if (make_tiled_2d(&P.tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
+        if (launch_fwd_bn(P, bn, el.bf16, st)) return 1;
       }
+    if (pass == 1 && n_multi > 0) {
+      const int bn = pick_bn(m_all, d->c);
+      for (int i = 0; i < n_multi; ++i)
+        if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
+      if (launch_fwd_multi_bn(PM, n_multi, bn, el.bf16, st)) return 1;
+    }
     if (pass == 0 && need_zero) {
       cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st);
       if (e != cudaSuccess) {
@@ -674,13 +786,14 @@ int igemm_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* 
   return 0;
 }
 
-template <int BN, int KP, int NSTAGES>
+template <int BN, int KP, int NSTAGES, bool BF16>
 static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NSTAGES * ((4 + BN / 32) * KP * 128) + 1024;
+  constexpr int kSlabCh = BF16 ? 64 : 32;
+  constexpr size_t smem = (size_t)NSTAGES * ((kTileM / kSlabCh + BN / kSlabCh) * KP * 128) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(igemm_wgrad_kernel<BN, KP, NSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN, KP, NSTAGES, BF16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("igemm wgrad: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return 1;
@@ -688,13 +801,14 @@ static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits
     attr_set = true;
   }
   dim3 grid(ktiles, ntiles, splits);
-  igemm_wgrad_kernel<BN, KP, NSTAGES><<<grid, kThreadsIgemm, smem, st>>>(P);
+  igemm_wgrad_kernel<BN, KP, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(P);
   return check_launch("igemm_wgrad_kernel");
 }
 
-int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
+int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st) {
   if (load_driver_fns()) return 1;
+  const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   int bn, splits, sps, total;
   const int KP = wgrad_plan(d, &bn, &splits, &sps, &total);
   const int64_t wsize = (int64_t)d->k * d->r * d->s * d->c;
@@ -704,20 +818,22 @@ int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* 
   WgradParams P;
   memset(&P, 0, sizeof(P));
   const int64_t m = (int64_t)d->n * d->p * d->q;
-  // MN-major fp32 operands: 128B-span / 32B-atom swizzle (TMA) <-> UMMA layout type 1, 4-row K groups 512 B apart,
-  // 32-channel slabs KP*128 B apart.  (TTB_WGRAD_* env overrides exist for bring-up experiments only.)
-  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  // MN-major operands.  fp32: 128B-span / 32B-atom swizzle (TMA) <-> UMMA layout type 1, 4-row K groups 512 B apart.
+  // bf16: plain 128B swizzle <-> layout type 2, 8-row K groups 1024 B apart.  128-byte-wide slabs KP*128 B apart.
+  // (TTB_WGRAD_* env overrides exist for bring-up experiments only.)
+  CUtensorMapSwizzle swz = el.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   P.desc_lbo = (uint32_t)KP * 128;
-  P.desc_sbo = 512;
-  P.desc_layout = 1;
+  P.desc_sbo = el.bf16 ? 1024 : 512;
+  P.desc_layout = el.bf16 ? 2 : 1;
   if (const char* e = getenv("TTB_WGRAD_SWIZZLE")) swz = (CUtensorMapSwizzle)atoi(e);
   if (const char* e = getenv("TTB_WGRAD_LBO")) P.desc_lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("TTB_WGRAD_SBO")) P.desc_sbo = (uint32_t)atoi(e);
   if (const char* e = getenv("TTB_WGRAD_LAYOUT")) P.desc_layout = (uint32_t)atoi(e);
-  // dY as a [pixels][K] matrix; box = KP pixel rows x 32 channels
-  if (make_tiled_2d(&P.tmDy, dy, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
+  // dY as a [pixels][K] matrix; box = KP pixel rows x 128 bytes of channels
+  if (make_tiled_2d(&P.tmDy, dy, el, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
   const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
-  if (make_im2col_4d(&P.tmX, x, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP, swz))
+  if (make_im2col_4d(&P.tmX, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP,
+                     swz))
     return 1;
   const int ncols = d->r * d->s * d->c;
   P.o.out = splits > 1 ? reinterpret_cast<float*>(ws) : dw;
@@ -747,19 +863,25 @@ int igemm_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* 
     }
   const int ktiles = (int)ceil_div(d->k, kTileM), ntiles = (int)ceil_div(ncols, bn);
   int rc;
-  if (KP == 32) {  // legacy small-box configuration, kept for A/B measurements (TTB_WGRAD_VARIANT=3)
+  if (el.bf16) {
     switch (bn) {
-      case 256: rc = launch_wgrad<256, 32, 4>(P, ktiles, ntiles, splits, st); break;
-      case 128: rc = launch_wgrad<128, 32, 4>(P, ktiles, ntiles, splits, st); break;
-      case 64: rc = launch_wgrad<64, 32, 6>(P, ktiles, ntiles, splits, st); break;
-      default: rc = launch_wgrad<32, 32, 6>(P, ktiles, ntiles, splits, st); break;
+      case 256: rc = launch_wgrad<256, 64, 4, true>(P, ktiles, ntiles, splits, st); break;
+      case 128: rc = launch_wgrad<128, 64, 6, true>(P, ktiles, ntiles, splits, st); break;
+      default: rc = launch_wgrad<64, 64, 6, true>(P, ktiles, ntiles, splits, st); break;
+    }
+  } else if (KP == 32) {  // legacy small-box configuration, kept for A/B measurements (TTB_WGRAD_VARIANT=3)
+    switch (bn) {
+      case 256: rc = launch_wgrad<256, 32, 4, false>(P, ktiles, ntiles, splits, st); break;
+      case 128: rc = launch_wgrad<128, 32, 4, false>(P, ktiles, ntiles, splits, st); break;
+      case 64: rc = launch_wgrad<64, 32, 6, false>(P, ktiles, ntiles, splits, st); break;
+      default: rc = launch_wgrad<32, 32, 6, false>(P, ktiles, ntiles, splits, st); break;
     }
   } else {
     switch (bn) {
-      case 256: rc = launch_wgrad<256, 64, 2>(P, ktiles, ntiles, splits, st); break;
-      case 128: rc = launch_wgrad<128, 64, 3>(P, ktiles, ntiles, splits, st); break;
-      case 64: rc = launch_wgrad<64, 64, 4>(P, ktiles, ntiles, splits, st); break;
-      default: rc = launch_wgrad<32, 64, 4>(P, ktiles, ntiles, splits, st); break;
+      case 256: rc = launch_wgrad<256, 64, 2, false>(P, ktiles, ntiles, splits, st); break;
+      case 128: rc = launch_wgrad<128, 64, 3, false>(P, ktiles, ntiles, splits, st); break;
+      case 64: rc = launch_wgrad<64, 64, 4, false>(P, ktiles, ntiles, splits, st); break;
+      default: rc = launch_wgrad<32, 64, 4, false>(P, ktiles, ntiles, splits, st); break;
     }
   }
   if (rc) return rc;

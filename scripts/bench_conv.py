@@ -36,7 +36,7 @@ def timeit(fn, iters=10):
 
 def main():
     variants = sys.argv[1:] or ["0"]
-    tt.set_math_mode("tf32")
+    tt.set_math_mode(os.environ.get("MATH", "tf32"))
     rng = np.random.default_rng(0)
     only = os.environ.get("ONLY")
     for name, n, c, h, w, k, ks, s, p in LAYERS:

@@ -16,6 +16,7 @@ import pytortto_b200 as tt  # noqa: E402
 from pytortto_b200 import _cabi, ops  # noqa: E402
 from pytortto_b200.xparray import cparray  # noqa: E402
 
+MODE = os.environ.get("MATH", "tf32")
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 
@@ -81,10 +82,10 @@ def main():
         for which in ("fprop", "dgrad", "wgrad"):
             ref, _ = run_pass("fp32", which, x, w, dy, s, p, d)
             t0 = time.time()
-            got, sup = run_pass("tf32", which, x, w, dy, s, p, d)
+            got, sup = run_pass(MODE, which, x, w, dy, s, p, d)
             denom = max(np.abs(ref).max(), 1e-30)
             rel = float(np.abs(got.astype(np.float64) - ref).max() / denom) if np.isfinite(got).all() else float("inf")
-            ok = rel < 2e-3
+            ok = rel < (2e-3 if MODE == "tf32" else 1e-2)
             print(f"  {which}: tensor_path={sup} rel={rel:.3e} {'OK' if ok else 'FAIL'} ({time.time() - t0:.2f}s)", flush=True)
             if not ok:
                 failed += 1
@@ -93,7 +94,7 @@ def main():
                     np.savez_compressed(os.path.join(OUT, f"diag_fail_{which}_{'_'.join(map(str, case))}.npz"), got=got,
                                         ref=ref, x=x.get(), w=w.get(), dy=dy.get())
     print("FAILED passes:", failed)
-    if failed:
+    if failed and MODE == "tf32":
         wgrad_variants()
     return 1 if failed else 0
 

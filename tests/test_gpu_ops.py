@@ -12,7 +12,7 @@ from oracle import tortto_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tf32": 2e-3}
+TOL = {"fp32": 2e-5, "tf32": 2e-3, "bf16": 1e-2}
 
 
 @pytest.fixture(autouse=True)
@@ -35,7 +35,7 @@ def _run_conv(tt, x, w, b, dy, stride, padding, dilation, groups):
     return (y.data.get(), xin.grad.get(), conv_w.grad.get(), None if b is None else conv_b.grad.get())
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("name", cases_of(load_golden("conv2d.npz")))
 def test_conv2d_golden(name, mode):
     tt = _tt(mode)
@@ -69,9 +69,10 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[f"n{c[0]}_c{c[1]}_{c[2]}x{c[3]}_k{c[4]}_f{c[5]}s{c[6]}p{c[7]}d{c[8]}" for c in TC_CASES])
-def test_conv2d_tensor_path_vs_oracle(case):
-    tt = _tt("tf32")
+def test_conv2d_tensor_path_vs_oracle(case, mode):
+    tt = _tt(mode)
     n, ci, h, w, co, k, s, p, d = case
     rng = np.random.default_rng(hash(case) % (2 ** 31))
     x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
@@ -85,11 +86,14 @@ def test_conv2d_tensor_path_vs_oracle(case):
     desc = ops.conv_desc(x.shape, wt.shape, (s, s), (p, p), (d, d), 1)
     used = [_cabi.load().ttb_conv2d_tensor_path_supported(ctypes.byref(desc), i) for i in range(3)]
     print("tensor path used (fprop, dgrad, wgrad):", used)
-    # dgrad contracts over output channels: its tensor path needs Cout % 32 == 0 (else the exact direct kernel runs)
-    assert used == [1, 1 if co % 32 == 0 else 0, 1], "this case is meant to exercise the tcgen05 path"
-    assert_close("y", y, yo, 2e-3)
-    assert_close("dx", dx, dxo, 2e-3)
-    assert_close("dw", dw, dwo, 2e-3)
+    # dgrad contracts over output channels: its tensor path needs Cout % 32 (tf32) / % 64 (bf16) == 0, otherwise the
+    # exact direct kernel runs; fprop / wgrad pad the input channels when needed
+    blk = 32 if mode == "tf32" else 64
+    assert used == [1, 1 if co % blk == 0 else 0, 1], "this case is meant to exercise the tcgen05 path"
+    tol = TOL[mode]
+    assert_close("y", y, yo, tol)
+    assert_close("dx", dx, dxo, tol)
+    assert_close("dw", dw, dwo, tol)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
