@@ -242,18 +242,30 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
+    launches0 = _cabi.launch_count
+    step(x_dev, y_dev)
+    launches = _cabi.launch_count - launches0  # kernels-launching C-ABI calls of ONE step (same count when replayed)
+    use_graph = args.graph and world == 1
+    if use_graph:
+        # the whole step (fwd + loss + bwd + SGD, ~270 kernels) recorded once and replayed with one driver call
+        graphed = tt.cuda_graph.GraphedStep(step, (x_dev, y_dev), modules=[net])
+        run_resident = lambda: graphed(*graphed.static_inputs)
+        run_from = graphed
+    else:
+        run_resident = lambda: step(x_dev, y_dev)
+        run_from = step
+    for _ in range(3):
+        run_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _cabi.launch_count
-    ms_total = timed(lambda: step(x_dev, y_dev), args.steps)
-    launches = (_cabi.launch_count - launches0) // max(1, args.steps)
+    ms_total = timed(run_resident, args.steps)
 
     # end to end: host batch -> pinned H2D + layout kernel -> step -> loss.item() (D2H) every step
     def e2e_step():
-        xb = tt.tensor(x_host.numpy()).cuda()
-        yb = tt.tensor(y_host.numpy(), dtype=np.int64).cuda()
-        return step(xb, yb).item()
+        xb = tt.tensor(x_host.numpy(), copy=False).cuda()
+        yb = tt.tensor(y_host.numpy(), dtype=np.int64, copy=False).cuda()
+        return run_from(xb, yb).item()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
@@ -284,7 +296,7 @@ def run_ours(args):
         "config": {"workload": f"{args.model} CIFAR-shaped 3x{hw}x{hw} training step (fwd+loss+bwd+SGD), batch {B} per GPU",
                    "global_batch": B * world, "parallelism": f"dp{world}" + ("+syncbn" if world > 1 else ""),
                    "l2": "per-step working set (~2.5 GB of activations at batch 256) >> 126 MB L2; no explicit flush",
-                   "math": args.math},
+                   "math": args.math, "cuda_graph": bool(use_graph)},
         "conv_tflops": achieved_tf,
         "conv_tflops_step_share": conv_ms / (prof["step_ms"] or 1.0),
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -298,7 +310,8 @@ def run_ours(args):
                          "sample": f"1 step of batch 16 ({cpu_s:.1f} s) of the same model, numpy oracle"},
         "e2e": {"value": e2e_img_s, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
         "clocks": clocks,
         "family_ms_per_step": prof,
     }
@@ -350,6 +363,7 @@ def main():
     ap.add_argument("--model", default="preact_resnet18", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--math", default="tf32", choices=["tf32", "bf16", "fp32"])
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph (single GPU), 0: eager")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,6 +17,7 @@ from .autograd.grad_nn import set_maxpool_backward_accumulate
 from . import nn
 from . import optim
 from . import distributed
+from . import cuda_graph
 from .serialization import save, load
 
 

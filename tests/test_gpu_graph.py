@@ -1,0 +1,52 @@
+"""GPU: a CUDA-graph replay of the training step (pytortto_b200.cuda_graph.GraphedStep) is bit-identical to the
+eager step - same parameters, momentum buffers and BN statistics after several steps on changing inputs."""
+import numpy as np
+import pytest
+
+from gpu_util import require_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(graphed_mode):
+    import pytortto_b200 as tt
+    from pytortto_b200.examples import make_models
+    tt.set_math_mode("tf32")
+    M = make_models(tt)
+    tt.manual_seed(9)
+    net = M["PreactResNet"](M["BasicBlock"], [1, 1, 1, 1], [32, 32, 64, 64]).cuda()
+    opt = tt.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    crit = tt.nn.NLLLoss()
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    rng = np.random.default_rng(9)
+    batches = [(rng.standard_normal((16, 3, 16, 16)).astype(np.float32), rng.integers(0, 10, 16).astype(np.int64))
+               for _ in range(8)]
+    dev = [(tt.tensor(x).cuda(), tt.tensor(y, dtype=np.int64).cuda()) for x, y in batches]
+    losses = []
+    if graphed_mode:
+        # GraphedStep runs 3 eager warm-up steps on its example inputs (batch 0); the recording itself executes nothing
+        g = tt.cuda_graph.GraphedStep(step, dev[0], modules=[net], warmup=3)
+        for x, y in dev[1:5]:
+            losses.append(g(x, y).item())
+    else:
+        for _ in range(3):
+            step(*dev[0])
+        for x, y in dev[1:5]:
+            losses.append(step(x, y).item())
+    return losses, net.state_dict()
+
+
+def test_graphed_step_matches_eager():
+    require_gpu()
+    eager_losses, eager_sd = _run(False)
+    graph_losses, graph_sd = _run(True)
+    assert eager_losses == graph_losses
+    for k in eager_sd:
+        np.testing.assert_array_equal(eager_sd[k], graph_sd[k], err_msg=k)
