@@ -135,6 +135,21 @@ int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* 
                        const int64_t* sizes, const unsigned char* first_step, float lr, float momentum, float dampening,
                        float weight_decay, int nesterov, void* stream);
 
+/* ---- small-message all-reduce over NVLink peer memory (SyncBN statistics; one process per GPU) ------------------- */
+/* cudaMalloc a zeroed communication buffer and export its CUDA-IPC handle (64 bytes) */
+int ttb_comm_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);
+/* map a peer's buffer into this process (peer access is enabled lazily) */
+int ttb_comm_open(const unsigned char* handle, void** peer_ptr);
+int ttb_comm_close(void* peer_ptr);
+int ttb_comm_free(void* dev_ptr);
+/* bytes of one slot holding up to max_values doubles (header + data) */
+size_t ttb_comm_slot_bytes(int max_values);
+/* sum partials[num_chunks][n] (fixed order) into this rank's slot at my_buf + slot_offset and bump the slot's flag */
+int ttb_comm_publish(const double* partials, int num_chunks, int n, void* my_buf, size_t slot_offset, void* stream);
+/* wait until every peer published the slot as often as this rank, then out[i] = sum over ranks (rank order) of their
+ * slot data, read over NVLink.  peers_dev: DEVICE array of `world` mapped buffer bases (own buffer at index rank). */
+int ttb_comm_gather(void* const* peers_dev, int world, int rank, size_t slot_offset, int n, double* out, void* stream);
+
 /* ---- max pool --------------------------------------------------------------------------------------------- */
 /* y[N,P,Q,C] = max over window (padding acts as -inf); idx[N,P,Q,C] (uint8) = r*kw+s of the FIRST maximum in
  * row-major window order (two-stage nanargmax of the reference) */

@@ -57,6 +57,13 @@ _PROTOS = {
     "ttb_sgd_step": (c_int, [_F, _F, _F, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, c_void_p]),
     "ttb_sgd_step_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_float, c_int, c_void_p]),
+    "ttb_comm_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "ttb_comm_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "ttb_comm_close": (c_int, [c_void_p]),
+    "ttb_comm_free": (c_int, [c_void_p]),
+    "ttb_comm_slot_bytes": (c_size_t, [c_int]),
+    "ttb_comm_publish": (c_int, [_F, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ttb_comm_gather": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, _F, c_void_p]),
     "ttb_maxpool2d_fwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_void_p]),
     "ttb_maxpool2d_bwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_int, c_void_p]),
 }

@@ -228,7 +228,8 @@ class _BatchNormBase(Function):
         gamma = None if xt1 is None else xt1.data
         beta = None if xt2 is None else xt2.data
         from .. import distributed as dist
-        hook = dist.bn_forward_hook() if training else None
+        ident = xt1 if xt1 is not None else running_mean  # a stable per-layer object keys the SyncBN slot
+        hook = dist.bn_forward_hook(None if ident is None else (id(ident), 'f')) if training else None
         relu = cls._fuse_relu
         if training:
             _verify_batch_size(xd0.shape)
@@ -245,7 +246,8 @@ class _BatchNormBase(Function):
             ctx.save_for_backward(xt0, xt1, yt0)
         else:
             ctx.save_for_backward(xt0, xt1)
-        ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None}
+        ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None,
+                      'sync_key': None if ident is None else (id(ident), 'b')}
         return yt0
 
     @classmethod
@@ -254,7 +256,7 @@ class _BatchNormBase(Function):
         xd0, xd1 = saved[0], saved[1]
         relu_out = saved[2] if cls._fuse_relu else None
         from .. import distributed as dist
-        hook = dist.bn_backward_hook() if ctx.params['synced'] else None
+        hook = dist.bn_backward_hook(ctx.params['sync_key']) if ctx.params['synced'] else None
         return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'], relu_out=relu_out,
                                need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
                                need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook)

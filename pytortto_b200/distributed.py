@@ -27,7 +27,7 @@ import torch
 
 from .autograd.function import AccumulateGrad
 
-_state = {"initialized": False, "world": 1, "rank": 0, "sync_bn": True, "backend": None}
+_state = {"initialized": False, "world": 1, "rank": 0, "sync_bn": True, "backend": None, "peer_comm": None}
 
 
 def is_initialized():
@@ -52,7 +52,14 @@ def init_process_group(backend=None, sync_bn=True):
             torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group(backend=backend)
     _state.update(initialized=True, world=dist.get_world_size(), rank=dist.get_rank(), sync_bn=bool(sync_bn),
-                  backend=backend)
+                  backend=backend, peer_comm=None)
+    if backend == "nccl" and sync_bn and _state["world"] > 1 and os.environ.get("TORTTO_B200_PEER_COMM", "1") != "0":
+        try:
+            enable_peer_comm()
+        except RuntimeError as e:  # CUDA IPC not permitted between these processes: keep the NCCL path
+            import warnings
+            warnings.warn(f"peer-memory SyncBN path unavailable ({e}); using NCCL all-reduce")
+            _state["peer_comm"] = None
     return _state["rank"], _state["world"]
 
 
@@ -60,7 +67,7 @@ def destroy_process_group():
     import torch.distributed as dist
     if dist.is_initialized():
         dist.destroy_process_group()
-    _state.update(initialized=False, world=1, rank=0)
+    _state.update(initialized=False, world=1, rank=0, peer_comm=None)
 
 
 def all_reduce_sum_(t, async_op=False):
@@ -71,22 +78,104 @@ def all_reduce_sum_(t, async_op=False):
     return None
 
 
-# ---- SyncBN hooks (called from ops.bn_forward_train / ops.bn_backward) ------------------------------------
+# ---- SyncBN statistic exchange (called from ops.bn_forward_train / ops.bn_backward) ---------------------------
+class PeerComm:
+    """Small-message all-reduce over NVLink peer memory (csrc/comm.cu): every rank owns a cudaMalloc'ed buffer of
+    fixed slots, exported through CUDA IPC and mapped by every peer.  A call site (BatchNorm layer x direction) owns
+    one slot for the life of the process, so replays of a captured CUDA graph keep working."""
+    MAX_VALUES = 2 * 4096   # 2C doubles, C <= 4096
+    SLOTS = 512
+
+    def __init__(self):
+        import ctypes
+        import torch.distributed as dist
+        from . import _cabi
+        self._cabi, self._ct = _cabi, ctypes
+        lib = _cabi.load()
+        self.world, self.rank = _state["world"], _state["rank"]
+        self.slot_bytes = (int(lib.ttb_comm_slot_bytes(self.MAX_VALUES)) + 255) // 256 * 256
+        nbytes = self.slot_bytes * self.SLOTS
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _cabi.call("ttb_comm_alloc", nbytes, ctypes.byref(ptr), handle)
+        self.own = ptr.value
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        bases = []
+        self._opened = []
+        for r, h in enumerate(gathered):
+            if r == self.rank:
+                bases.append(self.own)
+                continue
+            hb = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
+            pp = ctypes.c_void_p()
+            _cabi.call("ttb_comm_open", hb, ctypes.byref(pp))
+            bases.append(pp.value)
+            self._opened.append(pp.value)
+        self.peers_dev = torch.tensor(bases, dtype=torch.int64, device="cuda")
+        self.slots = {}
+        dist.barrier()
+
+    def slot_offset(self, key):
+        idx = self.slots.get(key)
+        if idx is None:
+            idx = len(self.slots)
+            if idx >= self.SLOTS:
+                raise RuntimeError("PeerComm: out of SyncBN slots")
+            self.slots[key] = idx
+        return idx * self.slot_bytes
+
+    def all_reduce_partials(self, partials, chunks, n, key):
+        """partials [chunks][n] doubles (this rank) -> [n] doubles summed over chunks and ranks (rank order)."""
+        if n > self.MAX_VALUES:
+            return None
+        off = self.slot_offset(key)
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.empty((n,), dtype=torch.float64, device=partials.device)
+        self._cabi.call("ttb_comm_publish", partials.data_ptr(), chunks, n, self.own, off, st)
+        self._cabi.call("ttb_comm_gather", self.peers_dev.data_ptr(), self.world, self.rank, off, n, out.data_ptr(), st)
+        return out
+
+
 def _sync_bn_active():
     return _state["initialized"] and _state["world"] > 1 and _state["sync_bn"]
 
 
-def _stat_hook(sums, local_count):
-    all_reduce_sum_(sums)
-    return local_count * _state["world"]  # equal shards by construction (shard_batch)
+def _make_stat_hook(key):
+    def hook(partials, chunks, n, local_count):
+        comm = _state.get("peer_comm")
+        sums = None
+        if comm is not None and key is not None and partials.is_cuda:
+            sums = comm.all_reduce_partials(partials, chunks, n, key)
+        if sums is None:  # generic path: collapse the chunks locally, then a library all-reduce (NCCL / gloo)
+            sums = partials.reshape(chunks, n).sum(dim=0) if not partials.is_cuda else _collapse(partials, chunks, n)
+            all_reduce_sum_(sums)
+        return sums, local_count * _state["world"]  # equal shards by construction (shard_batch)
+    return hook
 
 
-def bn_forward_hook():
-    return _stat_hook if _sync_bn_active() else None
+def _collapse(partials, chunks, n):
+    from . import _cabi
+    sums = torch.empty((n,), dtype=torch.float64, device=partials.device)
+    _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, n, sums.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+    return sums
 
 
-def bn_backward_hook():
-    return _stat_hook if _sync_bn_active() else None
+def bn_forward_hook(key=None):
+    return _make_stat_hook(key) if _sync_bn_active() else None
+
+
+def bn_backward_hook(key=None):
+    return _make_stat_hook(key) if _sync_bn_active() else None
+
+
+def enable_peer_comm():
+    """Switch the SyncBN statistic exchange to the NVLink peer-memory path (needs CUDA IPC between the ranks)."""
+    if _state.get("peer_comm") is None and _state["initialized"] and _state["world"] > 1 and _state["backend"] == "nccl":
+        _state["peer_comm"] = PeerComm()
+    return _state.get("peer_comm") is not None
 
 
 def shard_batch(*arrays):

@@ -123,7 +123,7 @@ def _rows_channels(x):
 def bn_sums(x, reduce_hook=None):
     """per-channel sum(x), sum(x^2) as double partials [chunks][2][C] -> (buffer, chunks, count).  Without a hook
     the per-chunk partials go straight to the finalize kernel (which sums them in fixed order); with a hook
-    (SyncBN) they are first collapsed to [2][C] and `reduce_hook(t, count)` all-reduces that tensor in place."""
+    (SyncBN) `reduce_hook(partials, chunks, 2C, count)` returns the cross-rank [2][C] sums and the global count."""
     m, c = _rows_channels(x)
     chunks = _cabi.load().ttb_bn_num_chunks(m, c)
     partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
@@ -131,9 +131,7 @@ def bn_sums(x, reduce_hook=None):
     _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
     if reduce_hook is None:
         return partials, chunks, m
-    sums = torch.empty((2, c), dtype=torch.float64, device=x.t.device)
-    _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
-    m = reduce_hook(sums, m)
+    sums, m = reduce_hook(partials, chunks, 2 * c, m)
     return sums, 1, m
 
 
@@ -178,9 +176,7 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     if reduce_hook is None:
         sums, nchunks = partials, chunks
     else:
-        sums, nchunks = torch.empty((2, c), dtype=torch.float64, device=x.t.device), 1
-        _cabi.call("ttb_bn_reduce_partials", partials.data_ptr(), chunks, 2 * c, sums.data_ptr(), st)
-        reduce_hook(sums, m)
+        (sums, _), nchunks = reduce_hook(partials, chunks, 2 * c, m), 1
     dgamma = new_f32((c,)) if need_dgamma else None
     dbeta = new_f32((c,)) if need_dbeta else None
     coef = new_f32((3, c))

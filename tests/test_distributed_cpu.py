@@ -41,9 +41,13 @@ def _worker(rank, world, port, q):
         # ---- SyncBN statistics: all-reduced double sums == global-batch statistics (oracle) ----------------------
         hook = dist.bn_forward_hook()
         assert hook is not None
-        sums = torch.from_numpy(np.stack([xs.sum((0, 2, 3), dtype=np.float64), (xs.astype(np.float64) ** 2).sum((0, 2, 3))]))
-        count = hook(sums, xs.shape[0] * 25)
-        assert count == 8 * 25
+        # two per-chunk partial rows per rank, like the stats kernel emits them: [chunks][2C]
+        halves = [xs[:2], xs[2:]]
+        partials = torch.from_numpy(np.stack([np.concatenate([h.sum((0, 2, 3), dtype=np.float64),
+                                                              (h.astype(np.float64) ** 2).sum((0, 2, 3))]) for h in halves]))
+        sums, count = hook(partials, 2, 12, xs.shape[0] * 25)
+        assert count == 8 * 25 and tuple(sums.shape) == (12,)
+        sums = sums.reshape(2, 6)
         mean = sums[0].numpy() / count
         var = sums[1].numpy() / count - mean ** 2
         _, rm, rv, saved = O.batch_norm_forward(x, None, None, np.zeros(6, np.float32), np.ones(6, np.float32), True, 0.1, 1e-5)
