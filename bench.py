@@ -245,9 +245,10 @@ def run_ours(args):
     launches0 = _cabi.launch_count
     step(x_dev, y_dev)
     launches = _cabi.launch_count - launches0  # kernels-launching C-ABI calls of ONE step (same count when replayed)
-    use_graph = bool(args.graph) and (world == 1 or args.graph >= 2)
+    use_graph = bool(args.graph)
     if use_graph:
-        # the whole step (fwd + loss + bwd + SGD, ~270 kernels) recorded once and replayed with one driver call
+        # the whole step (fwd + loss + bwd [+ NCCL gradient buckets, peer-memory SyncBN] + SGD, ~270 kernels) recorded
+        # once and replayed with one driver call
         graphed = tt.cuda_graph.GraphedStep(step, (x_dev, y_dev), modules=[net])
         run_resident = lambda: graphed(*graphed.static_inputs)
         run_from = graphed
@@ -363,7 +364,7 @@ def main():
     ap.add_argument("--model", default="preact_resnet18", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--math", default="tf32", choices=["tf32", "bf16", "fp32"])
-    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph (single GPU), 2: also when data-parallel, 0: eager")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph, 0: eager dispatch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
