@@ -24,6 +24,10 @@ struct ColGeom {
   int64_t rows_per_chunk;
 };
 
+// resident CTAs per SM of the column-reduce kernels (smallest over the variants), queried once: the grid is sized to
+// ONE full wave so no SM idles through a partial second wave
+static int col_reduce_ctas_per_sm();
+
 static ColGeom col_geom(int64_t m, int c) {
   ColGeom g;
   int cq = (c + 3) / 4;
@@ -34,8 +38,8 @@ static ColGeom col_geom(int64_t m, int c) {
   g.qblocks = (cq + tx - 1) / tx;
   int64_t rows_per_chunk = (int64_t)g.ty * kRowsPerThread;
   int64_t chunks = ceil_div(m, rows_per_chunk);
-  // keep the partial buffer and the finalize loop small: at most ~8 CTAs per SM worth of chunks
-  int64_t cap = (int64_t)sm_count() * 4 / g.qblocks;
+  // one wave: at most (SMs x resident CTAs per SM) CTAs in total
+  int64_t cap = (int64_t)sm_count() * col_reduce_ctas_per_sm() / g.qblocks;
   if (cap < 1) cap = 1;
   if (chunks > cap) {
     chunks = cap;
@@ -173,6 +177,19 @@ __device__ __forceinline__ double chunk_sum(const double* __restrict__ partials,
     for (int j = 0; j < kLanes; ++j) t += sm[j][threadIdx.x];
   __syncthreads();
   return t;
+}
+
+static int col_reduce_ctas_per_sm() {
+  static int cached = 0;
+  if (cached == 0) {
+    int best = 8;
+    const size_t smem = sizeof(float4) * 2 * kBnThreads;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, col_reduce_kernel<0, true>, kBnThreads, smem) == cudaSuccess && n > 0 && n < best) best = n;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, col_reduce_kernel<1, true>, kBnThreads, smem) == cudaSuccess && n > 0 && n < best) best = n;
+    cached = best;
+  }
+  return cached;
 }
 
 __global__ void __launch_bounds__(1024)

@@ -46,10 +46,18 @@ comm_publish_kernel(const double* __restrict__ partials, int num_chunks, int n, 
   SlotHeader* hdr = reinterpret_cast<SlotHeader*>(slot);
   double* data = reinterpret_cast<double*>(slot + kSlotHeaderBytes);
   const int i = blockIdx.x * 32 + threadIdx.x;
-  double s = 0.0;
-  if (i < n)
-    for (int k = threadIdx.y; k < num_chunks; k += 32) s += partials[(int64_t)k * n + i];
-  sm[threadIdx.y][threadIdx.x] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four loads in flight per thread (the loop is latency-bound)
+  if (i < n) {
+    int k = threadIdx.y;
+    for (; k + 96 < num_chunks; k += 128) {
+      s0 += partials[(int64_t)k * n + i];
+      s1 += partials[(int64_t)(k + 32) * n + i];
+      s2 += partials[(int64_t)(k + 64) * n + i];
+      s3 += partials[(int64_t)(k + 96) * n + i];
+    }
+    for (; k < num_chunks; k += 32) s0 += partials[(int64_t)k * n + i];
+  }
+  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
     double t = 0.0;
@@ -72,26 +80,25 @@ comm_publish_kernel(const double* __restrict__ partials, int num_chunks, int n, 
 __global__ void __launch_bounds__(256)
 comm_gather_kernel(char* const* __restrict__ peers, int world, int rank, size_t slot_offset, int n,
                    double* __restrict__ out, unsigned long long spin_limit) {
-  __shared__ int ok;
-  if (threadIdx.x == 0) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  // one thread per peer polls that peer's flag (all NVLink round trips in flight at once)
+  for (int r = threadIdx.x; r < world; r += blockDim.x) {
+    if (r == rank) continue;
     const unsigned long long want = ld_acquire_sys(&reinterpret_cast<const SlotHeader*>(peers[rank] + slot_offset)->flag);
-    int good = 1;
-    for (int r = 0; r < world && good; ++r) {
-      if (r == rank) continue;
-      const unsigned long long* f = &reinterpret_cast<const SlotHeader*>(peers[r] + slot_offset)->flag;
-      unsigned long long spins = 0;
-      while (ld_acquire_sys(f) < want) {
-        if (++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly instead of hanging the GPU
-          good = 0;
-          break;
-        }
-        __nanosleep(64);
+    const unsigned long long* f = &reinterpret_cast<const SlotHeader*>(peers[r] + slot_offset)->flag;
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(f) < want) {
+      if (++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly instead of hanging the GPU
+        atomicExch(&bad, 1);
+        break;
       }
+      __nanosleep(32);
     }
-    ok = good;
   }
   __syncthreads();
-  if (!ok) __trap();
+  if (bad) __trap();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double t = 0.0;

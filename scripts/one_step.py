@@ -6,6 +6,7 @@ import pytortto_b200 as tt
 from pytortto_b200.examples import make_models
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+tt.set_math_mode(os.environ.get("MATH", "tf32"))
 M = make_models(tt)
 tt.manual_seed(0)
 net = M["preact_resnet18"]().cuda()
