@@ -144,11 +144,11 @@ int ttb_comm_close(void* peer_ptr);
 int ttb_comm_free(void* dev_ptr);
 /* bytes of one slot holding up to max_values doubles (header + data) */
 size_t ttb_comm_slot_bytes(int max_values);
-/* sum partials[num_chunks][n] (fixed order) into this rank's slot at my_buf + slot_offset and bump the slot's flag */
-int ttb_comm_publish(const double* partials, int num_chunks, int n, void* my_buf, size_t slot_offset, void* stream);
-/* wait until every peer published the slot as often as this rank, then out[i] = sum over ranks (rank order) of their
- * slot data, read over NVLink.  peers_dev: DEVICE array of `world` mapped buffer bases (own buffer at index rank). */
-int ttb_comm_gather(void* const* peers_dev, int world, int rank, size_t slot_offset, int n, double* out, void* stream);
+/* out[i] = sum over ranks (rank order) of sum over chunks of that rank's partials[chunk][i], exchanged through the
+ * slot at `slot_offset` of every rank's buffer.  peers_dev: DEVICE array of `world` mapped buffer bases (own buffer at
+ * index `rank`).  One kernel, one NVLink round trip; every rank must call it for the same slot the same number of times. */
+int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,
+                       size_t slot_offset, double* out, void* stream);
 
 /* ---- max pool --------------------------------------------------------------------------------------------- */
 /* y[N,P,Q,C] = max over window (padding acts as -inf); idx[N,P,Q,C] (uint8) = r*kw+s of the FIRST maximum in

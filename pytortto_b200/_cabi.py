@@ -62,8 +62,7 @@ _PROTOS = {
     "ttb_comm_close": (c_int, [c_void_p]),
     "ttb_comm_free": (c_int, [c_void_p]),
     "ttb_comm_slot_bytes": (c_size_t, [c_int]),
-    "ttb_comm_publish": (c_int, [_F, c_int, c_int, c_void_p, c_size_t, c_void_p]),
-    "ttb_comm_gather": (c_int, [c_void_p, c_int, c_int, c_size_t, c_int, _F, c_void_p]),
+    "ttb_comm_allreduce": (c_int, [_F, c_int, c_int, c_void_p, c_int, c_int, c_size_t, _F, c_void_p]),
     "ttb_maxpool2d_fwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_void_p]),
     "ttb_maxpool2d_bwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_int, c_void_p]),
 }

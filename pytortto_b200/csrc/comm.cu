@@ -5,13 +5,12 @@
 // stream.  Here every rank owns a communication buffer (cudaMalloc + CUDA IPC, mapped into every peer) made of
 // fixed "slots" {flag, arrive counter, data[]}; a call site (one BatchNorm layer, forward or backward) always uses
 // the same slot, so nothing but device memory changes between steps (CUDA-graph safe).
-//   publish : sum this rank's per-chunk partials (fixed order) into its own slot, then flag = flag + 1
-//             (last-arriving block, release at system scope)
-//   gather  : wait until every peer's flag for that slot has reached this rank's own flag, then add the peers' data
-//             IN RANK ORDER (bit-identical result on every rank) straight over NVLink (peer loads bypass L1) into a
-//             local [n] buffer that the ordinary bn finalize kernels consume.
+// One kernel per exchange (comm_allreduce_kernel below): sum this rank's per-chunk partials, write the result into its
+// own slot as self-validating 8-byte words {sequence | 32 data bits}, poll the same words of every peer over NVLink
+// (peer loads bypass L1) and add them IN RANK ORDER (bit-identical result on every rank) into a local [n] buffer that
+// the ordinary bn finalize kernels consume.
 // Why reuse of a slot is safe: a rank reaches the same call site again only after every peer has passed all the
-// call sites in between, each of which needed this rank's later publishes, which are stream-ordered after its gather.
+// call sites in between, each of which needed this rank's later exchanges, which are stream-ordered after this one.
 #include <string.h>
 
 #include "common.cuh"
@@ -19,32 +18,41 @@
 namespace ttb {
 
 struct SlotHeader {
-  unsigned long long flag;    // number of publishes completed on this slot (monotonic)
-  unsigned int arrive;        // block arrival counter of the running publish
-  unsigned int pad;
+  unsigned int seq;           // number of exchanges completed on this slot (owner-written)
+  unsigned int arrive;        // block arrival counter of the running exchange
+  unsigned int pad[2];
 };
 constexpr size_t kSlotHeaderBytes = 16;
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double ld_volatile_f64(const double* p) {
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// grid = ceil(n / 32) blocks of (32 values x 32 chunk lanes)
+constexpr int kMaxWorld = 16;
+
+// ONE kernel per exchange, one NVLink round trip ("LL" style: every 8-byte word carries its own sequence number, so
+// the data is its own flag and no fence / separate flag write is needed; aligned 8-byte accesses are atomic).
+//   value i of this rank  = sum over chunks of partials[chunk][i]            (fixed order)
+//   own slot word pair i  = {seq | low 32 bits}, {seq | high 32 bits}
+//   out[i]                = sum over ranks r = 0..world-1 of rank r's value i (rank order => same bits everywhere)
+// grid = ceil(n / 32) blocks of (32 values x 32 chunk lanes); peers[r] = rank r's buffer mapped in this process.
 __global__ void __launch_bounds__(1024)
-comm_publish_kernel(const double* __restrict__ partials, int num_chunks, int n, char* slot) {
+comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n, char* const* __restrict__ peers,
+                      int world, int rank, size_t slot_offset, double* __restrict__ out, unsigned long long spin_limit) {
   __shared__ double sm[32][33];
-  SlotHeader* hdr = reinterpret_cast<SlotHeader*>(slot);
-  double* data = reinterpret_cast<double*>(slot + kSlotHeaderBytes);
+  char* own = peers[rank] + slot_offset;
+  SlotHeader* hdr = reinterpret_cast<SlotHeader*>(own);
+  const unsigned int seq = ld_volatile_u32(&hdr->seq) + 1u;  // every block reads it before any block can finish last
   const int i = blockIdx.x * 32 + threadIdx.x;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // four loads in flight per thread (the loop is latency-bound)
   if (i < n) {
@@ -59,52 +67,52 @@ comm_publish_kernel(const double* __restrict__ partials, int num_chunks, int n, 
   }
   sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
+  bool failed = false;
   if (threadIdx.y == 0 && i < n) {
-    double t = 0.0;
-    for (int j = 0; j < 32; ++j) t += sm[j][threadIdx.x];
-    data[i] = t;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
-    unsigned int ticket = atomicAdd(&hdr->arrive, 1u);
-    if (ticket == gridDim.x - 1) {  // every block's data is written and fenced: publish
-      hdr->arrive = 0;
-      __threadfence_system();
-      st_release_sys(&hdr->flag, hdr->flag + 1ull);
-    }
-  }
-}
-
-// peers[r] = base of rank r's communication buffer as mapped in THIS process (peers[rank] = own buffer)
-__global__ void __launch_bounds__(256)
-comm_gather_kernel(char* const* __restrict__ peers, int world, int rank, size_t slot_offset, int n,
-                   double* __restrict__ out, unsigned long long spin_limit) {
-  __shared__ int bad;
-  if (threadIdx.x == 0) bad = 0;
-  __syncthreads();
-  // one thread per peer polls that peer's flag (all NVLink round trips in flight at once)
-  for (int r = threadIdx.x; r < world; r += blockDim.x) {
-    if (r == rank) continue;
-    const unsigned long long want = ld_acquire_sys(&reinterpret_cast<const SlotHeader*>(peers[rank] + slot_offset)->flag);
-    const unsigned long long* f = &reinterpret_cast<const SlotHeader*>(peers[r] + slot_offset)->flag;
+    double mine = 0.0;
+    for (int j = 0; j < 32; ++j) mine += sm[j][threadIdx.x];
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + kSlotHeaderBytes) + 2 * (size_t)i;
+    st_volatile_u64(w, tag | (bits & 0xffffffffull));
+    st_volatile_u64(w + 1, tag | (bits >> 32));
+    double vals[kMaxWorld];
+    unsigned int pending = 0;
+    for (int r = 0; r < world; ++r)
+      if (r != rank) pending |= 1u << r;
+    vals[rank] = mine;
     unsigned long long spins = 0;
-    while (ld_acquire_sys(f) < want) {
-      if (++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly instead of hanging the GPU
-        atomicExch(&bad, 1);
+    while (pending) {
+      for (int r = 0; r < world; ++r) {
+        if (!(pending >> r & 1u)) continue;
+        const unsigned long long* pw =
+            reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes) + 2 * (size_t)i;
+        const unsigned long long a = ld_volatile_u64(pw), b = ld_volatile_u64(pw + 1);
+        if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) {
+          vals[r] = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+          pending &= ~(1u << r);
+        }
+      }
+      if (pending && ++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly, do not hang
+        failed = true;
         break;
       }
-      __nanosleep(32);
+    }
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += vals[r];
+    out[i] = acc;
+  }
+  if (failed) __trap();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&hdr->arrive, 1u);
+    if (ticket == gridDim.x - 1) {  // last block of this exchange: the slot's sequence number advances
+      hdr->arrive = 0;
+      __threadfence();
+      hdr->seq = seq;
     }
   }
-  __syncthreads();
-  if (bad) __trap();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double t = 0.0;
-  for (int r = 0; r < world; ++r)  // fixed rank order: the same bits on every rank
-    t += ld_volatile_f64(reinterpret_cast<const double*>(peers[r] + slot_offset + kSlotHeaderBytes) + i);
-  out[i] = t;
 }
 
 }  // namespace ttb
@@ -163,21 +171,17 @@ int ttb_comm_free(void* dev_ptr) {
   return 0;
 }
 
-size_t ttb_comm_slot_bytes(int max_values) { return kSlotHeaderBytes + (size_t)max_values * sizeof(double); }
+size_t ttb_comm_slot_bytes(int max_values) { return kSlotHeaderBytes + (size_t)max_values * 16; }
 
-int ttb_comm_publish(const double* partials, int num_chunks, int n, void* my_buf, size_t slot_offset, void* stream) {
-  TTB_REQUIRE(partials && my_buf && n > 0 && num_chunks > 0, "comm_publish: bad arguments");
-  comm_publish_kernel<<<(n + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(partials, num_chunks, n,
-                                                                             reinterpret_cast<char*>(my_buf) + slot_offset);
-  return check_launch("comm_publish");
-}
-
-int ttb_comm_gather(void* const* peers_dev, int world, int rank, size_t slot_offset, int n, double* out, void* stream) {
-  TTB_REQUIRE(peers_dev && out && n > 0 && world > 0 && rank >= 0 && rank < world, "comm_gather: bad arguments");
-  // >= 100 ns per probe: give a missing peer about a minute before trapping
-  comm_gather_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(reinterpret_cast<char* const*>(peers_dev), world, rank,
-                                                                     slot_offset, n, out, 600000000ull);
-  return check_launch("comm_gather");
+int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,
+                       size_t slot_offset, double* out, void* stream) {
+  TTB_REQUIRE(partials && peers_dev && out && n > 0 && num_chunks > 0, "comm_allreduce: bad arguments");
+  TTB_REQUIRE(world > 0 && world <= kMaxWorld && rank >= 0 && rank < world, "comm_allreduce: world size %d not in 1..%d", world,
+              kMaxWorld);
+  // about a minute of polling before a missing peer is declared lost
+  comm_allreduce_kernel<<<(n + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+      partials, num_chunks, n, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, out, 200000000ull);
+  return check_launch("comm_allreduce");
 }
 
 }  // extern "C"

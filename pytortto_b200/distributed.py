@@ -84,7 +84,7 @@ class PeerComm:
     fixed slots, exported through CUDA IPC and mapped by every peer.  A call site (BatchNorm layer x direction) owns
     one slot for the life of the process, so replays of a captured CUDA graph keep working."""
     MAX_VALUES = 2 * 4096   # 2C doubles, C <= 4096
-    SLOTS = 512
+    SLOTS = 256
 
     def __init__(self):
         import ctypes
@@ -133,8 +133,8 @@ class PeerComm:
         off = self.slot_offset(key)
         st = torch.cuda.current_stream().cuda_stream
         out = torch.empty((n,), dtype=torch.float64, device=partials.device)
-        self._cabi.call("ttb_comm_publish", partials.data_ptr(), chunks, n, self.own, off, st)
-        self._cabi.call("ttb_comm_gather", self.peers_dev.data_ptr(), self.world, self.rank, off, n, out.data_ptr(), st)
+        self._cabi.call("ttb_comm_allreduce", partials.data_ptr(), chunks, n, self.peers_dev.data_ptr(), self.world,
+                        self.rank, off, out.data_ptr(), st)
         return out
 
 
@@ -226,12 +226,16 @@ class _Bucket:
             self.work.wait()  # makes the current stream wait for the collective
         self.flat.mul_(inv_world)
         off = 0
+        dsts, srcs = [], []
         for p in self.params:
             v = _flat_view(p.grad.t)
             n = v.numel()
             if id(p) not in skip:
-                v.copy_(self.flat[off:off + n])
+                dsts.append(v)
+                srcs.append(self.flat[off:off + n])
             off += n
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)  # one multi-tensor launch instead of one copy per parameter
 
 
 class DistributedDataParallel:
