@@ -89,6 +89,18 @@ static int make_tiled_2d(CUtensorMap* tm, const void* base, Elem el, uint64_t ro
   return 0;
 }
 
+// generic tiled map (rank <= 5): dims / byte strides (strides[i] = stride of dim i+1) / box / traversal strides
+static int make_tiled_nd(CUtensorMap* tm, const void* base, Elem el, int rank, const cuuint64_t* dims,
+                         const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swz) {
+  CUresult r = g_encodeTiled(tm, el.dt, (cuuint32_t)rank, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r);
+    return 1;
+  }
+  return 0;
+}
+
 // NHWC activation [n][h][w][c] -> im2col map: `pixels` base pixels x 128 bytes of channels per load, traversal strides
 // (tw, th), bounding-box corners in W/H order, 128B swizzle, zero fill outside the image.
 static int make_im2col_4d(CUtensorMap* tm, const void* base, Elem el, int n, int h, int w, int c, int lower_w, int lower_h,
@@ -149,6 +161,11 @@ struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B =
   int p_dim, q_dim;        // output pixel grid (for decomposing the pixel index of a step)
   int base_w, base_h, trav_w, trav_h;
   uint32_t desc_lbo, desc_sbo, desc_layout;  // UMMA smem-descriptor fields for the MN-major operands
+  // "rectangular" fast path: the KP pixels of a step form a box (rect_w x rect_h x rect_n) of the output grid, so all
+  // channel slabs of one tap come from ONE tiled 5-D load (tmX = [32|64 ch][W][H][N][C/32|64]) and all slabs of dY
+  // from ONE tiled 3-D load (tmDy = [ch][pixels][K/32|64]) - 2..5 TMA instructions per step instead of 12.
+  int rect;                // 0: im2col / per-slab loads
+  int pad_w, pad_h, dil_w, dil_h;
   uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
 };
 
@@ -395,15 +412,34 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStageBytes;
         ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+        if (P.rect) {
+          // dY: all kASlabs channel slabs in one 3-D box (channel-in-slab, pixel, slab)
+          ptx::tma_load_3d(sa, &P.tmDy, &full_bar[stage], 0, pix0, k0 / kSlabCh);
+          // x: one 5-D box per filter tap covering every channel slab of that tap inside this N tile
+          int sl = 0;
+          while (sl < nslab) {
+            const int col = n0 + sl * kSlabCh;
+            const int tap = col / P.c;
+            const int c0 = col - tap * P.c;
+            int run = (P.c - c0) / kSlabCh;  // slabs left in this tap
+            if (run > nslab - sl) run = nslab - sl;
+            // run is baked into the tensor map's box (slabs per tap inside a tile is constant: see host code)
+            ptx::tma_load_5d(sa + kABytes + sl * kSlabBytes, &P.tmX, &full_bar[stage], 0,
+                             j * P.trav_w - P.pad_w + P.off_w[tap], i * P.trav_h - P.pad_h + P.off_h[tap], n,
+                             c0 / kSlabCh);
+            sl += run;
+          }
+        } else {
 #pragma unroll
-        for (int sl = 0; sl < kASlabs; ++sl)  // dY[pix0 .. pix0+KP, k0 + slab]  (rows past the tensor are zero-filled)
-          ptx::tma_load_2d(sa + sl * kSlabBytes, &P.tmDy, &full_bar[stage], k0 + sl * kSlabCh, pix0);
-        for (int sl = 0; sl < nslab; ++sl) {
-          const int col = n0 + sl * kSlabCh;
-          const int tap = col / P.c;
-          const int c0 = col - tap * P.c;
-          ptx::tma_load_im2col_4d(sa + kABytes + sl * kSlabBytes, &P.tmX, &full_bar[stage], c0, cw, ch, n,
-                                  P.off_w[tap], P.off_h[tap]);
+          for (int sl = 0; sl < kASlabs; ++sl)  // dY[pix0 .. pix0+KP, k0 + slab]  (rows past the tensor are zero-filled)
+            ptx::tma_load_2d(sa + sl * kSlabBytes, &P.tmDy, &full_bar[stage], k0 + sl * kSlabCh, pix0);
+          for (int sl = 0; sl < nslab; ++sl) {
+            const int col = n0 + sl * kSlabCh;
+            const int tap = col / P.c;
+            const int c0 = col - tap * P.c;
+            ptx::tma_load_im2col_4d(sa + kABytes + sl * kSlabBytes, &P.tmX, &full_bar[stage], c0, cw, ch, n,
+                                    P.off_w[tap], P.off_h[tap]);
+          }
         }
         if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
       }
@@ -829,13 +865,61 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
   if (const char* e = getenv("TTB_WGRAD_LBO")) P.desc_lbo = (uint32_t)atoi(e);
   if (const char* e = getenv("TTB_WGRAD_SBO")) P.desc_sbo = (uint32_t)atoi(e);
   if (const char* e = getenv("TTB_WGRAD_LAYOUT")) P.desc_layout = (uint32_t)atoi(e);
-  // dY as a [pixels][K] matrix; box = KP pixel rows x 128 bytes of channels
-  if (make_tiled_2d(&P.tmDy, dy, el, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
-  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
-  if (make_im2col_4d(&P.tmX, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP,
-                     swz))
-    return 1;
   const int ncols = d->r * d->s * d->c;
+  // Rectangular fast path: when the KP output pixels of a step are a box of the (n, p, q) grid and taps / N tiles
+  // nest, every tap's channel slabs arrive in ONE 5-D tiled load and dY's slabs in ONE 3-D load.
+  const int slab = el.per_row;
+  int bw = 0, bh = 0, bnimg = 0;
+  {
+    const char* e = getenv("TTB_WGRAD_RECT");
+    bool ok = !(e && atoi(e) == 0) && d->k % slab == 0 && (d->c % bn == 0 || bn % d->c == 0) && m % KP == 0;
+    if (ok) {
+      if (d->q >= KP) {
+        ok = d->q % KP == 0;
+        bw = KP; bh = 1; bnimg = 1;
+      } else if (KP % d->q == 0) {
+        const int rows = KP / d->q;
+        if (d->p % rows == 0) { bw = d->q; bh = rows; bnimg = 1; }
+        else if (rows % d->p == 0) { bw = d->q; bh = d->p; bnimg = rows / d->p; }
+        else ok = false;
+      } else {
+        ok = false;
+      }
+    }
+    if (ok && (bw * d->stride_w > 256 || bh * d->stride_h > 256 || bnimg > 256)) ok = false;
+    P.rect = ok ? 1 : 0;
+  }
+  if (P.rect) {
+    const cuuint64_t es = (cuuint64_t)el.size;
+    {  // dY viewed as [K/slab][pixels][slab]
+      cuuint64_t dims[3] = {(cuuint64_t)slab, (cuuint64_t)m, (cuuint64_t)(d->k / slab)};
+      cuuint64_t strides[2] = {(cuuint64_t)d->k * es, (cuuint64_t)slab * es};
+      cuuint32_t box[3] = {(cuuint32_t)slab, (cuuint32_t)KP, (cuuint32_t)(kTileM / slab)};
+      cuuint32_t estr[3] = {1, 1, 1};
+      if (make_tiled_nd(&P.tmDy, dy, el, 3, dims, strides, box, estr, swz)) return 1;
+    }
+    {  // x viewed as [C/slab][N][H][W][slab]; box = one tap's slabs for a (bnimg x bh x bw) block of output pixels
+      const int per_box = (d->c < bn ? d->c : bn) / slab;
+      cuuint64_t dims[5] = {(cuuint64_t)slab, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)(d->c / slab)};
+      cuuint64_t strides[4] = {(cuuint64_t)d->c * es, (cuuint64_t)d->w * d->c * es, (cuuint64_t)d->h * d->w * d->c * es,
+                               (cuuint64_t)slab * es};
+      cuuint32_t box[5] = {(cuuint32_t)slab, (cuuint32_t)(bw * d->stride_w), (cuuint32_t)(bh * d->stride_h), (cuuint32_t)bnimg,
+                           (cuuint32_t)per_box};
+      cuuint32_t estr[5] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1, 1};
+      if (make_tiled_nd(&P.tmX, x, el, 5, dims, strides, box, estr, swz)) return 1;
+    }
+  } else {
+    // dY as a [pixels][K] matrix; box = KP pixel rows x 128 bytes of channels
+    if (make_tiled_2d(&P.tmDy, dy, el, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
+    const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
+    if (make_im2col_4d(&P.tmX, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP,
+                       swz))
+      return 1;
+  }
+  P.pad_w = d->pad_w;
+  P.pad_h = d->pad_h;
+  P.dil_w = d->dil_w;
+  P.dil_h = d->dil_h;
   P.o.out = splits > 1 ? reinterpret_cast<float*>(ws) : dw;
   P.o.n_stride = ncols;
   P.o.h_stride = 0;
