@@ -6,7 +6,7 @@
 // sum(dy), sum(dy*(x-mean)); then one fused dx pass).
 //
 // Column reductions: thread -> fixed channel quad (float4 = 4 channels), rows strided across the block and
-// the grid; per-thread fp32 partials over <= kRowsPerThread rows, block tree in shared memory, one double
+// the grid; per-thread fp32 partials over its share of one wave's rows (tens to a few hundred), block tree in shared memory, one double
 // partial per (chunk, channel) written to HBM, and a tiny second kernel sums chunks in double in a FIXED
 // order (deterministic; no atomics).  The [2][C] double sums are what a data-parallel run all-reduces.
 #include "common.cuh"
@@ -14,7 +14,6 @@
 namespace ttb {
 
 constexpr int kBnThreads = 256;
-constexpr int kRowsPerThread = 32;  // fp32 accumulation length per thread before widening to double
 
 struct ColGeom {
   int tx;        // threads along channel quads (power of two <= 256)
@@ -36,17 +35,16 @@ static ColGeom col_geom(int64_t m, int c) {
   g.tx = tx;
   g.ty = kBnThreads / tx;
   g.qblocks = (cq + tx - 1) / tx;
-  int64_t rows_per_chunk = (int64_t)g.ty * kRowsPerThread;
-  int64_t chunks = ceil_div(m, rows_per_chunk);
-  // one wave: at most (SMs x resident CTAs per SM) CTAs in total
+  // Spread the rows over ONE full wave of CTAs (SMs x resident CTAs per SM) whenever there are enough rows: the
+  // kernel is a chain of dependent load batches per thread, so its latency is (rows per thread / unroll) x DRAM
+  // latency - small tensors want many short threads, not few long ones.  At least kMinRowsPerThread rows per thread.
+  constexpr int kMinRowsPerThread = 4;
   int64_t cap = (int64_t)sm_count() * col_reduce_ctas_per_sm() / g.qblocks;
   if (cap < 1) cap = 1;
-  if (chunks > cap) {
-    chunks = cap;
-    rows_per_chunk = ceil_div(m, chunks);
-    rows_per_chunk = ceil_div(rows_per_chunk, g.ty) * g.ty;
-    chunks = ceil_div(m, rows_per_chunk);
-  }
+  int64_t rows_per_chunk = ceil_div(m, cap);
+  rows_per_chunk = ceil_div(rows_per_chunk, g.ty) * g.ty;
+  if (rows_per_chunk < (int64_t)g.ty * kMinRowsPerThread) rows_per_chunk = (int64_t)g.ty * kMinRowsPerThread;
+  int64_t chunks = ceil_div(m, rows_per_chunk);
   if (chunks < 1) chunks = 1;
   g.chunks = (int)chunks;
   g.rows_per_chunk = rows_per_chunk;
@@ -95,8 +93,9 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     };
     int64_t r = r0 + ty;
     if (VEC) {
-      // 4 rows per iteration: all loads of the batch are issued before the first use (memory-level parallelism)
-      constexpr int U = 4;
+      // U rows per iteration: all loads of the batch are issued before the first use (memory-level parallelism);
+      // 8 float4 in flight per thread for the single-input statistics pass, 4 x 3 for the three-input backward pass
+      constexpr int U = MODE == 0 ? 8 : 4;
       for (; r + (U - 1) * ty_n < r1; r += U * ty_n) {
         float4 va[U], vb[U], vm[U];
 #pragma unroll
