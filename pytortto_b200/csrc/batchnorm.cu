@@ -40,6 +40,9 @@ static ColGeom col_geom(int64_t m, int c) {
   // latency - small tensors want many short threads, not few long ones.  At least kMinRowsPerThread rows per thread.
   constexpr int kMinRowsPerThread = 4;
   int64_t cap = (int64_t)sm_count() * col_reduce_ctas_per_sm() / g.qblocks;
+  // ... but keep the partial buffer [chunks][2][C] doubles under ~1 MB so the finalize kernel stays a few microseconds
+  const int64_t cap_bytes = (int64_t)(1 << 20) / ((int64_t)2 * c * 8);
+  if (cap > cap_bytes) cap = cap_bytes;
   if (cap < 1) cap = 1;
   int64_t rows_per_chunk = ceil_div(m, cap);
   rows_per_chunk = ceil_div(rows_per_chunk, g.ty) * g.ty;
