@@ -151,6 +151,12 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def workload_text(args):
+    cfg = MODELS[args.model]
+    return (f"{args.model} CIFAR-shaped 3x{cfg['hw']}x{cfg['hw']} training step (fwd+loss+bwd+SGD), "
+            f"batch {args.batch} per GPU")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -167,9 +173,9 @@ def run_reference(args):
         "impl": "reference", "metric": "ResNet train images/sec", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} CIFAR-shaped 3x{cfg['hw']}x{cfg['hw']} training step, SGD(momentum 0.9, "
-                               f"wd 1e-4); reference numpy algorithm (oracle port) on host cores",
-                   "batch_per_step_sampled": per_step, "nominal_batch_per_gpu": args.batch},
+        "config": {"workload": workload_text(args), "global_batch": args.batch * args.gpus,
+                   "parallelism": "host cpu (reference numpy algorithm, oracle port; rank 0 only)",
+                   "batch_per_step_sampled": per_step, "math": "fp32"},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {per_step} (bounded sample of the batch-{args.batch} step)"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -290,18 +296,25 @@ def run_ours(args):
     bn_bytes = elems * 4 * (3 + 5 + 2 + 3)
     achieved_gbs = bn_bytes / (bn_ms / 1e3) / 1e9 if bn_ms > 0 else 0.0
     cpu_ips, cpu_s = oracle_images_per_sec(args.model, 16, 1, 0)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_conv_family_traffic.json")
+    if os.path.exists(tpath) and args.model == "preact_resnet18" and B == 256 and args.math == "tf32":
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_total")  # DRAM bytes of the conv family per step (ncu --set full)
     line = {
         "metric": "ResNet train images/sec", "value": img_s, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.math, "data": "synthetic",
-        "config": {"workload": f"{args.model} CIFAR-shaped 3x{hw}x{hw} training step (fwd+loss+bwd+SGD), batch {B} per GPU",
+        "config": {"workload": workload_text(args),
                    "global_batch": B * world, "parallelism": f"dp{world}" + ("+syncbn" if world > 1 else ""),
                    "l2": "per-step working set (~2.5 GB of activations at batch 256) >> 126 MB L2; no explicit flush",
                    "math": args.math, "cuda_graph": bool(use_graph)},
         "conv_tflops": achieved_tf,
         "conv_tflops_step_share": conv_ms / (prof["step_ms"] or 1.0),
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write summed over the conv-family launches of one step, "
+                                     "profiles/r1_conv_family_traffic.json (per step, like `achieved`)",
                      "kernel": "igemm_fwd_kernel + igemm_wgrad_kernel (conv fprop+dgrad+wgrad of one step)",
                      "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed inside a long step); "
                                     "TF32 math peaks at half of it",

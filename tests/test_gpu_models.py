@@ -123,3 +123,36 @@ def test_adam_step_and_eval_mode():
     np.testing.assert_array_equal(y1, y2)  # eval mode: no statistics update, deterministic
     sd = net.state_dict()
     assert float(sd["down.0.conv.1.num_batches_tracked"]) == 5.0
+
+
+def test_full_size_resnet50_and_unet_shapes():
+    """BASELINE configs 3 and 4 at their real spatial sizes (224x224 ResNet-50, 3x64x64 UNet with the notebook's
+    features) at a small batch: the TF32 tensor path (incl. the 7x7/s2 padded stem, 49 taps, non-rectangular wgrad
+    steps, ConvTranspose2d) against the exact-fp32 path on the same weights."""
+    import pytortto_b200 as tt
+    M = _models(tt)
+    rng = np.random.default_rng(17)
+    x50 = rng.standard_normal((4, 3, 224, 224)).astype(np.float32)
+    lab = rng.integers(0, 10, 4).astype(np.int64)
+    xu = rng.standard_normal((4, 3, 64, 64)).astype(np.float32)
+    tu = rng.integers(0, 2, (4, 1, 64, 64)).astype(np.float32)
+    out = {}
+    for mode in ("tf32", "fp32"):
+        tt.set_math_mode(mode)
+        tt.manual_seed(2)
+        net = M["standard_resnet50"]().cuda()
+        loss = tt.nn.NLLLoss()(net(tt.tensor(x50).cuda()), tt.tensor(lab, dtype=np.int64).cuda())
+        loss.backward()
+        g50 = net.stem[0].weight.grad.get()
+        tt.manual_seed(3)
+        unet = M["UNet"](3, 1, [32, 64, 128, 256]).cuda()
+        lu = tt.nn.BCEWithLogitsLoss()(unet(tt.tensor(xu).cuda()), tt.tensor(tu).cuda())
+        lu.backward()
+        gu = unet.out.weight.grad.get()
+        assert np.isfinite(g50).all() and np.isfinite(gu).all()
+        out[mode] = (loss.item(), lu.item(), g50, gu)
+    assert abs(out["tf32"][0] - out["fp32"][0]) < 5e-3 * abs(out["fp32"][0])
+    assert abs(out["tf32"][1] - out["fp32"][1]) < 5e-3 * abs(out["fp32"][1])
+    for i in (2, 3):
+        a, b = out["tf32"][i].astype(np.float64), out["fp32"][i].astype(np.float64)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 0.3
