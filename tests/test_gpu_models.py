@@ -125,10 +125,52 @@ def test_adam_step_and_eval_mode():
     assert float(sd["down.0.conv.1.num_batches_tracked"]) == 5.0
 
 
+def _layerwise_conv_parity(tt, net, run, tol=3e-3):
+    """Run `run(net)` once in TF32 mode recording the input of every Conv2d / ConvTranspose2d call, then replay every
+    recorded call on ITS OWN recorded input in tf32 and in exact-fp32 mode (forward + backward with a fixed upstream
+    gradient) and compare per layer.  Whole-network comparisons of tf32 against fp32 are chaotic for deep nets at a
+    small batch; this is the size-independent form of the same check."""
+    from pytortto_b200.nn.modules import Conv2d, ConvTranspose2d
+    calls = []
+    convs = [m for m in net.modules() if isinstance(m, (Conv2d, ConvTranspose2d))]
+    for m in convs:
+        def rec(*a, _m=m, _f=m.forward, **kw):
+            calls.append((_m, a[0].data.get(), kw))
+            return _f(*a, **kw)
+        m.forward = rec
+    tt.set_math_mode("tf32")
+    run(net)
+    for m in convs:
+        del m.forward  # back to the class method
+    rng = np.random.default_rng(99)
+    worst = {}
+    for idx, (m, xin, kw) in enumerate(calls):
+        res = {}
+        dy = None
+        for mode in ("tf32", "fp32"):
+            tt.set_math_mode(mode)
+            leaf = tt.tensor(xin, requires_grad=True)
+            m.weight.grad = None
+            y = m(leaf.cuda(), **kw)
+            if dy is None:
+                dy = rng.standard_normal(y.shape).astype(np.float32)
+            y.backward(tt.tensor(dy).cuda())
+            res[mode] = (y.data.get(), np.asarray(leaf.grad), m.weight.grad.get())
+        for name, a, b in zip(("y", "dx", "dw"), res["tf32"], res["fp32"]):
+            err = float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+            key = f"{type(m).__name__} {tuple(m.weight.shape)} s{m.stride[0]} in{tuple(xin.shape)} {name}"
+            worst[key] = max(worst.get(key, 0.0), err)
+            assert err < tol, (idx, key, err)
+        m.weight.grad = None
+    tt.set_math_mode("tf32")
+    return len(calls), worst
+
+
 def test_full_size_resnet50_and_unet_shapes():
     """BASELINE configs 3 and 4 at their real spatial sizes (224x224 ResNet-50, 3x64x64 UNet with the notebook's
-    features) at a small batch: the TF32 tensor path (incl. the 7x7/s2 padded stem, 49 taps, non-rectangular wgrad
-    steps, ConvTranspose2d) against the exact-fp32 path on the same weights."""
+    features) at a small batch: every conv layer of the net (incl. the 7x7/s2 padded stem with 49 taps,
+    non-rectangular wgrad steps, 1x1 / strided / biased convs, ConvTranspose2d) on the TF32 tensor path against the
+    exact-fp32 path, layer by layer on the activations of a real forward pass."""
     import pytortto_b200 as tt
     M = _models(tt)
     rng = np.random.default_rng(17)
@@ -136,23 +178,25 @@ def test_full_size_resnet50_and_unet_shapes():
     lab = rng.integers(0, 10, 4).astype(np.int64)
     xu = rng.standard_normal((4, 3, 64, 64)).astype(np.float32)
     tu = rng.integers(0, 2, (4, 1, 64, 64)).astype(np.float32)
-    out = {}
-    for mode in ("tf32", "fp32"):
-        tt.set_math_mode(mode)
-        tt.manual_seed(2)
-        net = M["standard_resnet50"]().cuda()
+    losses = {}
+
+    def run50(net):
         loss = tt.nn.NLLLoss()(net(tt.tensor(x50).cuda()), tt.tensor(lab, dtype=np.int64).cuda())
         loss.backward()
-        g50 = net.stem[0].weight.grad.get()
-        tt.manual_seed(3)
-        unet = M["UNet"](3, 1, [32, 64, 128, 256]).cuda()
-        lu = tt.nn.BCEWithLogitsLoss()(unet(tt.tensor(xu).cuda()), tt.tensor(tu).cuda())
-        lu.backward()
-        gu = unet.out.weight.grad.get()
-        assert np.isfinite(g50).all() and np.isfinite(gu).all()
-        out[mode] = (loss.item(), lu.item(), g50, gu)
-    assert abs(out["tf32"][0] - out["fp32"][0]) < 5e-3 * abs(out["fp32"][0])
-    assert abs(out["tf32"][1] - out["fp32"][1]) < 5e-3 * abs(out["fp32"][1])
-    for i in (2, 3):
-        a, b = out["tf32"][i].astype(np.float64), out["fp32"][i].astype(np.float64)
-        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 0.3
+        losses["resnet50"] = loss.item()
+        assert all(np.isfinite(p.grad.get()).all() for p in net.parameters())
+
+    def runu(net):
+        loss = tt.nn.BCEWithLogitsLoss()(net(tt.tensor(xu).cuda()), tt.tensor(tu).cuda())
+        loss.backward()
+        losses["unet"] = loss.item()
+        assert all(np.isfinite(p.grad.get()).all() for p in net.parameters())
+
+    tt.manual_seed(2)
+    n50, w50 = _layerwise_conv_parity(tt, M["standard_resnet50"]().cuda(), run50)
+    tt.manual_seed(3)
+    nu, wu = _layerwise_conv_parity(tt, M["UNet"](3, 1, [32, 64, 128, 256]).cuda(), runu)
+    assert n50 == 53 and nu == 23
+    for k, v in sorted({**w50, **wu}.items(), key=lambda kv: -kv[1])[:8]:
+        print(f"worst layer-wise tf32-vs-fp32 rel-err {v:.2e}  {k}")
+    assert np.isfinite(losses["resnet50"]) and np.isfinite(losses["unet"])
