@@ -149,6 +149,8 @@ struct FwdParams {         // fprop / dgrad (K-major A via im2col TMA, K-major B
   int trav_w, trav_h;      // traversal strides
   int b_koff[kMaxTaps];    // column offset of the tap's K-slice in the weight matrix
   uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
+  int dbg;                 // TTB_IGEMM_DBG bits (timing experiments, wrong results): 1 no MMA, 2 no A loads, 4 no B loads
+  long long* trace;        // optional clock64() timeline of CTA (0,0): see scripts/igemm_trace.py
 };
 
 struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B = im2col(x) via im2col TMA)
@@ -241,6 +243,8 @@ __device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
   const int m0 = blockIdx.x * kTileM;
   const int n0 = blockIdx.y * BN;
   const int num_kb = P.num_taps * P.c_blocks;
+  long long* const tr = (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? P.trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&P.tmA);
@@ -262,6 +266,7 @@ __device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -279,10 +284,11 @@ __device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
         const int kb0 = P.b_koff[tap];
         for (int cb = 0; cb < P.c_blocks; ++cb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (tr && tap * P.c_blocks + cb < 500) tr[16 + tap * P.c_blocks + cb] = clock64();
           uint8_t* sa = smem + stage * kStageBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], kStageBytes);
-          ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
-          ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
+          ptx::mbar_expect_tx(&full_bar[stage], ((P.dbg & 2) ? 0 : kABytes) + ((P.dbg & 4) ? 0 : kBBytes));
+          if (!(P.dbg & 2)) ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
+          if (!(P.dbg & 4)) ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -296,8 +302,14 @@ __device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
+        if (tr && kb < 500) tr[16 + 512 + kb] = clock64();
         const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
+        if (P.dbg & 1) {
+          ptx::mbar_arrive(&empty_bar[stage]);
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
           uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
@@ -312,14 +324,18 @@ __device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
     }
   } else {
     // ===================== epilogue =====================
-    ptx::mbar_wait(&accum_bar, 0);
+    if (lane == 0) ptx::mbar_wait(&accum_bar, 0);  // one poller per warp: 128 spinning threads slow every other mbarrier op of the SM
+    __syncwarp();
     ptx::tc_fence_after();
+    if (tr && warp == 2 && lane == 0) tr[2] = clock64();
     // all MMAs (hence all TMA reads of the ring) are done: the ring is reused as staging space
     epilogue_store<BN>(tmem_base, reinterpret_cast<float*>(smem), P.o, m0, n0, P.bias, warp - 2, warp & 3);
+    if (tr && warp == 2 && lane == 0) tr[3] = clock64();
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if (tr && threadIdx.x == 32) tr[4] = clock64();
 }
 
 template <int BN, int NSTAGES, bool BF16>
@@ -341,6 +357,186 @@ igemm_fwd_multi_kernel(const __grid_constant__ FwdParamsMulti PM) {
   const FwdParams& P = PM.p[blockIdx.z];
   if ((int)blockIdx.x * kTileM >= P.o.m_total) return;  // classes can differ by one tile; whole CTA leaves
   igemm_fwd_body<BN, NSTAGES, BF16>(P);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent fprop / dgrad kernel: one CTA per SM walks a static list of output tiles (tile = blockIdx.x + i*gridDim.x)
+// of up to kMaxMulti problems (the stride-parity classes of a strided dgrad).
+//   * NPROD producer threads (one per warp) issue the TMA loads, K-block g belongs to producer g % NPROD: a K-block costs
+//     one thread ~450 cycles of dependent mbarrier.try_wait / arrive.expect_tx / 2 x cp.async.bulk.tensor latency
+//     (measured), more than the 128-256 cycles the tensor core needs for it, so a single producer starves the MMAs.
+//     NSTAGES % NPROD == 0 keeps every stage with one producer (no parity aliasing between threads).
+//   * the smem ring (~192 KB) keeps running across tile boundaries: no pipeline drain / refill per tile.
+//   * two accumulator buffers in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles: [0, NPROD) producers, NPROD = MMA issuer + TMEM owner, NPROD+1 .. NPROD+4 epilogue.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kEpilogueStagingBytes = 4 * 32 * kStagePitch * 4;
+
+template <int BN, int NSTAGES, int NPROD, bool BF16>
+__global__ void __launch_bounds__((NPROD + 5) * 32, 1)
+igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
+  static_assert(NSTAGES % NPROD == 0, "a stage must always be filled by the same producer thread");
+  constexpr int kElems = BF16 ? 64 : 32;
+  constexpr uint32_t kABytes = kTileM * 128;
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr int kAccCols = BN < 32 ? 32 : BN;
+  constexpr int kTmemCols = 2 * kAccCols;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* staging = reinterpret_cast<float*>(smem + (size_t)NSTAGES * kStageBytes);
+  __shared__ uint64_t full_bar[NSTAGES], empty_bar[NSTAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // The producer / MMA loops below are executed by WHOLE warps with warp-uniform control flow and operands, and only
+  // the asynchronous instruction itself sits under elect.sync.  Issued from a `lane == 0` branch instead, every
+  // UTMALDG / UTCHMMA / UTCBAR gets a divergence "waterfall" (ELECT + R2UR.BROADCAST + BRA.U.ANY loop) around it and a
+  // K-block costs ~450 cycles of issue latency - more than its 128..512 cycles of tensor-core time (measured).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int nt = (PM.p[0].o.n_total + BN - 1) / BN;  // N tiles (same for every problem of the launch)
+  int tiles_total = 0;
+  for (int c = 0; c < count; ++c) tiles_total += ((PM.p[c].o.m_total + kTileM - 1) / kTileM) * nt;
+  long long* const tr = (PM.p[0].trace && blockIdx.x == 0) ? PM.p[0].trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+
+  if (warp == 0 && ptx::elect_one())
+    for (int c = 0; c < count; ++c) {
+      ptx::prefetch_tmap(&PM.p[c].tmA);
+      ptx::prefetch_tmap(&PM.p[c].tmB);
+    }
+  if (warp == NPROD) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&acc_full[b], 1);
+        ptx::mbar_init(&acc_empty[b], 4);  // one arrival per epilogue warp
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(&tmem_base_smem);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
+
+  // tile index -> problem, first row, first column
+  auto decode = [&](int t, int& cls, int& m0, int& n0) {
+    cls = 0;
+    while (cls + 1 < count) {
+      const int tc = ((PM.p[cls].o.m_total + kTileM - 1) / kTileM) * nt;
+      if (t < tc) break;
+      t -= tc;
+      ++cls;
+    }
+    m0 = (t / nt) * kTileM;
+    n0 = (t % nt) * BN;
+  };
+
+  if (warp < NPROD) {
+    // ===================== TMA producers (whole warp, one elected lane issues) =====================
+    const int dbg = PM.p[0].dbg;
+    const uint32_t tx_bytes = ((dbg & 2) ? 0 : kABytes) + ((dbg & 4) ? 0 : kBBytes);
+    uint32_t g = 0;  // K-blocks of this CTA so far, counted by every producer; K-block g belongs to producer g % NPROD
+    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+      int cls, m0, n0;
+      decode(t, cls, m0, n0);
+      const FwdParams& P = PM.p[cls];
+      const int j = m0 % P.o.q_dim;
+      const int tt = m0 / P.o.q_dim;
+      const int i = tt % P.o.p_dim;
+      const int n = tt / P.o.p_dim;
+      const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
+      for (int tap = 0; tap < P.num_taps; ++tap) {
+        const uint16_t ow = P.off_w[tap], oh = P.off_h[tap];
+        const int kb0 = P.b_koff[tap];
+        for (int cb = 0; cb < P.c_blocks; ++cb, ++g) {
+          if ((int)(g % NPROD) != warp) continue;
+          const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (tr && lane == 0 && g < 1000) tr[2048 + g] = clock64();
+          uint8_t* sa = smem + stage * kStageBytes;
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (!(dbg & 2)) ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
+            if (!(dbg & 4)) ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == NPROD) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1 /*bf16*/ : 2 /*tf32*/, 0, 0, kTileM, BN);
+    const int dbg = PM.p[0].dbg;
+    uint32_t g = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++it) {
+      int cls, m0, n0;
+      decode(t, cls, m0, n0);
+      const int num_kb = PM.p[cls].num_taps * PM.p[cls].c_blocks;
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      if (tr && lane == 0 && it < 250) tr[16 + 2 * it] = clock64();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kAccCols);
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (tr && lane == 0 && g < 1000) tr[3072 + g] = clock64();
+        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+        const uint32_t sb = sa + kABytes;
+        if (ptx::elect_one()) {
+          if (!(dbg & 1)) {
+            const int nmma = (dbg & 8) ? 1 : (dbg & 16) ? 2 : 4;  // experiment: fewer MMAs per K-block (wrong results)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
+              if (k >= nmma) break;
+              uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+              uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+              if (BF16) ptx::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+              else ptx::mma_tf32(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+        }
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::mma_commit(&acc_full[buf]);  // accumulator of this tile complete
+      __syncwarp();
+      if (tr && lane == 0 && it < 250) tr[17 + 2 * it] = clock64();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - (NPROD + 1);
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++it) {
+      int cls, m0, n0;
+      decode(t, cls, m0, n0);
+      const FwdParams& P = PM.p[cls];
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
+      ptx::tc_fence_after();
+      if (tr && ew == 0 && lane == 0 && it < 250) tr[528 + 2 * it] = clock64();
+      epilogue_store<BN>(tmem_base + (uint32_t)(buf * kAccCols), staging, P.o, m0, n0, P.bias, ew, warp & 3);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      if (tr && ew == 0 && lane == 0 && it < 250) tr[529 + 2 * it] = clock64();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == NPROD) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -469,7 +665,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
       ptx::mma_commit(&accum_bar);
     }
   } else {
-    ptx::mbar_wait(&accum_bar, 0);
+    if (lane == 0) ptx::mbar_wait(&accum_bar, 0);  // one poller per warp: 128 spinning threads slow every other mbarrier op of the SM
+    __syncwarp();
     ptx::tc_fence_after();
     OutMap o = P.o;
     o.out = P.o.out + (int64_t)split * P.split_stride;
@@ -565,6 +762,13 @@ static int launch_fwd(const FwdParams& P, cudaStream_t st) {
 
 // Widest N tile that still gives every SM a CTA; narrow channel counts get a matching narrow tile.
 static int pick_bn(int64_t m_total, int n_total) {
+  if (const char* e = getenv("TTB_FORCE_BN")) {  // experiment switch
+    const int v = atoi(e);
+    if (v == 256 && n_total > 128) return 256;
+    if (v >= 128 && n_total > 64) return 128;
+    if (v >= 64 && n_total > 32) return 64;
+    if (v == 32) return 32;
+  }
   const int64_t mtiles = ceil_div(m_total, kTileM);
   const int sms = sm_count();
   if (n_total > 128 && mtiles * ceil_div(n_total, 256) >= sms) return 256;
@@ -581,6 +785,15 @@ static int launch_fwd_bn(const FwdParams& P, int bn, bool bf16, cudaStream_t st)
       case 64: return launch_fwd<64, 4, true>(P, st);
       default: return launch_fwd<32, 4, true>(P, st);
     }
+  }
+  static int deep = -1;
+  if (deep < 0) {
+    const char* e = getenv("TTB_FWD_DEEP");
+    deep = e ? atoi(e) : 0;
+  }
+  if (deep) {
+    if (bn == 128) return launch_fwd<128, 6, false>(P, st);
+    if (bn == 64) return launch_fwd<64, 8, false>(P, st);
   }
   switch (bn) {
     case 256: return launch_fwd<256, 4, false>(P, st);
@@ -608,6 +821,62 @@ static int launch_fwd_multi(const FwdParamsMulti& PM, int count, cudaStream_t st
   dim3 grid((unsigned)ceil_div(m_max, kTileM), (unsigned)ceil_div(PM.p[0].o.n_total, BN), (unsigned)count);
   igemm_fwd_multi_kernel<BN, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(PM);
   return check_launch("igemm_fwd_multi_kernel");
+}
+
+template <int BN, int NSTAGES, int NPROD, bool BF16>
+static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + kEpilogueStagingBytes + 1024;
+  static_assert(smem <= 232448, "shared memory budget of one SM");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, BF16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set = true;
+  }
+  int64_t tiles = 0;
+  for (int i = 0; i < count; ++i) tiles += (int64_t)ceil_div(PM.p[i].o.m_total, kTileM) * ceil_div(PM.p[0].o.n_total, BN);
+  // narrow tiles leave room for two CTAs per SM (two independent MMA-issue streams: a 64-column K-block is 128
+  // tensor-core cycles but ~300 cycles of issue-side latency per CTA)
+  int sms = sm_count() * (smem <= 113 * 1024 ? 2 : 1);
+  if (const char* e = getenv("TTB_PERSIST_GRID")) sms = atoi(e);  // experiment switch: cap the number of CTAs
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, BF16><<<grid, (NPROD + 5) * 32, smem, st>>>(PM, count);
+  return check_launch("igemm_fwd_persist_kernel");
+}
+
+static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
+  if (bf16) {
+    switch (bn) {
+      case 256: return launch_persist<256, 4, 2, true>(PM, count, st);
+      case 128: return launch_persist<128, 6, 3, true>(PM, count, st);
+      case 64: return launch_persist<64, 3, 3, true>(PM, count, st);
+      default: return launch_persist<32, 4, 2, true>(PM, count, st);
+    }
+  }
+  static int narrow2 = -1;
+  if (narrow2 < 0) {
+    const char* e = getenv("TTB_NARROW_2CTA");
+    narrow2 = e ? atoi(e) : 1;
+  }
+  switch (bn) {
+    case 256: return launch_persist<256, 4, 2, false>(PM, count, st);
+    case 128: return launch_persist<128, 6, 3, false>(PM, count, st);
+    case 64: return narrow2 ? launch_persist<64, 3, 3, false>(PM, count, st) : launch_persist<64, 8, 4, false>(PM, count, st);
+    default: return launch_persist<32, 4, 2, false>(PM, count, st);
+  }
+}
+
+static int use_persist() {  // TTB_FWD_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparisons)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTB_FWD_PERSIST");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 static int launch_fwd_multi_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
@@ -675,6 +944,18 @@ size_t igemm_workspace_size(const ttb_conv_desc* d, int pass) {
   return splits > 1 ? (size_t)splits * welems * sizeof(float) : 0;
 }
 
+static long long* g_trace = nullptr;
+void igemm_set_trace(long long* p) { g_trace = p; }
+
+static int igemm_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TTB_IGEMM_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 // x, w: operands in the element type of d->math_mode (fp32 for TF32, bf16 for BF16); y, bias: fp32
 int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* /*ws*/,
                 size_t /*ws_bytes*/, cudaStream_t st) {
@@ -699,6 +980,8 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
   P.num_taps = d->r * d->s;
   P.base_w = -d->pad_w;
   P.base_h = -d->pad_h;
+  P.dbg = igemm_dbg();
+  P.trace = g_trace;
   P.trav_w = d->stride_w;
   P.trav_h = d->stride_h;
   for (int r = 0; r < d->r; ++r)
@@ -711,6 +994,11 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
   // weight matrix [K rows][R*S*C cols]; the TMA box height is the kernel's N tile
   const int bn = pick_bn(P.o.m_total, P.o.n_total);
   if (make_tiled_2d(&P.tmB, w, el, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
+  if (use_persist()) {
+    static thread_local FwdParamsMulti PM1;
+    PM1.p[0] = P;
+    return launch_persist_bn(PM1, 1, bn, el.bf16, st);
+  }
   return launch_fwd_bn(P, bn, el.bf16, st);
 }
 
@@ -803,13 +1091,18 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         }
         const int bn = pick_bn(P.o.m_total, P.o.n_total);
         if (make_tiled_2d(&P.tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-        if (launch_fwd_bn(P, bn, el.bf16, st)) return 1;
+        if (use_persist()) {
+          static thread_local FwdParamsMulti PM1;
+          PM1.p[0] = P;
+          if (launch_persist_bn(PM1, 1, bn, el.bf16, st)) return 1;
+        } else if (launch_fwd_bn(P, bn, el.bf16, st)) return 1;
       }
     if (pass == 1 && n_multi > 0) {
       const int bn = pick_bn(m_all, d->c);
       for (int i = 0; i < n_multi; ++i)
         if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-      if (launch_fwd_multi_bn(PM, n_multi, bn, el.bf16, st)) return 1;
+      if (use_persist() ? launch_persist_bn(PM, n_multi, bn, el.bf16, st) : launch_fwd_multi_bn(PM, n_multi, bn, el.bf16, st))
+        return 1;
     }
     if (pass == 0 && need_zero) {
       cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st);
