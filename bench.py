@@ -315,7 +315,7 @@ def run_ours(args):
                      "frac": achieved_tf / peaks["bf16_sustained"], "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write summed over the conv-family launches of one step, "
                                      "profiles/r1_conv_family_traffic.json (per step, like `achieved`)",
-                     "kernel": "igemm_fwd_kernel + igemm_wgrad_kernel (conv fprop+dgrad+wgrad of one step)",
+                     "kernel": "igemm_fwd_persist_kernel + igemm_wgrad_kernel (conv fprop+dgrad+wgrad of one step)",
                      "peak_source": peaks["source"] + "; sustained bf16 figure (kernel timed inside a long step); "
                                     "TF32 math peaks at half of it",
                      "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -372,14 +372,15 @@ igemm_fwd_multi_kernel(const __grid_constant__ FwdParamsMulti PM) {
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kEpilogueStagingBytes = 4 * 32 * kStagePitch * 4;
 
-template <int BN, int NSTAGES, int NPROD, bool BF16>
+template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
 __global__ void __launch_bounds__((NPROD + 5) * 32, 1)
 igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
   static_assert(NSTAGES % NPROD == 0, "a stage must always be filled by the same producer thread");
   constexpr int kElems = BF16 ? 64 : 32;
   constexpr uint32_t kABytes = kTileM * 128;
   constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kKbBytes = kABytes + kBBytes;       // one K-block: A tile + B tile
+  constexpr uint32_t kStageBytes = KPS * kKbBytes;       // a pipeline stage (one mbarrier hand-shake) holds KPS K-blocks
   constexpr int kAccCols = BN < 32 ? 32 : BN;
   constexpr int kTmemCols = 2 * kAccCols;
 
@@ -444,7 +445,7 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
     // ===================== TMA producers (whole warp, one elected lane issues) =====================
     const int dbg = PM.p[0].dbg;
     const uint32_t tx_bytes = ((dbg & 2) ? 0 : kABytes) + ((dbg & 4) ? 0 : kBBytes);
-    uint32_t g = 0;  // K-blocks of this CTA so far, counted by every producer; K-block g belongs to producer g % NPROD
+    uint32_t g = 0;  // stages filled by this CTA so far, counted by every producer; stage-fill g belongs to producer g % NPROD
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
       int cls, m0, n0;
       decode(t, cls, m0, n0);
@@ -454,22 +455,28 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
       const int i = tt % P.o.p_dim;
       const int n = tt / P.o.p_dim;
       const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
-      for (int tap = 0; tap < P.num_taps; ++tap) {
-        const uint16_t ow = P.off_w[tap], oh = P.off_h[tap];
-        const int kb0 = P.b_koff[tap];
-        for (int cb = 0; cb < P.c_blocks; ++cb, ++g) {
-          if ((int)(g % NPROD) != warp) continue;
-          const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (tr && lane == 0 && g < 1000) tr[2048 + g] = clock64();
-          uint8_t* sa = smem + stage * kStageBytes;
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (!(dbg & 2)) ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
-            if (!(dbg & 4)) ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
+      const int num_kb = P.num_taps * P.c_blocks;
+      for (int kb = 0; kb < num_kb; kb += KPS, ++g) {
+        if ((int)(g % NPROD) != warp) continue;
+        const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
+        const int nvalid = num_kb - kb < KPS ? num_kb - kb : KPS;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (tr && lane == 0 && g < 1000) tr[2048 + g] = clock64();
+        uint8_t* sa = smem + stage * kStageBytes;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * tx_bytes);
+#pragma unroll
+          for (int u = 0; u < KPS; ++u) {
+            if (u >= nvalid) break;
+            const int tap = (kb + u) / P.c_blocks;
+            const int cb = (kb + u) - tap * P.c_blocks;
+            if (!(dbg & 2))
+              ptx::tma_load_im2col_4d(sa + u * kKbBytes, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, P.off_w[tap], P.off_h[tap]);
+            if (!(dbg & 4))
+              ptx::tma_load_2d(sa + u * kKbBytes + kABytes, &P.tmB, &full_bar[stage], P.b_koff[tap] + cb * kElems, n0);
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
   } else if (warp == NPROD) {
@@ -487,23 +494,28 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
       ptx::tc_fence_after();
       if (tr && lane == 0 && it < 250) tr[16 + 2 * it] = clock64();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kAccCols);
-      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+      for (int kb = 0; kb < num_kb; kb += KPS, ++g) {
         const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
+        const int nvalid = num_kb - kb < KPS ? num_kb - kb : KPS;
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (tr && lane == 0 && g < 1000) tr[3072 + g] = clock64();
-        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t s0 = ptx::smem_u32(smem + stage * kStageBytes);
         if (ptx::elect_one()) {
           if (!(dbg & 1)) {
             const int nmma = (dbg & 8) ? 1 : (dbg & 16) ? 2 : 4;  // experiment: fewer MMAs per K-block (wrong results)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
-              if (k >= nmma) break;
-              uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
-              uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
-              if (BF16) ptx::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
-              else ptx::mma_tf32(d_tmem, da, db, idesc, (kb | k) != 0);
+            for (int u = 0; u < KPS; ++u) {
+              if (u >= nvalid) break;
+              const uint32_t sa = s0 + u * kKbBytes, sb = sa + kABytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
+                if (k >= nmma) break;
+                uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+                uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+                if (BF16) ptx::mma_bf16(d_tmem, da, db, idesc, (kb | u | k) != 0);
+                else ptx::mma_tf32(d_tmem, da, db, idesc, (kb | u | k) != 0);
+              }
             }
           }
           ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
@@ -561,7 +573,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   __shared__ uint64_t full_bar[NSTAGES], empty_bar[NSTAGES], accum_bar;
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see fwd kernel)
   const int lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kTileM;   // first output channel of the tile
   const int n0 = blockIdx.y * BN;       // first (tap,c) column of the tile
@@ -572,7 +584,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   const int ncol = P.o.n_total - n0 < BN ? P.o.n_total - n0 : BN;  // valid columns (whole slabs)
   const int nslab = ncol / kSlabCh;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&P.tmDy);
     ptx::prefetch_tmap(&P.tmX);
   }
@@ -594,7 +606,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp runs the loop; one elected lane issues (no divergence waterfall around the TMA instructions)
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kABytes + nslab * kSlabBytes;
@@ -607,6 +619,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStageBytes;
+        if (ptx::elect_one()) {
         ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
         if (P.rect) {
           // dY: all kASlabs channel slabs in one 3-D box (channel-in-slab, pixel, slab)
@@ -637,11 +650,13 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
                                     P.off_w[tap], P.off_h[tap]);
           }
         }
+        }
+        __syncwarp();
         if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1 /*bf16*/ : 2 /*tf32*/, 1, 1, kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -650,6 +665,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
         const uint32_t sb = sa + kABytes;
+        if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < KP / kMmaRows; ++k) {  // 8 (tf32) / 16 (bf16) pixel rows of every slab per MMA
           // MN-major operands: fp32 must use the 128B-span / 32B-atom swizzle (4-row K groups 512 B apart), bf16 the
@@ -660,9 +676,12 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
           else ptx::mma_tf32(tmem_base, da, db, idesc, (s | k) != 0);
         }
         ptx::mma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
         if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::mma_commit(&accum_bar);
+      if (ptx::elect_one()) ptx::mma_commit(&accum_bar);
+      __syncwarp();
     }
   } else {
     if (lane == 0) ptx::mbar_wait(&accum_bar, 0);  // one poller per warp: 128 spinning threads slow every other mbarrier op of the SM
@@ -771,7 +790,9 @@ static int pick_bn(int64_t m_total, int n_total) {
   }
   const int64_t mtiles = ceil_div(m_total, kTileM);
   const int sms = sm_count();
-  if (n_total > 128 && mtiles * ceil_div(n_total, 256) >= sms) return 256;
+  // 256-wide tiles are the only tensor-bound TF32 configuration (see launch_persist_bn): take them as soon as they
+  // fill most of one wave of SMs
+  if (n_total > 128 && mtiles * ceil_div(n_total, 256) * 5 >= sms * 4) return 256;
   if (n_total > 64 && (mtiles * ceil_div(n_total, 128) >= sms || n_total > 128)) return 128;
   if (n_total > 32) return 64;
   return 32;
@@ -823,13 +844,13 @@ static int launch_fwd_multi(const FwdParamsMulti& PM, int count, cudaStream_t st
   return check_launch("igemm_fwd_multi_kernel");
 }
 
-template <int BN, int NSTAGES, int NPROD, bool BF16>
+template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
 static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + kEpilogueStagingBytes + 1024;
+  constexpr size_t smem = (size_t)NSTAGES * KPS * (kTileM * 128 + BN * 128) + kEpilogueStagingBytes + 1024;
   static_assert(smem <= 232448, "shared memory budget of one SM");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, BF16>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -844,29 +865,35 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
   int sms = sm_count() * (smem <= 113 * 1024 ? 2 : 1);
   if (const char* e = getenv("TTB_PERSIST_GRID")) sms = atoi(e);  // experiment switch: cap the number of CTAs
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, BF16><<<grid, (NPROD + 5) * 32, smem, st>>>(PM, count);
+  igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16><<<grid, (NPROD + 5) * 32, smem, st>>>(PM, count);
   return check_launch("igemm_fwd_persist_kernel");
 }
 
 static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
+  // <BN, stages, producer warps, K-blocks per stage>.  Measured on B200 (TF32): the MMA warp pays ~170 cycles per
+  // stage hand-shake + ~30 cycles per MMA issue against 32 / 64 / 128 tensor-core cycles per MMA at N = 64 / 128 / 256,
+  // so N = 256 is tensor-bound (512 cycles per K-block), N = 128 nearly (300 vs 256) and N <= 64 issue-bound: narrow
+  // tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
+  // Two K-blocks per stage (KPS = 2) halve the hand-shakes but the 3-stage ring that fits then hides less latency:
+  // measured slower (layer 2: 40.8 vs 38.2 us), kept instantiable for experiments (TTB_KPS2=1).
+  static int kps2 = -1;
+  if (kps2 < 0) {
+    const char* e = getenv("TTB_KPS2");
+    kps2 = e ? atoi(e) : 0;
+  }
   if (bf16) {
     switch (bn) {
-      case 256: return launch_persist<256, 4, 2, true>(PM, count, st);
-      case 128: return launch_persist<128, 6, 3, true>(PM, count, st);
-      case 64: return launch_persist<64, 3, 3, true>(PM, count, st);
-      default: return launch_persist<32, 4, 2, true>(PM, count, st);
+      case 256: return launch_persist<256, 4, 2, 1, true>(PM, count, st);
+      case 128: return launch_persist<128, 6, 3, 1, true>(PM, count, st);
+      case 64: return launch_persist<64, 3, 3, 1, true>(PM, count, st);
+      default: return launch_persist<32, 3, 3, 1, true>(PM, count, st);
     }
   }
-  static int narrow2 = -1;
-  if (narrow2 < 0) {
-    const char* e = getenv("TTB_NARROW_2CTA");
-    narrow2 = e ? atoi(e) : 1;
-  }
   switch (bn) {
-    case 256: return launch_persist<256, 4, 2, false>(PM, count, st);
-    case 128: return launch_persist<128, 6, 3, false>(PM, count, st);
-    case 64: return narrow2 ? launch_persist<64, 3, 3, false>(PM, count, st) : launch_persist<64, 8, 4, false>(PM, count, st);
-    default: return launch_persist<32, 4, 2, false>(PM, count, st);
+    case 256: return launch_persist<256, 4, 2, 1, false>(PM, count, st);
+    case 128: return kps2 ? launch_persist<128, 3, 3, 2, false>(PM, count, st) : launch_persist<128, 6, 3, 1, false>(PM, count, st);
+    case 64: return kps2 ? launch_persist<64, 4, 2, 2, false>(PM, count, st) : launch_persist<64, 3, 3, 1, false>(PM, count, st);
+    default: return launch_persist<32, 3, 3, 1, false>(PM, count, st);
   }
 }
 
