@@ -12,7 +12,7 @@ from .tensor import Tensor, tensor, float16, float32, float64, int16, int32, int
 from .autograd.grad_mode import no_grad, enable_grad, set_grad_enabled, is_grad_enabled
 from .VariableFunctions import (manual_seed, add, mul, sum, mean, exp, reshape, flatten, transpose, matmul, cat, zeros,
                                 ones, empty, randn)
-from .ops import set_math_mode, get_math_mode
+from .ops import set_math_mode, get_math_mode, set_wgrad_overlap
 from .autograd.grad_nn import set_maxpool_backward_accumulate
 from . import nn
 from . import optim

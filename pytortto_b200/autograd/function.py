@@ -70,9 +70,12 @@ class AccumulateGrad(BackwardFunction):
         if var.grad is None:
             var.grad = g
         else:
+            ops.join_wgrad()  # `g` may still be in flight on the wgrad stream
             var.grad = ops.add_arrays(var.grad, g)
-        for hook in AccumulateGrad.post_hooks:
-            hook(var)
+        if AccumulateGrad.post_hooks:
+            ops.join_wgrad()
+            for hook in AccumulateGrad.post_hooks:
+                hook(var)
 
 
 class Function(FunctionBase):

@@ -169,6 +169,7 @@ struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B =
   int rect;                // 0: im2col / per-slab loads
   int pad_w, pad_h, dil_w, dil_h;
   uint16_t off_w[kMaxTaps], off_h[kMaxTaps];
+  int dbg;                 // TTB_IGEMM_DBG bits (timing experiments, wrong results): 1 no MMA, 2 no dY loads, 4 no x loads
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -609,7 +610,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     {  // whole warp runs the loop; one elected lane issues (no divergence waterfall around the TMA instructions)
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + nslab * kSlabBytes;
+      const uint32_t tx_bytes = ((P.dbg & 2) ? 0 : kABytes) + ((P.dbg & 4) ? 0 : nslab * kSlabBytes);
       for (int s = 0; s < steps; ++s) {
         const int pix0 = (step0 + s) * KP;
         int j = pix0 % P.q_dim;
@@ -623,10 +624,10 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
         if (P.rect) {
           // dY: all kASlabs channel slabs in one 3-D box (channel-in-slab, pixel, slab)
-          ptx::tma_load_3d(sa, &P.tmDy, &full_bar[stage], 0, pix0, k0 / kSlabCh);
+          if (!(P.dbg & 2)) ptx::tma_load_3d(sa, &P.tmDy, &full_bar[stage], 0, pix0, k0 / kSlabCh);
           // x: one 5-D box per filter tap covering every channel slab of that tap inside this N tile
           int sl = 0;
-          while (sl < nslab) {
+          while (sl < nslab && !(P.dbg & 4)) {
             const int col = n0 + sl * kSlabCh;
             const int tap = col / P.c;
             const int c0 = col - tap * P.c;
@@ -667,7 +668,8 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
         const uint32_t sb = sa + kABytes;
         if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KP / kMmaRows; ++k) {  // 8 (tf32) / 16 (bf16) pixel rows of every slab per MMA
+        for (int k = 0; k < KP / kMmaRows; ++k) {
+          if (P.dbg & 1) break;  // 8 (tf32) / 16 (bf16) pixel rows of every slab per MMA
           // MN-major operands: fp32 must use the 128B-span / 32B-atom swizzle (4-row K groups 512 B apart), bf16 the
           // plain 128B swizzle (8-row K groups 1024 B apart); 128-byte-wide slabs are kSlabBytes apart
           uint64_t da = ptx::umma_desc(sa + k * (kMmaRows * 128), P.desc_lbo, P.desc_sbo, P.desc_layout);
@@ -1209,6 +1211,7 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     if (ok && (bw * d->stride_w > 256 || bh * d->stride_h > 256 || bnimg > 256)) ok = false;
     P.rect = ok ? 1 : 0;
   }
+  P.dbg = igemm_dbg();
   if (P.rect) {
     const cuuint64_t es = (cuuint64_t)el.size;
     {  // dY viewed as [K/slab][pixels][slab]

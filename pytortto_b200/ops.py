@@ -84,11 +84,48 @@ def conv2d_dgrad(dy, w, d):
     return dx
 
 
-def conv2d_wgrad(x, dy, d):
+# Weight gradients are leaves of the backward pass: nothing downstream of a conv's backward needs dW before the
+# optimizer (or the gradient all-reduce), while dX is on the critical path.  With `overlap=True` the wgrad kernels go to
+# a second stream that forks from the current one, so the tensor-bound wgrad runs under the HBM-bound BatchNorm / ReLU
+# backward kernels of the next layers; `join_wgrad()` (end of Tensor.backward, or whoever reads a gradient earlier)
+# makes the current stream wait for it.  Operands are kept referenced until the join so the caching allocator cannot
+# hand their memory out again; the fork / join also works under CUDA-graph capture (a parallel branch of the graph).
+_overlap = {"enabled": os.environ.get("TORTTO_B200_WGRAD_OVERLAP", "1") != "0", "stream": {}, "keep": [], "dirty": False}
+
+
+def set_wgrad_overlap(flag):
+    join_wgrad()
+    _overlap["enabled"] = bool(flag)
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    st = _overlap["stream"].get(dev)
+    if st is None:
+        st = _overlap["stream"][dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def join_wgrad():
+    if _overlap["dirty"]:
+        torch.cuda.current_stream().wait_stream(_side_stream())
+        _overlap["keep"].clear()
+        _overlap["dirty"] = False
+
+
+def conv2d_wgrad(x, dy, d, overlap=False):
     dw = new_f32((d.k, d.c // d.groups, d.r, d.s))
     if dw.size == 0:
         return dw
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 2))
+    if overlap and _overlap["enabled"]:
+        side = _side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        _cabi.call("ttb_conv2d_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw),
+                   None if ws is None else ws.data_ptr(), nb, side.cuda_stream)
+        _overlap["keep"].append((x, dy, dw, ws))
+        _overlap["dirty"] = True
+        return dw
     _cabi.call("ttb_conv2d_wgrad", ctypes.byref(d), _ptr(x), _ptr(dy), _ptr(dw),
                None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
     return dw

@@ -233,6 +233,7 @@ class Tensor:
                     else:
                         slot[ind] = ops.add_arrays(slot[ind], g)  # out of place: producers may share `g`
             node.clear()
+        ops.join_wgrad()  # weight gradients computed on the second stream are complete for whoever runs next
 
 
 def tensor(data, requires_grad=False, dtype=None, copy=True, **kwargs):
