@@ -379,10 +379,15 @@ def main():
     ap.add_argument("--math", default="tf32", choices=["tf32", "bf16", "fp32"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph, 0: eager dispatch")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
