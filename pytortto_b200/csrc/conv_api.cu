@@ -100,9 +100,16 @@ static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
   t->p = *d;
   t->bf16 = d->math_mode == TTB_MATH_BF16;
   const int blk = igemm_channel_block(d);
-  if (pass != 1) t->p.c = (d->c + blk - 1) / blk * blk;  // dgrad has no padded variant (needs K % blk == 0)
+  if (pass != 1) {
+    t->p.c = (d->c + blk - 1) / blk * blk;
+  } else {
+    // dgrad reduces over the output channels (zero-padded to whole K-blocks in the staged dy / w copies) and writes
+    // the input channels (a narrow dx, e.g. a 3-channel image, is produced 8 channels wide and cropped)
+    t->p.k = (d->k + blk - 1) / blk * blk;
+    t->p.c = (d->c + 7) / 8 * 8;
+  }
   if (!igemm_supported(&t->p, pass)) return false;
-  const bool padded = t->p.c != d->c;
+  const bool padded = t->p.c != d->c || t->p.k != d->k;
   t->stage_ops = t->bf16 || padded;
   const size_t es = t->bf16 ? 2 : 4;
   t->a_bytes = t->b_bytes = t->c_bytes = 0;
@@ -112,8 +119,9 @@ static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
       t->a_bytes = align256(xrows * t->p.c * es);
       t->b_bytes = align256(wrows * t->p.c * es);
     } else if (pass == 1) {
-      t->a_bytes = align256(yrows * d->k * es);
-      t->b_bytes = align256(wrows * d->c * es);
+      t->a_bytes = align256(yrows * t->p.k * es);
+      t->b_bytes = align256((size_t)t->p.k * d->r * d->s * t->p.c * es);
+      t->c_bytes = t->p.c != d->c ? align256(xrows * t->p.c * sizeof(float)) : 0;
     } else {
       t->a_bytes = align256(xrows * t->p.c * es);
       t->b_bytes = t->bf16 ? align256(yrows * d->k * es) : 0;
@@ -185,13 +193,30 @@ int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, fl
               need, workspace_bytes);
   char* ws = reinterpret_cast<char*>(workspace);
   const void *dya = dy, *wa = w;
-  if (t.stage_ops) {  // bf16 only (dgrad has no channel padding)
-    if (stage(dy, ws, (int64_t)d->n * d->p * d->q, d->k, d->k, t.bf16, st)) return 1;
-    if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, d->c, t.bf16, st)) return 1;
+  float* dxa = dx;
+  if (t.stage_ops) {  // bf16 conversion and / or channel padding (K to whole K-blocks, C to a multiple of 8)
+    if (stage(dy, ws, (int64_t)d->n * d->p * d->q, d->k, t.p.k, t.bf16, st)) return 1;
+    const int64_t wrows = (int64_t)d->k * d->r * d->s;
+    if (stage(w, ws + t.a_bytes, wrows, d->c, t.p.c, t.bf16, st)) return 1;
+    if (t.p.k != d->k) {  // filters k >= K do not exist: zero rows
+      const size_t row_bytes = (size_t)t.p.c * (t.bf16 ? 2 : 4);
+      const size_t tail = (size_t)(t.p.k - d->k) * d->r * d->s * row_bytes;
+      if (cudaMemsetAsync(ws + t.a_bytes + (size_t)wrows * row_bytes, 0, tail, st) != cudaSuccess) {
+        set_error("conv2d_dgrad: memset of the padded filters failed");
+        return 1;
+      }
+    }
     dya = ws;
     wa = ws + t.a_bytes;
+    if (t.c_bytes) dxa = reinterpret_cast<float*>(ws + t.a_bytes + t.b_bytes);
   }
-  return igemm_dgrad(&t.p, dya, wa, dx, ws + t.a_bytes + t.b_bytes, t.inner, st);
+  if (int rc = igemm_dgrad(&t.p, dya, wa, dxa, ws + t.a_bytes + t.b_bytes + t.c_bytes, t.inner, st)) return rc;
+  if (t.c_bytes) {
+    const int64_t xrows = (int64_t)d->n * d->h * d->w;
+    unpad_channels_kernel<<<elementwise_grid(xrows * d->c, 256), 256, 0, st>>>(dxa, dx, xrows, d->c, t.p.c);
+    return check_launch("unpad_channels");
+  }
+  return 0;
 }
 
 int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,

@@ -86,10 +86,9 @@ def test_conv2d_tensor_path_vs_oracle(case, mode):
     desc = ops.conv_desc(x.shape, wt.shape, (s, s), (p, p), (d, d), 1)
     used = [_cabi.load().ttb_conv2d_tensor_path_supported(ctypes.byref(desc), i) for i in range(3)]
     print("tensor path used (fprop, dgrad, wgrad):", used)
-    # dgrad contracts over output channels: its tensor path needs Cout % 32 (tf32) / % 64 (bf16) == 0, otherwise the
-    # exact direct kernel runs; fprop / wgrad pad the input channels when needed
-    blk = 32 if mode == "tf32" else 64
-    assert used == [1, 1 if co % blk == 0 else 0, 1], "this case is meant to exercise the tcgen05 path"
+    # every pass pads its reduction channels to whole K-blocks (32 tf32 / 64 bf16) in a staged copy when needed, and
+    # dgrad a narrow dx to 8 channels, so all three run on the tensor path
+    assert used == [1, 1, 1], "this case is meant to exercise the tcgen05 path"
     tol = TOL[mode]
     assert_close("y", y, yo, tol)
     assert_close("dx", dx, dxo, tol)
@@ -182,7 +181,8 @@ def test_batch_norm_vs_oracle_large():
 
 
 def test_stem_conv_runs_on_tensor_path_via_channel_padding():
-    """Cin = 3 (network stems) is zero-padded to 32 channels and runs fprop + wgrad on tcgen05."""
+    """Cin = 3 (network stems) is zero-padded to 32 channels for fprop + wgrad, and dgrad writes an 8-channel dx that
+    is cropped to 3: all three passes run on tcgen05."""
     tt = _tt("tf32")
     import ctypes
     from pytortto_b200 import _cabi, ops
@@ -193,10 +193,10 @@ def test_stem_conv_runs_on_tensor_path_via_channel_padding():
     dy = rng.standard_normal(yo.shape).astype(np.float32)
     dxo, dwo, _ = O.conv2d_backward(x, wt, dy, 1, 1, 1)
     desc = ops.conv_desc(x.shape, wt.shape, (1, 1), (1, 1), (1, 1), 1)
-    assert [_cabi.load().ttb_conv2d_tensor_path_supported(ctypes.byref(desc), i) for i in range(3)] == [1, 0, 1]
+    assert [_cabi.load().ttb_conv2d_tensor_path_supported(ctypes.byref(desc), i) for i in range(3)] == [1, 1, 1]
     y, dx, dw, _ = _run_conv(tt, x, wt, None, dy, (1, 1), (1, 1), (1, 1), 1)
     assert_close("stem y", y, yo, 2e-3)
-    assert_close("stem dx", dx, dxo, 2e-5)   # exact direct kernel
+    assert_close("stem dx", dx, dxo, 2e-3)
     assert_close("stem dw", dw, dwo, 2e-3)
 
 
