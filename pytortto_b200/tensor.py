@@ -117,6 +117,15 @@ class Tensor:
     def item(self):
         return self.data.item()
 
+    def item_async(self):
+        """Extension (not in the reference): start the device->host copy of a one-element CUDA tensor into pinned
+        memory on the current stream and return a handle; `handle.get()` waits for that copy only.  Lets a training
+        loop read step i's loss after it has queued step i+1 instead of draining the GPU every step."""
+        if not self.is_cuda:
+            v = self.data.item()
+            return _ReadyScalar(v)
+        return _PendingScalar(self.data.t)
+
     def data_ptr(self):
         return self.data.data.ptr if self.is_cuda else self.data.ctypes.data
 
@@ -234,6 +243,34 @@ class Tensor:
                         slot[ind] = ops.add_arrays(slot[ind], g)  # out of place: producers may share `g`
             node.clear()
         ops.join_wgrad()  # weight gradients computed on the second stream are complete for whoever runs next
+
+
+class _ReadyScalar:
+    def __init__(self, v):
+        self._v = v
+
+    def get(self):
+        return self._v
+
+
+class _PendingScalar:
+    _pool = []  # recycled (pinned buffer, event) pairs
+
+    def __init__(self, t):
+        import torch
+        if t.numel() != 1:
+            raise ValueError("only one element tensors can be converted to Python scalars")
+        self._buf, self._ev = _PendingScalar._pool.pop() if _PendingScalar._pool else (
+            torch.empty(1, dtype=torch.float64).pin_memory(), torch.cuda.Event())
+        self._host = self._buf.view(torch.uint8)[:t.element_size()].view(t.dtype)
+        self._host.copy_(t.reshape(1), non_blocking=True)
+        self._ev.record()
+
+    def get(self):
+        self._ev.synchronize()
+        v = self._host.item()
+        _PendingScalar._pool.append((self._buf, self._ev))
+        return v
 
 
 def tensor(data, requires_grad=False, dtype=None, copy=True, **kwargs):

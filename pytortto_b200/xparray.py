@@ -79,7 +79,7 @@ class cparray:
             n, c, h, w = a.shape
             _cabi.call("ttb_nchw_to_nhwc", staged.data_ptr(), out.data_ptr(), n, c, h, w, current_stream_ptr())
             return cls(out)
-        return cls(host.to(_device()))
+        return cls(host.to(_device(), non_blocking=host.is_pinned()))  # pinned source: truly asynchronous
 
     def get(self):
         """Device -> host numpy array in the logical (reference) index order."""

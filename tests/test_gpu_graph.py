@@ -50,3 +50,12 @@ def test_graphed_step_matches_eager():
     assert eager_losses == graph_losses
     for k in eager_sd:
         np.testing.assert_array_equal(eager_sd[k], graph_sd[k], err_msg=k)
+
+
+def test_item_async_matches_item():
+    """Tensor.item_async(): the pinned D2H read-back used by pipelined training loops returns what item() returns."""
+    import pytortto_b200 as tt
+    vals = [tt.tensor(np.array([v], dtype=np.float32)).cuda() for v in (1.5, -2.25, 3.0)]
+    handles = [(v + v).item_async() for v in vals]  # all queued before the first one is read
+    assert [h.get() for h in handles] == [3.0, -4.5, 6.0]
+    assert tt.tensor(np.array([7.0], dtype=np.float32)).item_async().get() == 7.0  # host tensor: immediate
