@@ -201,7 +201,7 @@ def run_ours(args):
         raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", sync_bn=os.environ.get("TORTTO_B200_DEBUG_NO_SYNCBN") != "1")
     tt.set_math_mode(args.math)
     cfg = MODELS[args.model]
     M = make_models(tt)

@@ -85,6 +85,24 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
 /* db[K] = sum over rows of dy[M,K] */
 int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void* stream);
 
+/* Multi-tensor forms of the two small per-layer helpers of the backward pass: a training step has ~20 dgrad weight
+ * re-orderings and ~20 wgrad split reductions, each a latency-bound launch on its own; these do all layers in one.
+ *   ttb_conv2d_dgrad_prepacked_supported  1 if dgrad of this problem can take pre-packed weights (tensor path without a
+ *                                         staged copy), else use ttb_conv2d_dgrad
+ *   ttb_conv2d_dgrad_pack_weights         w[i] ([K][R][S][C]) -> w_packed[i] ([C][R][S][K], same size) for count layers
+ *   ttb_conv2d_dgrad_prepacked            ttb_conv2d_dgrad on weights packed by the call above (no workspace)
+ *   ttb_conv2d_wgrad_partial              ttb_conv2d_wgrad without the split reduction: leaves *splits_out partial
+ *                                         buffers of K*R*S*C floats at *partials_out (inside workspace); <= 1: dw is final
+ *   ttb_sum_splits_multi                  outs[i][e] = sum_s partials[i][s*sizes[i] + e], fixed order, count tensors   */
+int ttb_conv2d_dgrad_prepacked_supported(const ttb_conv_desc* d);
+int ttb_conv2d_dgrad_pack_weights(int count, const ttb_conv_desc* const* descs, const float* const* w,
+                                  float* const* w_packed, void* stream);
+int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, void* stream);
+int ttb_conv2d_wgrad_partial(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
+                             size_t workspace_bytes, int* splits_out, const float** partials_out, void* stream);
+int ttb_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
+                         float* const* outs, void* stream);
+
 /* ---- batch norm (x viewed as [M = N*H*W rows][C channels]) ---------------------------------------------- */
 /* number of row chunks ttb_bn_stats / ttb_bn_bwd_reduce emit partial sums for */
 int ttb_bn_num_chunks(int64_t m, int c);

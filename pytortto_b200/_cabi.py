@@ -39,6 +39,11 @@ _PROTOS = {
     "ttb_conv2d_dgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
     "ttb_conv2d_wgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
     "ttb_bias_grad": (c_int, [_F, _F, c_int64, c_int, c_void_p]),
+    "ttb_conv2d_dgrad_prepacked_supported": (c_int, [POINTER(ConvDesc)]),
+    "ttb_conv2d_dgrad_pack_weights": (c_int, [c_int, POINTER(POINTER(ConvDesc)), POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
+    "ttb_conv2d_dgrad_prepacked": (c_int, [POINTER(ConvDesc), _F, _F, _F, c_void_p]),
+    "ttb_conv2d_wgrad_partial": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, POINTER(c_int), POINTER(c_void_p), c_void_p]),
+    "ttb_sum_splits_multi": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int64), POINTER(c_void_p), c_void_p]),
     "ttb_bn_num_chunks": (c_int, [c_int64, c_int]),
     "ttb_bn_stats": (c_int, [_F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_reduce_partials": (c_int, [_F, c_int, c_int, _F, c_void_p]),

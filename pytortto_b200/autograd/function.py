@@ -72,10 +72,8 @@ class AccumulateGrad(BackwardFunction):
         else:
             ops.join_wgrad()  # `g` may still be in flight on the wgrad stream
             var.grad = ops.add_arrays(var.grad, g)
-        if AccumulateGrad.post_hooks:
-            ops.join_wgrad()
-            for hook in AccumulateGrad.post_hooks:
-                hook(var)
+        for hook in AccumulateGrad.post_hooks:  # a hook that READS var.grad on the device calls ops.join_wgrad() first
+            hook(var)
 
 
 class Function(FunctionBase):

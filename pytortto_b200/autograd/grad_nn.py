@@ -79,6 +79,8 @@ class Convolution(Function):
         yt0 = build_links(yd0, grad_fn=ctx)
         ctx.save_for_backward(xt0, xt1)
         ctx.params['desc'] = d
+        if xt0.requires_grad:
+            ops.register_dgrad_weight(xd1, d)  # its dgrad re-ordering joins the step's one multi-tensor launch
         return yt0
 
     @staticmethod

@@ -67,43 +67,50 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
   }
   sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  bool failed = false;
+  __shared__ double mine_sm[32];
   if (threadIdx.y == 0 && i < n) {
     double mine = 0.0;
     for (int j = 0; j < 32; ++j) mine += sm[j][threadIdx.x];
+    mine_sm[threadIdx.x] = mine;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
     const unsigned long long tag = (unsigned long long)seq << 32;
     unsigned long long* w = reinterpret_cast<unsigned long long*>(own + kSlotHeaderBytes) + 2 * (size_t)i;
     st_volatile_u64(w, tag | (bits & 0xffffffffull));
     st_volatile_u64(w + 1, tag | (bits >> 32));
-    double vals[kMaxWorld];
-    unsigned int pending = 0;
-    for (int r = 0; r < world; ++r)
-      if (r != rank) pending |= 1u << r;
-    vals[rank] = mine;
-    unsigned long long spins = 0;
-    while (pending) {
-      for (int r = 0; r < world; ++r) {
-        if (!(pending >> r & 1u)) continue;
-        const unsigned long long* pw =
-            reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes) + 2 * (size_t)i;
-        const unsigned long long a = ld_volatile_u64(pw), b = ld_volatile_u64(pw + 1);
-        if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) {
-          vals[r] = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
-          pending &= ~(1u << r);
+  }
+  __syncthreads();  // sm[][] is reused below: row r = the value of rank r
+  // thread (x = value, y = peer rank) polls ONE peer, so the NVLink round trips of all peers overlap (polled one after
+  // the other by a single thread, an exchange took ~1.5 us per peer); rank order is restored by the sum below
+  bool failed = false;
+  const int r = threadIdx.y;
+  if (r < world && i < n) {
+    double v;
+    if (r == rank) {
+      v = mine_sm[threadIdx.x];
+    } else {
+      const unsigned long long* pw =
+          reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes) + 2 * (size_t)i;
+      unsigned long long a, b, spins = 0;
+      for (;;) {
+        a = ld_volatile_u64(pw);
+        b = ld_volatile_u64(pw + 1);
+        if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+        if (++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly, do not hang
+          failed = true;
+          break;
         }
       }
-      if (pending && ++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly, do not hang
-        failed = true;
-        break;
-      }
+      v = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
     }
-    double acc = 0.0;
-    for (int r = 0; r < world; ++r) acc += vals[r];
-    out[i] = acc;
+    sm[r][threadIdx.x] = v;
   }
   if (failed) __trap();
   __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    double acc = 0.0;
+    for (int q = 0; q < world; ++q) acc += sm[q][threadIdx.x];  // rank order => the same bits on every rank
+    out[i] = acc;
+  }
   if (threadIdx.x == 0 && threadIdx.y == 0) {
     __threadfence();
     const unsigned int ticket = atomicAdd(&hdr->arrive, 1u);

@@ -26,9 +26,13 @@ size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
 int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* ws,
                 size_t ws_bytes, cudaStream_t st);
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st);
+                cudaStream_t st, const void* prepacked = nullptr);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-                cudaStream_t st);
+                cudaStream_t st, int* splits_out = nullptr);
+int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const float* const* w, float* const* wt,
+                             cudaStream_t st);
+int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
+                           float* const* outs, cudaStream_t st);
 
 // [rows][c] fp32 -> [rows][cp] OutT (zero-filled channels c..cp-1); 4 output channels per thread
 template <class OutT>
@@ -247,6 +251,56 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
     return check_launch("unpad_channels");
   }
   return 0;
+}
+
+/* ---- multi-tensor forms of the two small per-layer helpers (one launch for all layers of a step) ----------- */
+
+/* 1 if dgrad of this problem can consume weights pre-packed by ttb_conv2d_dgrad_pack_weights (tensor path without a
+ * staged copy: TF32, Cout % 32 == 0, Cin % 8 == 0, groups == 1) */
+int ttb_conv2d_dgrad_prepacked_supported(const ttb_conv_desc* d) {
+  if (!d) return 0;
+  TensorPlan t;
+  return (plan_tensor(d, 1, &t) && !t.stage_ops) ? 1 : 0;
+}
+
+/* w[i] (Cout, Cin, kh, kw channels-last = [K][R][S][C]) -> w_packed[i] [C][R][S][K], same byte size, for `count` layers */
+int ttb_conv2d_dgrad_pack_weights(int count, const ttb_conv_desc* const* descs, const float* const* w,
+                                  float* const* w_packed, void* stream) {
+  TTB_REQUIRE(count >= 0 && (count == 0 || (descs && w && w_packed)), "dgrad_pack_weights: bad arguments");
+  for (int i = 0; i < count; ++i)
+    TTB_REQUIRE(ttb_conv2d_dgrad_prepacked_supported(descs[i]), "dgrad_pack_weights: layer %d cannot use packed weights", i);
+  return igemm_pack_dgrad_weights(count, descs, w, w_packed, as_stream(stream));
+}
+
+int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, void* stream) {
+  if (int rc = validate(d, "conv2d_dgrad_prepacked")) return rc;
+  TensorPlan t;
+  TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops, "conv2d_dgrad_prepacked: problem needs the staged path");
+  return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed);
+}
+
+/* ttb_conv2d_wgrad without the split reduction: *splits_out partial buffers of K*R*S*C floats are left at
+ * *partials_out (inside workspace) for ttb_sum_splits_multi; *splits_out <= 1 means dw is final.  Problems that need a
+ * staged / padded copy are reduced immediately (then *splits_out = 0). */
+int ttb_conv2d_wgrad_partial(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
+                             size_t workspace_bytes, int* splits_out, const float** partials_out, void* stream) {
+  TTB_REQUIRE(splits_out && partials_out, "conv2d_wgrad_partial: null outputs");
+  *splits_out = 0;
+  *partials_out = nullptr;
+  if (int rc = validate(d, "conv2d_wgrad_partial")) return rc;
+  TensorPlan t;
+  if (!plan_tensor(d, 2, &t) || t.stage_ops) return ttb_conv2d_wgrad(d, x, dy, dw, workspace, workspace_bytes, stream);
+  TTB_REQUIRE(t.inner == 0 || (workspace != nullptr && workspace_bytes >= t.inner),
+              "conv2d_wgrad_partial: workspace of %zu bytes needed, %zu given", t.inner, workspace_bytes);
+  if (int rc = igemm_wgrad(&t.p, x, dy, dw, workspace, t.inner, as_stream(stream), splits_out)) return rc;
+  *partials_out = reinterpret_cast<const float*>(workspace);
+  return 0;
+}
+
+int ttb_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
+                         float* const* outs, void* stream) {
+  TTB_REQUIRE(count >= 0 && (count == 0 || (partials && splits && sizes && outs)), "sum_splits_multi: bad arguments");
+  return igemm_sum_splits_multi(count, partials, splits, sizes, outs, as_stream(stream));
 }
 
 /* diagnostics: device buffer (>= 1100 int64) that CTA (0,0) of every following fprop igemm launch fills with

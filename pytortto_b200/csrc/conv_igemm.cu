@@ -724,6 +724,65 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
   }
 }
 
+// Multi-tensor forms: one launch repacks the dgrad weights / sums the wgrad splits of up to kMaxBatch layers (a training
+// step has ~20 of each, every one a few-microsecond latency-bound launch on its own).  Work is cut into 1024-element
+// chunks; start[i] = first chunk of tensor i.
+constexpr int kMaxBatch = 32;
+constexpr int kBatchChunk = 1024;
+struct RepackBatch {
+  const float* w[kMaxBatch];
+  float* wt[kMaxBatch];
+  int K[kMaxBatch], T[kMaxBatch], C[kMaxBatch];
+  int start[kMaxBatch + 1];
+  int count;
+};
+struct SumBatch {
+  const float* partial[kMaxBatch];
+  float* out[kMaxBatch];
+  int splits[kMaxBatch];
+  int64_t n[kMaxBatch];
+  int start[kMaxBatch + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) repack_multi_kernel(const __grid_constant__ RepackBatch B) {
+  const int chunks = B.start[B.count];
+  for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    int i = 0;
+    while (i + 1 < B.count && ch >= B.start[i + 1]) ++i;
+    const int K = B.K[i], T = B.T[i], C = B.C[i];
+    const int64_t total = (int64_t)K * T * C;
+    const int64_t e0 = (int64_t)(ch - B.start[i]) * kBatchChunk;
+    const float* __restrict__ w = B.w[i];
+    float* __restrict__ wt = B.wt[i];
+    for (int64_t e = e0 + threadIdx.x; e < e0 + kBatchChunk && e < total; e += blockDim.x) {
+      const int k = (int)(e % K);
+      const int64_t r = e / K;
+      const int t = (int)(r % T);
+      const int c = (int)(r / T);
+      wt[e] = w[((int64_t)k * T + t) * C + c];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_splits_multi_kernel(const __grid_constant__ SumBatch B) {
+  const int chunks = B.start[B.count];
+  for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+    int i = 0;
+    while (i + 1 < B.count && ch >= B.start[i + 1]) ++i;
+    const int64_t n = B.n[i];
+    const int splits = B.splits[i];
+    const float* __restrict__ partial = B.partial[i];
+    float* __restrict__ out = B.out[i];
+    const int64_t e0 = (int64_t)(ch - B.start[i]) * kBatchChunk;
+    for (int64_t e = e0 + threadIdx.x; e < e0 + kBatchChunk && e < n; e += blockDim.x) {
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += partial[(int64_t)sp * n + e];  // fixed order: deterministic
+      out[e] = acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host: support checks, tile selection, launches
 // ------------------------------------------------------------------------------------------------------------
@@ -1031,14 +1090,16 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
   return launch_fwd_bn(P, bn, el.bf16, st);
 }
 
+// `prepacked` != null: the weights are already in the [C][R][S][K] order (igemm_pack_dgrad_weights), w / ws unused
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, const void* prepacked) {
   if (load_driver_fns()) return 1;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * el.size;
-  TTB_REQUIRE(ws != nullptr && ws_bytes >= wbytes, "conv2d_dgrad: workspace of %zu bytes needed, %zu given", wbytes, ws_bytes);
+  if (!prepacked)
+    TTB_REQUIRE(ws != nullptr && ws_bytes >= wbytes, "conv2d_dgrad: workspace of %zu bytes needed, %zu given", wbytes, ws_bytes);
   const int T = d->r * d->s;
-  {
+  if (!prepacked) {
     int64_t total = (int64_t)d->k * T * d->c;
     if (el.bf16)
       repack_krsc_to_crsk_kernel<uint16_t><<<elementwise_grid(total, 256), 256, 0, st>>>(
@@ -1048,7 +1109,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
           reinterpret_cast<const float*>(w), reinterpret_cast<float*>(ws), d->k, T, d->c);
     if (check_launch("repack_krsc_to_crsk")) return 1;
   }
-  const void* wt = ws;
+  const void* wt = prepacked ? prepacked : ws;
   // Stride-parity classes: input rows h = a + sh*i only receive taps r with (a + ph - r*dh) % sh == 0, from output
   // row p = i + (a + ph - r*dh)/sh.  Each class is a stride-1 gather over dY - no zero insertion, no wasted MACs.
   bool need_zero = false;
@@ -1163,8 +1224,10 @@ static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits
   return check_launch("igemm_wgrad_kernel");
 }
 
+// `splits_out` != null: the caller sums the splits (igemm_sum_splits_multi); *splits_out = number of partial buffers
+// [K*R*S*C] at the start of ws (<= 1: dw is already final)
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, int* splits_out) {
   if (load_driver_fns()) return 1;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   int bn, splits, sps, total;
@@ -1292,9 +1355,61 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     }
   }
   if (rc) return rc;
+  if (splits_out) {
+    *splits_out = splits;
+    return 0;
+  }
   if (splits > 1) {
     sum_splits_kernel<<<elementwise_grid(wsize, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws), splits, wsize, dw);
     return check_launch("wgrad sum_splits");
+  }
+  return 0;
+}
+
+int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const float* const* w, float* const* wt,
+                             cudaStream_t st) {
+  for (int base = 0; base < count; base += kMaxBatch) {
+    static thread_local RepackBatch B;
+    B.count = count - base < kMaxBatch ? count - base : kMaxBatch;
+    int chunks = 0;
+    for (int i = 0; i < B.count; ++i) {
+      const ttb_conv_desc* d = descs[base + i];
+      B.w[i] = w[base + i];
+      B.wt[i] = wt[base + i];
+      B.K[i] = d->k;
+      B.T[i] = d->r * d->s;
+      B.C[i] = d->c;
+      B.start[i] = chunks;
+      chunks += (int)ceil_div((int64_t)d->k * d->r * d->s * d->c, kBatchChunk);
+    }
+    B.start[B.count] = chunks;
+    if (chunks == 0) continue;
+    const int grid = chunks < sm_count() * 8 ? chunks : sm_count() * 8;
+    repack_multi_kernel<<<grid, 256, 0, st>>>(B);
+    if (check_launch("repack_multi")) return 1;
+  }
+  return 0;
+}
+
+int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
+                           float* const* outs, cudaStream_t st) {
+  for (int base = 0; base < count; base += kMaxBatch) {
+    static thread_local SumBatch B;
+    B.count = count - base < kMaxBatch ? count - base : kMaxBatch;
+    int chunks = 0;
+    for (int i = 0; i < B.count; ++i) {
+      B.partial[i] = partials[base + i];
+      B.out[i] = outs[base + i];
+      B.splits[i] = splits[base + i];
+      B.n[i] = sizes[base + i];
+      B.start[i] = chunks;
+      chunks += (int)ceil_div(sizes[base + i], (int64_t)kBatchChunk);
+    }
+    B.start[B.count] = chunks;
+    if (chunks == 0) continue;
+    const int grid = chunks < sm_count() * 8 ? chunks : sm_count() * 8;
+    sum_splits_multi_kernel<<<grid, 256, 0, st>>>(B);
+    if (check_launch("sum_splits_multi")) return 1;
   }
   return 0;
 }

@@ -8,7 +8,7 @@ concatenated batch:
 1. Parameter gradients.  Every rank back-propagates the mean loss of ITS shard.  `DistributedDataParallel` hooks
    `AccumulateGrad` (the leaf node of the autograd graph, reference autograd/function.py:70-93): as soon as a
    parameter's gradient is final it is appended to the current bucket (reverse parameter order = the order
-   backward produces them); a full bucket (~25 MB) is flattened and all-reduced (SUM) asynchronously on NCCL's own
+   backward produces them); a full bucket (~10 MB) is flattened and all-reduced (SUM) asynchronously on NCCL's own
    stream while the rest of backward keeps the compute stream busy.  `reduce_gradients()` (called between
    `loss.backward()` and `optimizer.step()`) waits for the outstanding buckets, scales by 1/world - the mean over
    ranks of local-mean gradients IS the global-batch mean gradient - and scatters the result back into `p.grad`.
@@ -25,6 +25,7 @@ import os
 import numpy as np
 import torch
 
+from . import ops
 from .autograd.function import AccumulateGrad
 
 _state = {"initialized": False, "world": 1, "rank": 0, "sync_bn": True, "backend": None, "peer_comm": None}
@@ -70,11 +71,15 @@ def destroy_process_group():
     _state.update(initialized=False, world=1, rank=0, peer_comm=None)
 
 
-def all_reduce_sum_(t, async_op=False):
-    """In-place SUM all-reduce of a torch tensor (no-op for world 1).  Returns the work handle when async."""
+def all_reduce_sum_(t, async_op=False, average=False):
+    """In-place SUM (or, with `average` on NCCL, AVG) all-reduce of a torch tensor (no-op for world 1).  Returns the
+    work handle when async."""
     if _state["initialized"] and _state["world"] > 1:
+        if os.environ.get("TORTTO_B200_DEBUG_SKIP_GRAD_ALLREDUCE") == "1":  # timing experiments only (wrong results)
+            return None
         import torch.distributed as dist
-        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
+        op = dist.ReduceOp.AVG if (average and _state["backend"] == "nccl") else dist.ReduceOp.SUM
+        return dist.all_reduce(t, op=op, async_op=async_op)
     return None
 
 
@@ -214,17 +219,19 @@ def _flat_view(t):
 
 
 class _Bucket:
-    __slots__ = ("params", "flat", "work")
+    __slots__ = ("params", "flat", "work", "averaged")
 
     def __init__(self, params):
         self.params = params
         self.flat = torch.cat([_flat_view(p.grad.t) for p in params])
-        self.work = all_reduce_sum_(self.flat, async_op=True)
+        self.averaged = _state["backend"] == "nccl"  # NCCL divides by the world size inside the collective
+        self.work = all_reduce_sum_(self.flat, async_op=True, average=True)
 
     def finish(self, inv_world, skip=()):
         if self.work is not None:
             self.work.wait()  # makes the current stream wait for the collective
-        self.flat.mul_(inv_world)
+        if not self.averaged:
+            self.flat.mul_(inv_world)
         off = 0
         dsts, srcs = [], []
         for p in self.params:
@@ -242,7 +249,7 @@ class DistributedDataParallel:
     """Wraps a Module.  Forward is unchanged; gradients are all-reduced in buckets that start during backward
     (AccumulateGrad hook) and complete in `reduce_gradients()`."""
 
-    def __init__(self, module, bucket_mb=25, broadcast=True, overlap=True):
+    def __init__(self, module, bucket_mb=10, broadcast=True, overlap=True):
         self.module = module
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.overlap = overlap
@@ -292,6 +299,7 @@ class DistributedDataParallel:
 
     def _launch_pending(self):
         if self._pending:
+            ops.join_wgrad()  # weight gradients still in flight on the wgrad stream are packed below
             self._buckets.append(_Bucket(self._pending))
             self._pending, self._pending_bytes = [], 0
 
@@ -309,12 +317,13 @@ class DistributedDataParallel:
             done.update(id(p) for p in b.params)
         # whatever was not bucketed during backward (overlap off, re-used parameters, grads set by hand)
         rest, size = [], 0
+        bn_grads = []
         for p in reversed(list(self.module.parameters())):
             if p.grad is None:
                 continue
             pid = id(p)
             if pid in self._synced_bn_params:
-                p.grad.t.mul_(inv)  # identical on all ranks and already the sum over ranks (see module docstring)
+                bn_grads.append(p.grad.t)  # identical on all ranks and already the sum over ranks (module docstring)
                 continue
             if pid in done and pid not in dirty:
                 continue
@@ -325,4 +334,6 @@ class DistributedDataParallel:
                 rest, size = [], 0
         if rest:
             _Bucket(rest).finish(inv)
+        if bn_grads:
+            torch._foreach_mul_(bn_grads, inv)  # one multi-tensor launch for the ~2 x (#BatchNorm layers) tiny tensors
         self._buckets, self._seen = [], set()

@@ -229,6 +229,13 @@ class Tensor:
             acc.apply(gradient)
             return
         self.grad_fn.grad[self._output_idx] = gradient
+        ops.begin_backward_sweep()
+        try:
+            self._sweep(ops)
+        finally:
+            ops.end_backward_sweep()
+
+    def _sweep(self, ops):
         for node in toposort(self.grad_fn):
             grads = node.apply(*node.grad)
             nf = node.next_functions
@@ -242,7 +249,6 @@ class Tensor:
                     else:
                         slot[ind] = ops.add_arrays(slot[ind], g)  # out of place: producers may share `g`
             node.clear()
-        ops.join_wgrad()  # weight gradients computed on the second stream are complete for whoever runs next
 
 
 class _ReadyScalar:
