@@ -132,8 +132,10 @@ int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const 
  * coefficients of dx = c1*(dy - c2 - (x-mean)*c3)  (grad_nn.py:984-988 re-associated) */
 int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef /*[3][C]*/, void* stream);
+/* dx = c1*(dy - c2 - (x-mean)*c3) [+ accum]; accum (may be null): a gradient that already reached the same tensor
+ * through another branch, i.e. the engine's `grad += new` (tensor.py:597-599) folded into this pass */
 int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
-                     float* dx, int64_t m, int c, void* stream);
+                     const float* accum, float* dx, int64_t m, int c, void* stream);
 
 /* ---- relu / elementwise ---------------------------------------------------------------------------------- */
 int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream);              /* y may alias x (in-place) */

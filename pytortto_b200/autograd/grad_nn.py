@@ -7,6 +7,7 @@ lines cited per class), so `nn.functional` and the modules above it are unchange
 the boundary: no `x_padded` copy is kept for wgrad (the TMA im2col load zero-fills the halo), dgrad is a gather
 (no zero-inserted `grad_dilated`), BN is two fused passes per direction.
 """
+import os
 import math
 
 from .. import ops
@@ -264,9 +265,16 @@ class _BatchNormBase(Function):
         relu_out = saved[2] if cls._fuse_relu else None
         from .. import distributed as dist
         hook = dist.bn_backward_hook(ctx.params['sync_key']) if ctx.params['synced'] else None
+        # `_accum0`: a gradient that already reached the input through another branch (the residual shortcut); the
+        # engine hands it over (Tensor._sweep) and the dx pass adds it instead of a separate add kernel
+        accum = ctx.params.pop('_accum0', None)
         return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'], relu_out=relu_out,
                                need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
-                               need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook)
+                               need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook, accum=accum)
+
+
+# its backward can fold the pending gradient of input 0 into dx (TORTTO_B200_FOLD_ACCUM=0: separate add kernel)
+_BatchNormBase._accumulates_input0 = os.environ.get("TORTTO_B200_FOLD_ACCUM", "1") != "0"
 
 
 class BatchNormRelu(_BatchNormBase):

@@ -303,12 +303,13 @@ __global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __res
   }
 }
 
-// dx = c1*(g - c2 - (x-mean)*c3), g = dy (masked by relu_out > 0 when given)
+// dx = c1*(g - c2 - (x-mean)*c3) [+ accum], g = dy (masked by relu_out > 0 when given).  `accum`: a gradient that already
+// reached the same tensor through another branch (the residual shortcut) - added here instead of by a separate kernel.
 template <bool MASK>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                    const float* __restrict__ mask, const float* __restrict__ coef, float* __restrict__ dx,
-                    int64_t n4, int cq, int c) {
+                    const float* __restrict__ mask, const float* __restrict__ coef, const float* __restrict__ accum,
+                    float* __restrict__ dx, int64_t n4, int cq, int c) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int q = (int)(i % cq);
@@ -325,6 +326,10 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
     r.y = c1.y * (g.y - c2.y - (v.y - mu.y) * c3.y);
     r.z = c1.z * (g.z - c2.z - (v.z - mu.z) * c3.z);
     r.w = c1.w * (g.w - c2.w - (v.w - mu.w) * c3.w);
+    if (accum) {
+      float4 a = ld_f4_stream(accum + 4 * i);
+      r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+    }
     st_f4(dx + 4 * i, r);
   }
 }
@@ -332,13 +337,15 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
 template <bool MASK>
 __global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                            const float* __restrict__ mean, const float* __restrict__ mask,
-                                           const float* __restrict__ coef, float* __restrict__ dx, int64_t n, int c) {
+                                           const float* __restrict__ coef, const float* __restrict__ accum,
+                                           float* __restrict__ dx, int64_t n, int c) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int ch = (int)(i % c);
     float g = dy[i];
     if (MASK) g = mask[i] > 0.f ? g : 0.f;
-    dx[i] = coef[ch] * (g - coef[c + ch] - (x[i] - mean[ch]) * coef[2 * c + ch]);
+    float r = coef[ch] * (g - coef[c + ch] - (x[i] - mean[ch]) * coef[2 * c + ch]);
+    dx[i] = accum ? r + accum[i] : r;
   }
 }
 
@@ -437,19 +444,20 @@ int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c
 }
 
 int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
-                     float* dx, int64_t m, int c, void* stream) {
+                     const float* accum, float* dx, int64_t m, int c, void* stream) {
   int64_t n = m * c;
   if (n <= 0) return 0;
   cudaStream_t st = as_stream(stream);
-  bool vec = c % 4 == 0 && a16(dy) && a16(x) && a16(dx) && a16(mean) && a16(coef) && (!relu_out || a16(relu_out));
+  bool vec = c % 4 == 0 && a16(dy) && a16(x) && a16(dx) && a16(mean) && a16(coef) && (!relu_out || a16(relu_out)) &&
+             (!accum || a16(accum));
   if (vec) {
     int grid = elementwise_grid(n / 4, 256);
-    if (relu_out) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n / 4, c / 4, c);
-    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n / 4, c / 4, c);
+    if (relu_out) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n / 4, c / 4, c);
+    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n / 4, c / 4, c);
   } else {
     int grid = elementwise_grid(n, 256);
-    if (relu_out) bn_bwd_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n, c);
-    else bn_bwd_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, dx, n, c);
+    if (relu_out) bn_bwd_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n, c);
+    else bn_bwd_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n, c);
   }
   return check_launch("bn_bwd_apply");
 }

@@ -33,7 +33,7 @@ extern "C" {
 
 const char* ttb_last_error(void) { return ttb::g_err; }
 
-int ttb_version(void) { return 1; }
+int ttb_version(void) { return 2; }
 
 int ttb_device_sm_count(int* out) {
   if (!out) return 2;

@@ -281,8 +281,9 @@ def bn_forward_eval(x, gamma, beta, mean, var, eps, relu=False):
 
 
 def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dgamma=True, need_dbeta=True,
-                reduce_hook=None):
-    """-> (dx, dgamma, dbeta).  `count` is the (global) number of elements per channel used in forward."""
+                reduce_hook=None, accum=None):
+    """-> (dx, dgamma, dbeta).  `count` is the (global) number of elements per channel used in forward.
+    `accum`: an array of x's shape that is added to dx inside the apply pass (never written)."""
     m, c = _rows_channels(x)
     base = stats.t.data_ptr()
     row = c * 4
@@ -302,7 +303,7 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     dx = None
     if need_dx:
         dx = cparray(empty_device(x.shape))
-        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), _ptr(coef), _ptr(dx), m, c, st)
+        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), _ptr(coef), _ptr(accum), _ptr(dx), m, c, st)
     return dx, dgamma, dbeta
 
 

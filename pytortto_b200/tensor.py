@@ -237,15 +237,26 @@ class Tensor:
 
     def _sweep(self, ops):
         for node in toposort(self.grad_fn):
-            grads = node.apply(*node.grad)
             nf = node.next_functions
+            fused0 = False
+            fcls = node._forward_cls
+            if fcls is not None and getattr(fcls, '_accumulates_input0', False) and node.needs_input_grad[0] \
+                    and nf[0][0] is not None:
+                # a gradient for input 0 has already arrived through another branch: let this op add it inside its own
+                # dx pass (the `grad += new` of tensor.py:597-599 without a separate elementwise kernel)
+                fn0, ind0 = nf[0]
+                pending = fn0.grad[ind0]
+                if pending is not None and pending.__class__ is cparray:
+                    node.params['_accum0'] = pending
+                    fused0 = True
+            grads = node.apply(*node.grad)
             for i in range(len(nf)):
                 g = grads[i]
                 if g is not None:
                     fn, ind = nf[i]
                     slot = fn.grad
-                    if slot[ind] is None:
-                        slot[ind] = g
+                    if slot[ind] is None or (i == 0 and fused0):
+                        slot[ind] = g  # (fused0: g already contains the gradient that was pending in the slot)
                     else:
                         slot[ind] = ops.add_arrays(slot[ind], g)  # out of place: producers may share `g`
             node.clear()

@@ -284,3 +284,52 @@ def test_error_messages_match_reference():
         tt.nn.BatchNorm2d(3).cuda()(tt.tensor(np.zeros((1, 3, 1, 1), np.float32)).cuda())
     with pytest.raises(ValueError, match="expected 4D input"):
         tt.nn.BatchNorm2d(3).cuda()(tt.tensor(np.zeros((3, 3), np.float32)).cuda())
+
+
+def test_multi_tensor_backward_helpers_match_per_layer_calls():
+    """ttb_conv2d_dgrad_pack_weights + ttb_conv2d_dgrad_prepacked and ttb_conv2d_wgrad_partial + ttb_sum_splits_multi
+    (one launch for several layers) give bit-identical results to the per-layer ttb_conv2d_dgrad / ttb_conv2d_wgrad."""
+    tt = _tt("tf32")
+    import ctypes
+    import torch
+    from pytortto_b200 import _cabi, ops
+    from pytortto_b200.xparray import cparray, current_stream_ptr
+    rng = np.random.default_rng(77)
+    layers = []
+    for (n, c, h, k, ks, s) in [(8, 64, 16, 64, 3, 1), (8, 32, 16, 64, 3, 2), (4, 128, 8, 96, 1, 1)]:
+        x = cparray.from_numpy(rng.standard_normal((n, c, h, h)).astype(np.float32))
+        w = cparray.from_numpy((rng.standard_normal((k, c, ks, ks)) * 0.1).astype(np.float32))
+        d = ops.conv_desc(x.shape, w.shape, (s, s), (ks // 2, ks // 2), (1, 1), 1)
+        dy = cparray.from_numpy(rng.standard_normal((n, k, d.p, d.q)).astype(np.float32))
+        layers.append((x, w, d, dy))
+    lib = _cabi.load()
+    st = current_stream_ptr()
+    n = len(layers)
+    assert all(lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d)) for _, _, d, _ in layers)
+    packed = [torch.empty(w.t.numel(), dtype=torch.float32, device="cuda") for _, w, _, _ in layers]
+    descs = (ctypes.POINTER(_cabi.ConvDesc) * n)(*[ctypes.pointer(d) for _, _, d, _ in layers])
+    src = (ctypes.c_void_p * n)(*[w.t.data_ptr() for _, w, _, _ in layers])
+    dst = (ctypes.c_void_p * n)(*[p.data_ptr() for p in packed])
+    _cabi.call("ttb_conv2d_dgrad_pack_weights", n, descs, src, dst, st)
+    sums, keep = [], []
+    for (x, w, d, dy), pk in zip(layers, packed):
+        dx_ref = ops.conv2d_dgrad(dy, w, d).get()
+        dx = cparray(torch.empty_like(x.t))
+        _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), pk.data_ptr(), dx.t.data_ptr(), st)
+        np.testing.assert_array_equal(dx.get(), dx_ref)
+        dw_ref = ops.conv2d_wgrad(x, dy, d).get()
+        dw = cparray(torch.zeros_like(w.t))
+        nb = lib.ttb_conv2d_workspace_size(ctypes.byref(d), 2)
+        ws = torch.empty(max(nb, 1), dtype=torch.uint8, device="cuda")
+        splits, partials = ctypes.c_int(0), ctypes.c_void_p(0)
+        _cabi.call("ttb_conv2d_wgrad_partial", ctypes.byref(d), x.t.data_ptr(), dy.t.data_ptr(), dw.t.data_ptr(), ws.data_ptr(), nb,
+                   ctypes.byref(splits), ctypes.byref(partials), st)
+        keep.append((ws, dw, dw_ref))
+        if splits.value > 1:
+            sums.append((partials.value, splits.value, dw.size, dw.t.data_ptr()))
+    assert sums, "at least one layer is expected to split its pixel range"
+    m = len(sums)
+    _cabi.call("ttb_sum_splits_multi", m, (ctypes.c_void_p * m)(*[t[0] for t in sums]), (ctypes.c_int * m)(*[t[1] for t in sums]),
+               (ctypes.c_int64 * m)(*[t[2] for t in sums]), (ctypes.c_void_p * m)(*[t[3] for t in sums]), st)
+    for ws, dw, dw_ref in keep:
+        np.testing.assert_array_equal(dw.get(), dw_ref)

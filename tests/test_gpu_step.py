@@ -113,3 +113,28 @@ def test_preact_resnet18_full_size_properties():
     assert worst_l2 < 0.25 and worst < 0.5
     l2, g2 = results["tf32_again"]
     assert l2 == l_tf32 and all(np.array_equal(g2[k], g_tf32[k]) for k in g2), "step is not deterministic"
+
+
+def test_residual_gradient_is_folded_into_bn_backward():
+    """x feeds BatchNorm->ReLU->conv AND an identity shortcut: the shortcut gradient that is already pending for x is
+    added inside the BatchNorm dx pass (Tensor._sweep / ttb_bn_bwd_apply accum) - same numbers as the separate add."""
+    import pytortto_b200 as tt
+    from pytortto_b200 import ops
+    tt.set_math_mode("fp32")
+    rng = np.random.default_rng(5)
+    xn = rng.standard_normal((4, 32, 8, 8)).astype(np.float32)
+    results = []
+    for fold in (True, False):
+        tt.manual_seed(11)
+        bn = tt.nn.Sequential(tt.nn.BatchNorm2d(32), tt.nn.ReLU()).cuda()
+        conv = tt.nn.Conv2d(32, 32, 3, padding=1, bias=False).cuda()
+        tt.autograd.grad_nn._BatchNormBase._accumulates_input0 = fold
+        calls0 = ops._cabi.launch_count
+        leaf = tt.tensor(xn, requires_grad=True)
+        x = leaf.cuda() * 1.5          # non-leaf x with two consumers
+        out = conv(bn(x)) + x
+        (out * out).sum().backward()
+        results.append((np.asarray(leaf.grad), ops._cabi.launch_count - calls0))
+    tt.autograd.grad_nn._BatchNormBase._accumulates_input0 = True
+    np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-6, atol=1e-6)
+    assert results[0][1] < results[1][1], "folding must save the separate add launch"
