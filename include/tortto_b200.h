@@ -125,17 +125,20 @@ int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float 
 int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale, const float* shift, int relu,
                  void* stream);
 /* partials[chunk][2][C]: sum(dy), sum(dy*(x-mean)).  If relu_out != NULL dy is first masked by (relu_out > 0)
- * (fused ReLU backward, grad_nn.py:64-69). */
-int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, int64_t m, int c,
-                      double* partials, int num_chunks, void* stream);
+ * (fused ReLU backward, grad_nn.py:64-69).  The mask of a fused BatchNorm+ReLU node comes either from relu_out (the
+ * saved ReLU output) or - one read per element cheaper - is recomputed as fmaf(x, relu_scale, relu_shift) > 0 with the
+ * scale / shift rows forward normalised with (bit-identical to what forward tested); give one of the two or neither. */
+int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
+                      const float* relu_shift, int64_t m, int c, double* partials, int num_chunks, void* stream);
 /* from sums[num_chunks][2][C]: dgamma = sum(dy*(x-mean))/sd, dbeta = sum(dy), and the three per-channel
  * coefficients of dx = c1*(dy - c2 - (x-mean)*c3)  (grad_nn.py:984-988 re-associated) */
 int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef /*[3][C]*/, void* stream);
 /* dx = c1*(dy - c2 - (x-mean)*c3) [+ accum]; accum (may be null): a gradient that already reached the same tensor
  * through another branch, i.e. the engine's `grad += new` (tensor.py:597-599) folded into this pass */
-int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
-                     const float* accum, float* dx, int64_t m, int c, void* stream);
+int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
+                     const float* relu_shift, const float* coef, const float* accum, float* dx, int64_t m, int c,
+                     void* stream);
 
 /* ---- relu / elementwise ---------------------------------------------------------------------------------- */
 int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream);              /* y may alias x (in-place) */

@@ -50,9 +50,9 @@ _PROTOS = {
     "ttb_bn_finalize": (c_int, [_F, c_int, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, c_int, c_void_p]),
-    "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
+    "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_bwd_finalize": (c_int, [_F, c_int, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
-    "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, _F, c_int64, c_int, c_void_p]),
+    "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, c_int64, c_int, c_void_p]),
     "ttb_relu_fwd": (c_int, [_F, _F, c_int64, c_void_p]),
     "ttb_relu_bwd": (c_int, [_F, _F, _F, c_int64, c_void_p]),
     "ttb_add": (c_int, [_F, _F, _F, c_int64, c_void_p]),

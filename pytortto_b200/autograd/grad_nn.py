@@ -270,7 +270,8 @@ class _BatchNormBase(Function):
         accum = ctx.params.pop('_accum0', None)
         return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'], relu_out=relu_out,
                                need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
-                               need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook, accum=accum)
+                               need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook, accum=accum,
+                               fused_relu=cls._fuse_relu)
 
 
 # its backward can fold the pending gradient of input 0 into dx (TORTTO_B200_FOLD_ACCUM=0: separate add kernel)

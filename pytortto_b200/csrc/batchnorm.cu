@@ -59,24 +59,32 @@ static ColGeom col_geom(int64_t m, int c) {
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
 col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
-                  const float* __restrict__ mask, int64_t m, int c, int tx_n, int64_t rows_per_chunk,
-                  double* __restrict__ partials) {
+                  const float* __restrict__ mask, const float* __restrict__ rscale, const float* __restrict__ rshift,
+                  int64_t m, int c, int tx_n, int64_t rows_per_chunk, double* __restrict__ partials) {
+  // ReLU mask of the fused BatchNorm+ReLU node: either read (mask = the ReLU output) or RECOMPUTED from x with the
+  // forward pass's own scale / shift (rscale != null): fmaf(x, scale, shift) > 0 is bit-for-bit what forward tested,
+  // and it saves one of the three reads of this pass
   extern __shared__ float4 sm[];  // [2][ty][tx]
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = kBnThreads / tx_n;
   const int quad = blockIdx.x * tx_n + tx;
   const int ch = quad * 4;
   float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
   if (ch < c) {
-    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = mu, rsh = mu;
+    const bool recompute = MODE == 1 && rscale != nullptr;
     if (MODE == 1) {
-      if (VEC) mu = ld_f4(mean + ch);
-      else {
-        mu.x = mean[ch];
-        if (ch + 1 < c) mu.y = mean[ch + 1];
-        if (ch + 2 < c) mu.z = mean[ch + 2];
-        if (ch + 3 < c) mu.w = mean[ch + 3];
+      if (VEC) {
+        mu = ld_f4(mean + ch);
+        if (recompute) { rsc = ld_f4(rscale + ch); rsh = ld_f4(rshift + ch); }
+      } else {
+        float* pm = &mu.x; float* ps = &rsc.x; float* ph = &rsh.x;
+        for (int j = 0; j < 4 && ch + j < c; ++j) {
+          pm[j] = mean[ch + j];
+          if (recompute) { ps[j] = rscale[ch + j]; ph[j] = rshift[ch + j]; }
+        }
       }
     }
+    const bool masked = mask != nullptr || recompute;
     int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
     auto accumulate = [&](float4 va, float4 vb, float4 vm) {
@@ -85,7 +93,11 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
         s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
         s1.z = fmaf(va.z, va.z, s1.z); s1.w = fmaf(va.w, va.w, s1.w);
       } else {
-        if (mask) {
+        if (recompute) {
+          vm.x = fmaf(vb.x, rsc.x, rsh.x); vm.y = fmaf(vb.y, rsc.y, rsh.y);
+          vm.z = fmaf(vb.z, rsc.z, rsh.z); vm.w = fmaf(vb.w, rsc.w, rsh.w);
+        }
+        if (masked) {
           va.x = vm.x > 0.f ? va.x : 0.f; va.y = vm.y > 0.f ? va.y : 0.f;
           va.z = vm.z > 0.f ? va.z : 0.f; va.w = vm.w > 0.f ? va.w : 0.f;
         }
@@ -305,17 +317,25 @@ __global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __res
 
 // dx = c1*(g - c2 - (x-mean)*c3) [+ accum], g = dy (masked by relu_out > 0 when given).  `accum`: a gradient that already
 // reached the same tensor through another branch (the residual shortcut) - added here instead of by a separate kernel.
-template <bool MASK>
+// MASK: 0 none, 1 read the ReLU output, 2 recompute it from x (fmaf(x, rscale, rshift), see col_reduce_kernel)
+template <int MASK>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                    const float* __restrict__ mask, const float* __restrict__ coef, const float* __restrict__ accum,
-                    float* __restrict__ dx, int64_t n4, int cq, int c) {
+                    const float* __restrict__ mask, const float* __restrict__ rscale, const float* __restrict__ rshift,
+                    const float* __restrict__ coef, const float* __restrict__ accum, float* __restrict__ dx, int64_t n4,
+                    int cq, int c) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int q = (int)(i % cq);
     float4 g = ld_f4_stream(dy + 4 * i), v = ld_f4_stream(x + 4 * i);
     if (MASK) {
-      float4 o = ld_f4_stream(mask + 4 * i);
+      float4 o;
+      if (MASK == 1) {
+        o = ld_f4_stream(mask + 4 * i);
+      } else {
+        float4 sc = ld_f4(rscale + 4 * q), sh = ld_f4(rshift + 4 * q);
+        o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+      }
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
       g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
@@ -334,16 +354,18 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
   }
 }
 
-template <bool MASK>
+template <int MASK>
 __global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                            const float* __restrict__ mean, const float* __restrict__ mask,
+                                           const float* __restrict__ rscale, const float* __restrict__ rshift,
                                            const float* __restrict__ coef, const float* __restrict__ accum,
                                            float* __restrict__ dx, int64_t n, int c) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int ch = (int)(i % c);
     float g = dy[i];
-    if (MASK) g = mask[i] > 0.f ? g : 0.f;
+    if (MASK == 1) g = mask[i] > 0.f ? g : 0.f;
+    if (MASK == 2) g = fmaf(x[i], rscale[ch], rshift[ch]) > 0.f ? g : 0.f;
     float r = coef[ch] * (g - coef[c + ch] - (x[i] - mean[ch]) * coef[2 * c + ch]);
     dx[i] = accum ? r + accum[i] : r;
   }
@@ -352,18 +374,20 @@ __global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const f
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int MODE>
-static int launch_col_reduce(const float* a, const float* b, const float* mean, const float* mask, int64_t m, int c,
-                             double* partials, int num_chunks, cudaStream_t st, const char* what) {
+static int launch_col_reduce(const float* a, const float* b, const float* mean, const float* mask, const float* rscale,
+                             const float* rshift, int64_t m, int c, double* partials, int num_chunks, cudaStream_t st,
+                             const char* what) {
   if (m <= 0 || c <= 0) return 0;
   ColGeom g = col_geom(m, c);
   TTB_REQUIRE(num_chunks == g.chunks, "%s: num_chunks=%d but ttb_bn_num_chunks gives %d", what, num_chunks, g.chunks);
-  bool vec = (c % 4 == 0) && a16(a) && (MODE == 0 || (a16(b) && a16(mean) && (!mask || a16(mask))));
+  bool vec = (c % 4 == 0) && a16(a) &&
+             (MODE == 0 || (a16(b) && a16(mean) && (!mask || a16(mask)) && (!rscale || (a16(rscale) && a16(rshift)))));
   dim3 grid(g.qblocks, g.chunks);
   size_t smem = sizeof(float4) * 2 * kBnThreads;
   if (vec)
-    col_reduce_kernel<MODE, true><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, m, c, g.tx, g.rows_per_chunk, partials);
+    col_reduce_kernel<MODE, true><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
   else
-    col_reduce_kernel<MODE, false><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, m, c, g.tx, g.rows_per_chunk, partials);
+    col_reduce_kernel<MODE, false><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
   return check_launch(what);
 }
 
@@ -379,7 +403,8 @@ int ttb_bn_num_chunks(int64_t m, int c) {
 }
 
 int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chunks, void* stream) {
-  return launch_col_reduce<0>(x, nullptr, nullptr, nullptr, m, c, partials, num_chunks, as_stream(stream), "bn_stats");
+  return launch_col_reduce<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, m, c, partials, num_chunks, as_stream(stream),
+                              "bn_stats");
 }
 
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
@@ -430,9 +455,11 @@ int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale,
   return check_launch("bn_apply");
 }
 
-int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, int64_t m, int c,
-                      double* partials, int num_chunks, void* stream) {
-  return launch_col_reduce<1>(dy, x, mean, relu_out, m, c, partials, num_chunks, as_stream(stream), "bn_bwd_reduce");
+int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
+                      const float* relu_shift, int64_t m, int c, double* partials, int num_chunks, void* stream) {
+  TTB_REQUIRE(!(relu_out && relu_scale) && (!relu_scale == !relu_shift), "bn_bwd_reduce: give relu_out OR relu_scale+relu_shift");
+  return launch_col_reduce<1>(dy, x, mean, relu_out, relu_scale, relu_shift, m, c, partials, num_chunks, as_stream(stream),
+                              "bn_bwd_reduce");
 }
 
 int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
@@ -443,21 +470,26 @@ int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c
   return check_launch("bn_bwd_finalize");
 }
 
-int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* coef,
-                     const float* accum, float* dx, int64_t m, int c, void* stream) {
+int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
+                     const float* relu_shift, const float* coef, const float* accum, float* dx, int64_t m, int c,
+                     void* stream) {
   int64_t n = m * c;
   if (n <= 0) return 0;
+  TTB_REQUIRE(!(relu_out && relu_scale) && (!relu_scale == !relu_shift), "bn_bwd_apply: give relu_out OR relu_scale+relu_shift");
   cudaStream_t st = as_stream(stream);
   bool vec = c % 4 == 0 && a16(dy) && a16(x) && a16(dx) && a16(mean) && a16(coef) && (!relu_out || a16(relu_out)) &&
-             (!accum || a16(accum));
+             (!accum || a16(accum)) && (!relu_scale || (a16(relu_scale) && a16(relu_shift)));
+  const int mode = relu_out ? 1 : (relu_scale ? 2 : 0);
   if (vec) {
     int grid = elementwise_grid(n / 4, 256);
-    if (relu_out) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n / 4, c / 4, c);
-    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n / 4, c / 4, c);
+    if (mode == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
+    else if (mode == 2) bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
+    else bn_bwd_apply_kernel<0><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
   } else {
     int grid = elementwise_grid(n, 256);
-    if (relu_out) bn_bwd_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n, c);
-    else bn_bwd_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, coef, accum, dx, n, c);
+    if (mode == 1) bn_bwd_apply_scalar_kernel<1><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
+    else if (mode == 2) bn_bwd_apply_scalar_kernel<2><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
+    else bn_bwd_apply_scalar_kernel<0><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
   }
   return check_launch("bn_bwd_apply");
 }

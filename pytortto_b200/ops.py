@@ -280,17 +280,25 @@ def bn_forward_eval(x, gamma, beta, mean, var, eps, relu=False):
     return y, stats, m
 
 
+_RECOMPUTE_RELU_MASK = os.environ.get("TORTTO_B200_RECOMPUTE_RELU_MASK", "1") != "0"
+
+
 def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dgamma=True, need_dbeta=True,
-                reduce_hook=None, accum=None):
+                reduce_hook=None, accum=None, fused_relu=False):
     """-> (dx, dgamma, dbeta).  `count` is the (global) number of elements per channel used in forward.
-    `accum`: an array of x's shape that is added to dx inside the apply pass (never written)."""
+    `accum`: an array of x's shape that is added to dx inside the apply pass (never written).
+    `fused_relu`: the node is BatchNorm+ReLU; the mask (y > 0) is recomputed from x with the scale / shift rows of
+    `stats` (what forward normalised with, so bit-identical) instead of reading `relu_out` - one read less per pass."""
     m, c = _rows_channels(x)
     base = stats.t.data_ptr()
     row = c * 4
     st = current_stream_ptr()
     chunks = _cabi.load().ttb_bn_num_chunks(m, c)
     partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
-    _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), m, c, partials.data_ptr(), chunks, st)
+    rsc = rsh = None
+    if fused_relu and _RECOMPUTE_RELU_MASK:
+        relu_out, rsc, rsh = None, base + 3 * row, base + 4 * row
+    _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, m, c, partials.data_ptr(), chunks, st)
     if reduce_hook is None:
         sums, nchunks = partials, chunks
     else:
@@ -303,7 +311,7 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     dx = None
     if need_dx:
         dx = cparray(empty_device(x.shape))
-        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), _ptr(coef), _ptr(accum), _ptr(dx), m, c, st)
+        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, _ptr(coef), _ptr(accum), _ptr(dx), m, c, st)
     return dx, dgamma, dbeta
 
 
