@@ -172,6 +172,17 @@ size_t ttb_comm_slot_bytes(int max_values);
  * index `rank`).  One kernel, one NVLink round trip; every rank must call it for the same slot the same number of times. */
 int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,
                        size_t slot_offset, double* out, void* stream);
+/* The same exchange fused with the BatchNorm finalisation that follows it - one kernel per BatchNorm layer and
+ * direction instead of ttb_comm_allreduce + ttb_bn_finalize / ttb_bn_bwd_finalize.  partials = this rank's
+ * [num_chunks][2][C] doubles, count = GLOBAL elements per channel; the remaining arguments are those of the finalize
+ * entry points. */
+int ttb_comm_bn_finalize(const double* partials, int num_chunks, void* const* peers_dev, int world, int rank, size_t slot_offset,
+                         int64_t count, int c, float eps, float momentum, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* mean, float* var_eps, float* sd, float* scale,
+                         float* shift, void* stream);
+int ttb_comm_bn_bwd_finalize(const double* partials, int num_chunks, void* const* peers_dev, int world, int rank,
+                             size_t slot_offset, int64_t count, int c, const float* gamma, const float* var_eps,
+                             const float* sd, float* dgamma, float* dbeta, float* coef, void* stream);
 
 /* ---- max pool --------------------------------------------------------------------------------------------- */
 /* y[N,P,Q,C] = max over window (padding acts as -inf); idx[N,P,Q,C] (uint8) = r*kw+s of the FIRST maximum in

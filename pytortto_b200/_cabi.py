@@ -68,6 +68,10 @@ _PROTOS = {
     "ttb_comm_free": (c_int, [c_void_p]),
     "ttb_comm_slot_bytes": (c_size_t, [c_int]),
     "ttb_comm_allreduce": (c_int, [_F, c_int, c_int, c_void_p, c_int, c_int, c_size_t, _F, c_void_p]),
+    "ttb_comm_bn_finalize": (c_int, [_F, c_int, _F, c_int, c_int, c_size_t, c_int64, c_int, c_float, c_float, _F, _F, _F, _F,
+                                     _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_comm_bn_bwd_finalize": (c_int, [_F, c_int, _F, c_int, c_int, c_size_t, c_int64, c_int, _F, _F, _F, _F, _F, _F,
+                                         c_void_p]),
     "ttb_maxpool2d_fwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_void_p]),
     "ttb_maxpool2d_bwd": (c_int, [POINTER(PoolDesc), _F, _F, _F, c_int, c_void_p]),
 }

@@ -10,6 +10,7 @@
 // partial per (chunk, channel) written to HBM, and a tiny second kernel sums chunks in double in a FIXED
 // order (deterministic; no atomics).  The [2][C] double sums are what a data-parallel run all-reduces.
 #include "common.cuh"
+#include "bn_finalize.cuh"
 
 namespace ttb {
 
@@ -215,31 +216,13 @@ reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int 
 }
 
 __global__ void __launch_bounds__(1024)
-bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c, float eps, float momentum,
-                   float one_minus_momentum, float unbias, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, float* running_mean, float* running_var,
-                   float* mean, float* var_eps, float* sd, float* scale, float* shift) {
+bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnFwdFinalize fin) {
   __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double s0 = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
   double s1 = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
   if (threadIdx.y != 0 || i >= c) return;
-  double mu = s0 / count;
-  double var = s1 / count - mu * mu;  // biased variance, grad_nn.py:924
-  if (var < 0.0) var = 0.0;
-  float muf = (float)mu, varf = (float)var;
-  if (running_mean) running_mean[i] = __fadd_rn(__fmul_rn(one_minus_momentum, running_mean[i]), __fmul_rn(momentum, muf));
-  if (running_var)
-    running_var[i] = __fadd_rn(__fmul_rn(one_minus_momentum, running_var[i]), __fmul_rn(momentum, __fmul_rn(varf, unbias)));
-  float ve = __fadd_rn(varf, eps);
-  float s = sqrtf(ve);
-  mean[i] = muf;
-  var_eps[i] = ve;
-  sd[i] = s;
-  float g = gamma ? gamma[i] : 1.f;
-  float sc = g / s;
-  scale[i] = sc;
-  shift[i] = (beta ? beta[i] : 0.f) - muf * sc;
+  fin(i, s0, s1);
 }
 
 __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const float* __restrict__ var_in, int c,
@@ -257,20 +240,13 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const 
 }
 
 __global__ void __launch_bounds__(1024)
-bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, double count, int c,
-                       const float* __restrict__ gamma, const float* __restrict__ var_eps,
-                       const float* __restrict__ sd, float* dgamma, float* dbeta, float* coef) {
+bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnBwdFinalize fin) {
   __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double sdy = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
   double sdyx = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
   if (threadIdx.y != 0 || i >= c) return;
-  if (dbeta) dbeta[i] = (float)sdy;
-  if (dgamma) dgamma[i] = (float)(sdyx / (double)sd[i]);
-  float g = gamma ? gamma[i] : 1.f;
-  coef[i] = g / sd[i];                                      // c1
-  coef[c + i] = (float)(sdy / count);                       // c2
-  coef[2 * c + i] = (float)(sdyx / (count * (double)var_eps[i]));  // c3
+  fin(i, sdy, sdyx);
 }
 
 // y = x*scale + shift (+ReLU).  One float4 = 4 channels; channel quad = i % cq.  Two independent float4 streams per
@@ -418,14 +394,14 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
                     float* sd, float* scale, float* shift, void* stream) {
   if (c <= 0) return 0;
   TTB_REQUIRE(count > 0, "bn_finalize: count must be positive");
-  // N/(N-1) and (1-momentum) are evaluated in double on the host like the reference's Python floats
-  // (grad_nn.py:927-930), then applied to float32 arrays.
-  float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
-  float omm = (float)(1.0 - (double)momentum);
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count, c,
-                                                                           eps, momentum, omm, unbias, gamma, beta,
-                                                                           running_mean, running_var, mean, var_eps, sd,
-                                                                           scale, shift);
+  BnFwdFinalize fin;
+  fin.count = (double)count;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  bn_fwd_host_factors(count, momentum, &fin.unbias, &fin.one_minus_momentum);
+  fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
+  fin.mean = mean; fin.var_eps = var_eps; fin.sd = sd; fin.scale = scale; fin.shift = shift;
+  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_finalize");
 }
 
@@ -465,8 +441,11 @@ int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const 
 int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c, const float* gamma, const float* var_eps,
                         const float* sd, float* dgamma, float* dbeta, float* coef, void* stream) {
   if (c <= 0) return 0;
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, (double)count,
-                                                                               c, gamma, var_eps, sd, dgamma, dbeta, coef);
+  BnBwdFinalize fin;
+  fin.count = (double)count;
+  fin.c = c;
+  fin.gamma = gamma; fin.var_eps = var_eps; fin.sd = sd; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.coef = coef;
+  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_bwd_finalize");
 }
 

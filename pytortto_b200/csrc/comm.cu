@@ -13,6 +13,7 @@
 // call sites in between, each of which needed this rank's later exchanges, which are stream-ordered after this one.
 #include <string.h>
 
+#include "bn_finalize.cuh"
 #include "common.cuh"
 
 namespace ttb {
@@ -122,6 +123,104 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
   }
 }
 
+// The same exchange fused with the BatchNorm finalisation that follows it (compute + collective + compute in ONE
+// kernel): block = 32 channels x 32 lanes; channel i owns values i (first sum) and c + i (second sum) of the [2][c]
+// statistics vector.  Chunk partials are summed, both values are published in this rank's slot and polled from every
+// peer (thread (x, y) polls peer y), summed in rank order, and `fin(i, total0, total1)` writes the per-channel
+// coefficients - what would otherwise be bn_finalize_kernel / bn_bwd_finalize_kernel as a second launch.
+template <class Finalize>
+__global__ void __launch_bounds__(1024)
+comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, char* const* __restrict__ peers, int world,
+                        int rank, size_t slot_offset, unsigned long long spin_limit, Finalize fin) {
+  __shared__ double sm0[32][33], sm1[32][33];
+  __shared__ double mine_sm[2][32];
+  char* own = peers[rank] + slot_offset;
+  SlotHeader* hdr = reinterpret_cast<SlotHeader*>(own);
+  const unsigned int seq = ld_volatile_u32(&hdr->seq) + 1u;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int n = 2 * c;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;  // two loads per value in flight per thread
+  if (i < c) {
+    int k = threadIdx.y;
+    for (; k + 32 < num_chunks; k += 64) {
+      a0 += partials[(int64_t)k * n + i];
+      b0 += partials[(int64_t)k * n + c + i];
+      a1 += partials[(int64_t)(k + 32) * n + i];
+      b1 += partials[(int64_t)(k + 32) * n + c + i];
+    }
+    for (; k < num_chunks; k += 32) {
+      a0 += partials[(int64_t)k * n + i];
+      b0 += partials[(int64_t)k * n + c + i];
+    }
+  }
+  sm0[threadIdx.y][threadIdx.x] = a0 + a1;
+  sm1[threadIdx.y][threadIdx.x] = b0 + b1;
+  __syncthreads();
+  if (threadIdx.y < 2 && i < c) {  // y = 0 publishes value i, y = 1 value c + i
+    double (*sm)[33] = threadIdx.y == 0 ? sm0 : sm1;
+    double mine = 0.0;
+    for (int j = 0; j < 32; ++j) mine += sm[j][threadIdx.x];
+    mine_sm[threadIdx.y][threadIdx.x] = mine;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    const size_t v = threadIdx.y == 0 ? (size_t)i : (size_t)c + i;
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + kSlotHeaderBytes) + 2 * v;
+    st_volatile_u64(w, tag | (bits & 0xffffffffull));
+    st_volatile_u64(w + 1, tag | (bits >> 32));
+  }
+  __syncthreads();  // sm0 / sm1 are reused: row r = the two values of rank r
+  bool failed = false;
+  const int r = threadIdx.y;
+  if (r < world && i < c) {
+    double v0, v1;
+    if (r == rank) {
+      v0 = mine_sm[0][threadIdx.x];
+      v1 = mine_sm[1][threadIdx.x];
+    } else {
+      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes);
+      const unsigned long long* p0 = base + 2 * (size_t)i;
+      const unsigned long long* p1 = base + 2 * ((size_t)c + i);
+      unsigned long long w0, w1, w2, w3, spins = 0;
+      for (;;) {
+        w0 = ld_volatile_u64(p0);
+        w1 = ld_volatile_u64(p0 + 1);
+        w2 = ld_volatile_u64(p1);
+        w3 = ld_volatile_u64(p1 + 1);
+        if ((unsigned int)(w0 >> 32) == seq && (unsigned int)(w1 >> 32) == seq && (unsigned int)(w2 >> 32) == seq &&
+            (unsigned int)(w3 >> 32) == seq)
+          break;
+        if (++spins > spin_limit) {  // a peer never arrived (ranks diverged): fail loudly, do not hang
+          failed = true;
+          break;
+        }
+      }
+      v0 = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+      v1 = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
+    }
+    sm0[r][threadIdx.x] = v0;
+    sm1[r][threadIdx.x] = v1;
+  }
+  if (failed) __trap();
+  __syncthreads();
+  if (threadIdx.y == 0 && i < c) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int q = 0; q < world; ++q) {  // rank order => the same bits on every rank
+      t0 += sm0[q][threadIdx.x];
+      t1 += sm1[q][threadIdx.x];
+    }
+    fin(i, t0, t1);
+  }
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&hdr->arrive, 1u);
+    if (ticket == gridDim.x - 1) {
+      hdr->arrive = 0;
+      __threadfence();
+      hdr->seq = seq;
+    }
+  }
+}
+
 }  // namespace ttb
 
 using namespace ttb;
@@ -189,6 +288,45 @@ int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* cons
   comm_allreduce_kernel<<<(n + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
       partials, num_chunks, n, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, out, 200000000ull);
   return check_launch("comm_allreduce");
+}
+
+static int comm_check(const void* partials, const void* peers_dev, int c, int num_chunks, int world, int rank, const char* what) {
+  TTB_REQUIRE(partials && peers_dev && c > 0 && num_chunks > 0, "%s: bad arguments", what);
+  TTB_REQUIRE(world > 0 && world <= kMaxWorld && rank >= 0 && rank < world, "%s: world size %d not in 1..%d", what, world, kMaxWorld);
+  return 0;
+}
+
+/* ttb_comm_allreduce of the [2][C] forward statistics + ttb_bn_finalize in one kernel; `count` = GLOBAL element count */
+int ttb_comm_bn_finalize(const double* partials, int num_chunks, void* const* peers_dev, int world, int rank, size_t slot_offset,
+                         int64_t count, int c, float eps, float momentum, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* mean, float* var_eps, float* sd, float* scale,
+                         float* shift, void* stream) {
+  if (comm_check(partials, peers_dev, c, num_chunks, world, rank, "comm_bn_finalize")) return 1;
+  TTB_REQUIRE(count > 0, "comm_bn_finalize: count must be positive");
+  BnFwdFinalize fin;
+  fin.count = (double)count;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  bn_fwd_host_factors(count, momentum, &fin.unbias, &fin.one_minus_momentum);
+  fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
+  fin.mean = mean; fin.var_eps = var_eps; fin.sd = sd; fin.scale = scale; fin.shift = shift;
+  comm_bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+      partials, num_chunks, c, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, 200000000ull, fin);
+  return check_launch("comm_bn_finalize");
+}
+
+/* ttb_comm_allreduce of the [2][C] backward sums + ttb_bn_bwd_finalize in one kernel; `count` = GLOBAL element count */
+int ttb_comm_bn_bwd_finalize(const double* partials, int num_chunks, void* const* peers_dev, int world, int rank,
+                             size_t slot_offset, int64_t count, int c, const float* gamma, const float* var_eps,
+                             const float* sd, float* dgamma, float* dbeta, float* coef, void* stream) {
+  if (comm_check(partials, peers_dev, c, num_chunks, world, rank, "comm_bn_bwd_finalize")) return 1;
+  BnBwdFinalize fin;
+  fin.count = (double)count;
+  fin.c = c;
+  fin.gamma = gamma; fin.var_eps = var_eps; fin.sd = sd; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.coef = coef;
+  comm_bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+      partials, num_chunks, c, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, 200000000ull, fin);
+  return check_launch("comm_bn_bwd_finalize");
 }
 
 }  // extern "C"

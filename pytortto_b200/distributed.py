@@ -131,6 +131,15 @@ class PeerComm:
             self.slots[key] = idx
         return idx * self.slot_bytes
 
+    def fits(self, n):
+        return n <= self.MAX_VALUES
+
+    def call(self, entry, key, partials, chunks, *rest):
+        """Fused exchange + BatchNorm finalize (ttb_comm_bn_finalize / ttb_comm_bn_bwd_finalize): `rest` = the
+        arguments of the entry point after slot_offset."""
+        self._cabi.call(entry, partials.data_ptr(), chunks, self.peers_dev.data_ptr(), self.world, self.rank,
+                        self.slot_offset(key), *rest)
+
     def all_reduce_partials(self, partials, chunks, n, key):
         """partials [chunks][n] doubles (this rank) -> [n] doubles summed over chunks and ranks (rank order)."""
         if n > self.MAX_VALUES:
@@ -157,6 +166,10 @@ def _make_stat_hook(key):
             sums = partials.reshape(chunks, n).sum(dim=0) if not partials.is_cuda else _collapse(partials, chunks, n)
             all_reduce_sum_(sums)
         return sums, local_count * _state["world"]  # equal shards by construction (shard_batch)
+    # when the peer-memory path is up, ops.bn_* call the fused "exchange + finalize" kernels through these attributes
+    comm = _state.get("peer_comm")
+    hook.key = key
+    hook.fused = comm if (comm is not None and key is not None and os.environ.get("TORTTO_B200_FUSED_SYNCBN", "1") != "0") else None
     return hook
 
 

@@ -254,14 +254,24 @@ def bn_sums(x, reduce_hook=None):
 
 def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, relu=False, reduce_hook=None):
     m, c = _rows_channels(x)
-    sums, nchunks, count = bn_sums(x, reduce_hook)
     stats = new_f32((5, c))  # rows: mean, var+eps, sd, scale, shift
     base = stats.t.data_ptr()
     row = c * 4
     st = current_stream_ptr()
-    _cabi.call("ttb_bn_finalize", sums.data_ptr(), nchunks, count, c, eps, 0.0 if momentum is None else momentum, _ptr(gamma),
-               _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row, base + 3 * row,
-               base + 4 * row, st)
+    fused = getattr(reduce_hook, "fused", None)  # SyncBN over NVLink peer memory: exchange + finalize are one kernel
+    if fused is not None and x.t.is_cuda and fused.fits(2 * c):
+        chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+        partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
+        _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
+        count = m * fused.world  # equal shards by construction (distributed.shard_batch)
+        fused.call("ttb_comm_bn_finalize", reduce_hook.key, partials, chunks, count, c, eps,
+                   0.0 if momentum is None else momentum, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                   base, base + row, base + 2 * row, base + 3 * row, base + 4 * row, st)
+    else:
+        sums, nchunks, count = bn_sums(x, reduce_hook)
+        _cabi.call("ttb_bn_finalize", sums.data_ptr(), nchunks, count, c, eps, 0.0 if momentum is None else momentum,
+                   _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row,
+                   base + 3 * row, base + 4 * row, st)
     y = cparray(empty_device(x.shape))
     _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base + 3 * row, base + 4 * row, int(relu), st)
     return y, stats, count
@@ -299,15 +309,20 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     if fused_relu and _RECOMPUTE_RELU_MASK:
         relu_out, rsc, rsh = None, base + 3 * row, base + 4 * row
     _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, m, c, partials.data_ptr(), chunks, st)
-    if reduce_hook is None:
-        sums, nchunks = partials, chunks
-    else:
-        (sums, _), nchunks = reduce_hook(partials, chunks, 2 * c, m), 1
     dgamma = new_f32((c,)) if need_dgamma else None
     dbeta = new_f32((c,)) if need_dbeta else None
     coef = new_f32((3, c))
-    _cabi.call("ttb_bn_bwd_finalize", sums.data_ptr(), nchunks, count, c, _ptr(gamma), base + row, base + 2 * row,
-               _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+    fused = getattr(reduce_hook, "fused", None)
+    if fused is not None and x.t.is_cuda and fused.fits(2 * c):
+        fused.call("ttb_comm_bn_bwd_finalize", reduce_hook.key, partials, chunks, count, c, _ptr(gamma), base + row,
+                   base + 2 * row, _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+    else:
+        if reduce_hook is None:
+            sums, nchunks = partials, chunks
+        else:
+            (sums, _), nchunks = reduce_hook(partials, chunks, 2 * c, m), 1
+        _cabi.call("ttb_bn_bwd_finalize", sums.data_ptr(), nchunks, count, c, _ptr(gamma), base + row, base + 2 * row,
+                   _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
     dx = None
     if need_dx:
         dx = cparray(empty_device(x.shape))
