@@ -272,23 +272,23 @@ def run_ours(args):
 
     # end to end: host batch -> pinned H2D + layout kernel -> step -> loss.item() (D2H) every step
     # (the loss of step i is read after step i+1 has been queued - every step's loss is still read inside the timed
-    # region, the last one by `drain` - so the GPU is not drained once per step)
+    # region, the last one by `drain` - and tt.prefetch.DevicePrefetcher issues the H2D copy + layout kernel of the next
+    # batch on a second stream; every batch's copy is issued inside the timed region)
     pending = []
 
-    def e2e_step():
-        xb = tt.tensor(x_host.numpy(), copy=False).cuda()
-        yb = tt.tensor(y_host.numpy(), dtype=np.int64, copy=False).cuda()
-        pending.append(run_from(xb, yb).item_async())
-        if len(pending) > 1:
-            pending.pop(0).get()
+    def host_batches(n):
+        for _ in range(n):
+            yield (tt.tensor(x_host.numpy(), copy=False), tt.tensor(y_host.numpy(), dtype=np.int64, copy=False))
 
-    def drain():
+    def e2e_run(n):
+        for xb, yb in tt.prefetch.DevicePrefetcher(host_batches(n)):
+            pending.append(run_from(xb, yb).item_async())
+            if len(pending) > 1:
+                pending.pop(0).get()
         while pending:
             pending.pop(0).get()
-    for _ in range(2):
-        e2e_step()
-    drain()
-    ms_e2e = timed(e2e_step, args.steps, after=drain)
+    e2e_run(8)  # also lets the caching allocator reach its steady set of staging blocks on the copy stream
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
     clocks = sampler.stop() if rank == 0 else None
 
     # per-kernel-family device time (CUDA events around every C-ABI call) on a few extra steps

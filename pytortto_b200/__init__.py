@@ -24,3 +24,4 @@ from .serialization import save, load
 def cuda_is_available():
     import torch
     return torch.cuda.is_available()
+from . import prefetch

@@ -59,3 +59,21 @@ def test_item_async_matches_item():
     handles = [(v + v).item_async() for v in vals]  # all queued before the first one is read
     assert [h.get() for h in handles] == [3.0, -4.5, 6.0]
     assert tt.tensor(np.array([7.0], dtype=np.float32)).item_async().get() == 7.0  # host tensor: immediate
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    """tt.prefetch.DevicePrefetcher: copies issued on a second stream arrive intact and in order."""
+    import torch
+    import pytortto_b200 as tt
+    rng = np.random.default_rng(3)
+    xs = [torch.from_numpy(rng.standard_normal((4, 3, 8, 8)).astype(np.float32)).pin_memory() for _ in range(5)]
+    ys = [torch.from_numpy(rng.integers(0, 10, 4).astype(np.int64)).pin_memory() for _ in range(5)]
+    host = [(tt.tensor(x.numpy(), copy=False), tt.tensor(y.numpy(), dtype=np.int64, copy=False)) for x, y in zip(xs, ys)]
+    seen = 0
+    for i, (xb, yb) in enumerate(tt.prefetch.DevicePrefetcher(host, depth=2)):
+        assert xb.is_cuda and yb.is_cuda
+        z = xb + xb  # consume on the current stream
+        np.testing.assert_array_equal(z.data.get(), 2 * xs[i].numpy())
+        np.testing.assert_array_equal(yb.data.get(), ys[i].numpy())
+        seen += 1
+    assert seen == 5
