@@ -12,9 +12,12 @@
 // filter-tap offset and zero-fills the padding halo.  Weight / dY tiles use tiled-mode TMA.  Every tile lands in
 // shared memory in the 128-byte-swizzled layout tcgen05.mma consumes directly.
 //
-// Kernel structure (both kernels): 192 threads = warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner),
-// warps 2-5 epilogue (TMEM -> registers -> padded smem transpose -> coalesced 128 B row-segment stores).
-// A ring of NSTAGES {A,B} stages is handed over with full/empty mbarriers; tcgen05.commit releases stages.
+// Kernel structure: warp-specialised - TMA producer warp(s), one MMA-issuing warp (+TMEM owner), four epilogue
+// warps (TMEM -> registers -> padded smem transpose -> coalesced 128 B row-segment stores).  A ring of NSTAGES {A,B}
+// stages is handed over with full/empty mbarriers; tcgen05.commit releases stages.  fprop / dgrad: persistent CTAs
+// over a static tile list, several producer warps, two TMEM accumulators (igemm_fwd_persist_kernel); wgrad: one tile
+// and one pixel range per CTA (igemm_wgrad_kernel).  Producer and MMA loops run warp-uniform with the asynchronous
+// instruction under elect.sync - from an `if (lane == 0)` branch ptxas wraps each one in a divergence waterfall.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -222,143 +225,12 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_base, float* stage_
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// fprop / dgrad kernel
-// ------------------------------------------------------------------------------------------------------------
-template <int BN, int NSTAGES, bool BF16>
-__device__ __forceinline__ void igemm_fwd_body(const FwdParams& P) {
-  constexpr int kElems = BF16 ? 64 : 32;  // channels per K-block (one 128-byte swizzle row)
-  constexpr uint32_t kABytes = kTileM * 128;
-  constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static_assert(NSTAGES * kStageBytes >= 4 * 32 * kStagePitch * 4, "epilogue staging must fit in the pipeline smem");
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[NSTAGES], empty_bar[NSTAGES], accum_bar;
-  __shared__ uint32_t tmem_base_smem;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTileM;
-  const int n0 = blockIdx.y * BN;
-  const int num_kb = P.num_taps * P.c_blocks;
-  long long* const tr = (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? P.trace : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&P.tmA);
-    ptx::prefetch_tmap(&P.tmB);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < NSTAGES; ++s) {
-        ptx::mbar_init(&full_bar[s], 1);
-        ptx::mbar_init(&empty_bar[s], 1);
-      }
-      ptx::mbar_init(&accum_bar, 1);
-      ptx::fence_barrier_init();
-    }
-    __syncwarp();
-    ptx::tmem_alloc<kTmemCols>(&tmem_base_smem);
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-  if (tr && threadIdx.x == 0) tr[1] = clock64();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      // first base pixel of this tile in tensor-map coordinates
-      int j = m0 % P.o.q_dim;
-      int t = m0 / P.o.q_dim;
-      int i = t % P.o.p_dim;
-      int n = t / P.o.p_dim;
-      const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tap = 0; tap < P.num_taps; ++tap) {
-        const uint16_t ow = P.off_w[tap], oh = P.off_h[tap];
-        const int kb0 = P.b_koff[tap];
-        for (int cb = 0; cb < P.c_blocks; ++cb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (tr && tap * P.c_blocks + cb < 500) tr[16 + tap * P.c_blocks + cb] = clock64();
-          uint8_t* sa = smem + stage * kStageBytes;
-          ptx::mbar_expect_tx(&full_bar[stage], ((P.dbg & 2) ? 0 : kABytes) + ((P.dbg & 4) ? 0 : kBBytes));
-          if (!(P.dbg & 2)) ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, ow, oh);
-          if (!(P.dbg & 4)) ptx::tma_load_2d(sa + kABytes, &P.tmB, &full_bar[stage], kb0 + cb * kElems, n0);
-          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(BF16 ? 1 /*bf16*/ : 2 /*tf32*/, 0, 0, kTileM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        if (tr && kb < 500) tr[16 + 512 + kb] = clock64();
-        const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + kABytes;
-        if (P.dbg & 1) {
-          ptx::mbar_arrive(&empty_bar[stage]);
-          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-          continue;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
-          uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
-          uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
-          if (BF16) ptx::mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
-          else ptx::mma_tf32(tmem_base, da, db, idesc, (kb | k) != 0);
-        }
-        ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
-        if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-      }
-      ptx::mma_commit(&accum_bar);  // accumulator complete
-    }
-  } else {
-    // ===================== epilogue =====================
-    if (lane == 0) ptx::mbar_wait(&accum_bar, 0);  // one poller per warp: 128 spinning threads slow every other mbarrier op of the SM
-    __syncwarp();
-    ptx::tc_fence_after();
-    if (tr && warp == 2 && lane == 0) tr[2] = clock64();
-    // all MMAs (hence all TMA reads of the ring) are done: the ring is reused as staging space
-    epilogue_store<BN>(tmem_base, reinterpret_cast<float*>(smem), P.o, m0, n0, P.bias, warp - 2, warp & 3);
-    if (tr && warp == 2 && lane == 0) tr[3] = clock64();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<kTmemCols>(tmem_base);
-  if (tr && threadIdx.x == 32) tr[4] = clock64();
-}
-
-template <int BN, int NSTAGES, bool BF16>
-__global__ void __launch_bounds__(kThreadsIgemm)
-igemm_fwd_kernel(const __grid_constant__ FwdParams P) {
-  igemm_fwd_body<BN, NSTAGES, BF16>(P);
-}
-
-// Up to kMaxMulti independent problems of the same shape class in one launch (blockIdx.z selects): the stride-parity
-// classes of a strided dgrad run concurrently instead of as 4 small back-to-back grids.
+// Up to kMaxMulti independent problems of the same shape class in one launch: the stride-parity classes of a strided
+// dgrad run as one persistent grid instead of 4 small back-to-back grids.
 constexpr int kMaxMulti = 4;
 struct FwdParamsMulti {
   FwdParams p[kMaxMulti];
 };
-
-template <int BN, int NSTAGES, bool BF16>
-__global__ void __launch_bounds__(kThreadsIgemm)
-igemm_fwd_multi_kernel(const __grid_constant__ FwdParamsMulti PM) {
-  const FwdParams& P = PM.p[blockIdx.z];
-  if ((int)blockIdx.x * kTileM >= P.o.m_total) return;  // classes can differ by one tile; whole CTA leaves
-  igemm_fwd_body<BN, NSTAGES, BF16>(P);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Persistent fprop / dgrad kernel: one CTA per SM walks a static list of output tiles (tile = blockIdx.x + i*gridDim.x)
@@ -823,23 +695,6 @@ bool igemm_supported(const ttb_conv_desc* d, int pass) {
   return true;
 }
 
-template <int BN, int NSTAGES, bool BF16>
-static int launch_fwd(const FwdParams& P, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_kernel<BN, NSTAGES, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
-  dim3 grid((unsigned)ceil_div(P.o.m_total, kTileM), (unsigned)ceil_div(P.o.n_total, BN));
-  igemm_fwd_kernel<BN, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(P);
-  return check_launch("igemm_fwd_kernel");
-}
-
 // Widest N tile that still gives every SM a CTA; narrow channel counts get a matching narrow tile.
 static int pick_bn(int64_t m_total, int n_total) {
   if (const char* e = getenv("TTB_FORCE_BN")) {  // experiment switch
@@ -857,52 +712,6 @@ static int pick_bn(int64_t m_total, int n_total) {
   if (n_total > 64 && (mtiles * ceil_div(n_total, 128) >= sms || n_total > 128)) return 128;
   if (n_total > 32) return 64;
   return 32;
-}
-
-static int launch_fwd_bn(const FwdParams& P, int bn, bool bf16, cudaStream_t st) {
-  if (bf16) {
-    switch (bn) {
-      case 256: return launch_fwd<256, 4, true>(P, st);
-      case 128: return launch_fwd<128, 3, true>(P, st);
-      case 64: return launch_fwd<64, 4, true>(P, st);
-      default: return launch_fwd<32, 4, true>(P, st);
-    }
-  }
-  static int deep = -1;
-  if (deep < 0) {
-    const char* e = getenv("TTB_FWD_DEEP");
-    deep = e ? atoi(e) : 0;
-  }
-  if (deep) {
-    if (bn == 128) return launch_fwd<128, 6, false>(P, st);
-    if (bn == 64) return launch_fwd<64, 8, false>(P, st);
-  }
-  switch (bn) {
-    case 256: return launch_fwd<256, 4, false>(P, st);
-    case 128: return launch_fwd<128, 3, false>(P, st);
-    case 64: return launch_fwd<64, 4, false>(P, st);
-    default: return launch_fwd<32, 4, false>(P, st);
-  }
-}
-
-template <int BN, int NSTAGES, bool BF16>
-static int launch_fwd_multi(const FwdParamsMulti& PM, int count, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NSTAGES * (kTileM * 128 + BN * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_multi_kernel<BN, NSTAGES, BF16>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
-      return 1;
-    }
-    attr_set = true;
-  }
-  int m_max = 0;
-  for (int i = 0; i < count; ++i) m_max = PM.p[i].o.m_total > m_max ? PM.p[i].o.m_total : m_max;
-  dim3 grid((unsigned)ceil_div(m_max, kTileM), (unsigned)ceil_div(PM.p[0].o.n_total, BN), (unsigned)count);
-  igemm_fwd_multi_kernel<BN, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(PM);
-  return check_launch("igemm_fwd_multi_kernel");
 }
 
 template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
@@ -955,32 +764,6 @@ static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool b
     case 128: return kps2 ? launch_persist<128, 3, 3, 2, false>(PM, count, st) : launch_persist<128, 6, 3, 1, false>(PM, count, st);
     case 64: return kps2 ? launch_persist<64, 4, 2, 2, false>(PM, count, st) : launch_persist<64, 3, 3, 1, false>(PM, count, st);
     default: return launch_persist<32, 3, 3, 1, false>(PM, count, st);
-  }
-}
-
-static int use_persist() {  // TTB_FWD_PERSIST=0 selects the one-tile-per-CTA kernels (A/B comparisons)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TTB_FWD_PERSIST");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
-
-static int launch_fwd_multi_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
-  if (bf16) {
-    switch (bn) {
-      case 256: return launch_fwd_multi<256, 4, true>(PM, count, st);
-      case 128: return launch_fwd_multi<128, 3, true>(PM, count, st);
-      case 64: return launch_fwd_multi<64, 4, true>(PM, count, st);
-      default: return launch_fwd_multi<32, 4, true>(PM, count, st);
-    }
-  }
-  switch (bn) {
-    case 256: return launch_fwd_multi<256, 4, false>(PM, count, st);
-    case 128: return launch_fwd_multi<128, 3, false>(PM, count, st);
-    case 64: return launch_fwd_multi<64, 4, false>(PM, count, st);
-    default: return launch_fwd_multi<32, 4, false>(PM, count, st);
   }
 }
 
@@ -1082,12 +865,9 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
   // weight matrix [K rows][R*S*C cols]; the TMA box height is the kernel's N tile
   const int bn = pick_bn(P.o.m_total, P.o.n_total);
   if (make_tiled_2d(&P.tmB, w, el, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
-  if (use_persist()) {
-    static thread_local FwdParamsMulti PM1;
-    PM1.p[0] = P;
-    return launch_persist_bn(PM1, 1, bn, el.bf16, st);
-  }
-  return launch_fwd_bn(P, bn, el.bf16, st);
+  static thread_local FwdParamsMulti PM1;
+  PM1.p[0] = P;
+  return launch_persist_bn(PM1, 1, bn, el.bf16, st);
 }
 
 // `prepacked` != null: the weights are already in the [C][R][S][K] order (igemm_pack_dgrad_weights), w / ws unused
@@ -1181,18 +961,15 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         }
         const int bn = pick_bn(P.o.m_total, P.o.n_total);
         if (make_tiled_2d(&P.tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-        if (use_persist()) {
-          static thread_local FwdParamsMulti PM1;
-          PM1.p[0] = P;
-          if (launch_persist_bn(PM1, 1, bn, el.bf16, st)) return 1;
-        } else if (launch_fwd_bn(P, bn, el.bf16, st)) return 1;
+        static thread_local FwdParamsMulti PM1;
+        PM1.p[0] = P;
+        if (launch_persist_bn(PM1, 1, bn, el.bf16, st)) return 1;
       }
     if (pass == 1 && n_multi > 0) {
       const int bn = pick_bn(m_all, d->c);
       for (int i = 0; i < n_multi; ++i)
         if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-      if (use_persist() ? launch_persist_bn(PM, n_multi, bn, el.bf16, st) : launch_fwd_multi_bn(PM, n_multi, bn, el.bf16, st))
-        return 1;
+      if (launch_persist_bn(PM, n_multi, bn, el.bf16, st)) return 1;
     }
     if (pass == 0 && need_zero) {
       cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st);
