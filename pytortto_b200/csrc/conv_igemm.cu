@@ -597,8 +597,8 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
 }
 
 // Multi-tensor forms: one launch repacks the dgrad weights / sums the wgrad splits of up to kMaxBatch layers (a training
-// step has ~20 of each, every one a few-microsecond latency-bound launch on its own).  Work is cut into 1024-element
-// chunks; start[i] = first chunk of tensor i.
+// step has ~20 of each, every one a few-microsecond latency-bound launch on its own).  Work is cut into units (tiles
+// for the re-ordering, 1024-element chunks for the sums); start[i] = first unit of tensor i.
 constexpr int kMaxBatch = 32;
 constexpr int kBatchChunk = 1024;
 struct RepackBatch {
@@ -617,23 +617,36 @@ struct SumBatch {
   int count;
 };
 
+// work unit = one 32 x 32 (k, c) tile of one filter tap, transposed through shared memory so that both the read
+// (c contiguous in [K][T][C]) and the write (k contiguous in [C][T][K]) are coalesced; start[i] = first tile of tensor i
 __global__ void __launch_bounds__(256) repack_multi_kernel(const __grid_constant__ RepackBatch B) {
-  const int chunks = B.start[B.count];
-  for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+  __shared__ float tile[32][33];
+  const int tiles = B.start[B.count];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int u = blockIdx.x; u < tiles; u += gridDim.x) {
     int i = 0;
-    while (i + 1 < B.count && ch >= B.start[i + 1]) ++i;
+    while (i + 1 < B.count && u >= B.start[i + 1]) ++i;
     const int K = B.K[i], T = B.T[i], C = B.C[i];
-    const int64_t total = (int64_t)K * T * C;
-    const int64_t e0 = (int64_t)(ch - B.start[i]) * kBatchChunk;
+    const int kt = (K + 31) / 32, ct = (C + 31) / 32;
+    int v = u - B.start[i];
+    const int c0 = (v % ct) * 32;
+    v /= ct;
+    const int k0 = (v % kt) * 32;
+    const int t = v / kt;
     const float* __restrict__ w = B.w[i];
     float* __restrict__ wt = B.wt[i];
-    for (int64_t e = e0 + threadIdx.x; e < e0 + kBatchChunk && e < total; e += blockDim.x) {
-      const int k = (int)(e % K);
-      const int64_t r = e / K;
-      const int t = (int)(r % T);
-      const int c = (int)(r / T);
-      wt[e] = w[((int64_t)k * T + t) * C + c];
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int k = k0 + r, c = c0 + tx;
+      tile[r][tx] = (k < K && c < C) ? w[((int64_t)k * T + t) * C + c] : 0.f;
     }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int c = c0 + r, k = k0 + tx;
+      if (c < C && k < K) wt[((int64_t)c * T + t) * K + k] = tile[tx][r];
+    }
+    __syncthreads();
   }
 }
 
@@ -1157,7 +1170,7 @@ int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const
       B.T[i] = d->r * d->s;
       B.C[i] = d->c;
       B.start[i] = chunks;
-      chunks += (int)ceil_div((int64_t)d->k * d->r * d->s * d->c, kBatchChunk);
+      chunks += d->r * d->s * (int)ceil_div(d->k, 32) * (int)ceil_div(d->c, 32);  // 32 x 32 tiles, see the kernel
     }
     B.start[B.count] = chunks;
     if (chunks == 0) continue;
