@@ -113,3 +113,49 @@ def test_optimizer_and_scheduler_host_logic():
         tt.optim.SGD(lin.parameters(), lr=0.1, nesterov=True)
     opt.zero_grad()
     assert all(p.grad is None for p in lin.parameters())
+
+
+def test_tensor_path_planning_is_host_logic():
+    """Which passes run on the tcgen05 path / can take pre-packed dgrad weights, and how much workspace they ask for,
+    is decided on the host (conv_api.cu::plan_tensor): callable without a GPU."""
+    from pytortto_b200 import _cabi, ops
+    lib = _cabi.load()
+    ops.set_math_mode("tf32")
+
+    def desc(n, c, h, k, ks, s, groups=1):
+        return ops.conv_desc((n, c, h, h), (k, c // groups, ks, ks), (s, s), (ks // 2, ks // 2), (1, 1), groups)
+
+    d = desc(8, 64, 16, 64, 3, 1)
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(d), i) for i in range(3)] == [1, 1, 1]
+    assert lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d)) == 1
+    assert lib.ttb_conv2d_workspace_size(ctypes.byref(d), 0) == 0          # fprop of aligned channels: no staging
+    assert lib.ttb_conv2d_workspace_size(ctypes.byref(d), 1) >= 64 * 9 * 64 * 4  # dgrad: the re-ordered filters
+
+    d3 = desc(8, 3, 32, 64, 3, 1)   # stem: input channels padded to a K-block; dgrad writes 8 channels and crops
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(d3), i) for i in range(3)] == [1, 1, 1]
+    assert lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d3)) == 0  # needs the staged (padded) copy
+    assert lib.ttb_conv2d_workspace_size(ctypes.byref(d3), 0) >= 8 * 32 * 32 * 32 * 4
+
+    d16 = desc(8, 16, 32, 16, 3, 1)  # 16-channel layers (small_preact_resnet110): padded reduction channels
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(d16), i) for i in range(3)] == [1, 1, 1]
+    assert lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d16)) == 0
+
+    dg = desc(8, 64, 16, 64, 3, 1, groups=2)  # grouped convolutions take the exact direct kernels
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(dg), i) for i in range(3)] == [0, 0, 0]
+
+    ops.set_math_mode("fp32")
+    df = desc(8, 64, 16, 64, 3, 1)
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(df), i) for i in range(3)] == [0, 0, 0]
+    ops.set_math_mode("tf32")
+
+
+def test_bad_arguments_fail_loudly_without_a_gpu():
+    """argument validation of the newer entry points happens before any CUDA call"""
+    from pytortto_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.ttb_sum_splits_multi(1, None, None, None, None, None) != 0
+    assert b"sum_splits_multi" in lib.ttb_last_error()
+    assert lib.ttb_conv2d_dgrad_pack_weights(1, None, None, None, None) != 0
+    assert lib.ttb_comm_bn_finalize(None, 0, None, 2, 0, 0, 1, 8, 1e-5, 0.1, None, None, None, None, None, None, None, None,
+                                    None, None) != 0
+    assert b"comm_bn_finalize" in lib.ttb_last_error()
