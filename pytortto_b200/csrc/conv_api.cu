@@ -29,6 +29,9 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
                 cudaStream_t st, const void* prepacked = nullptr);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st, int* splits_out = nullptr);
+// conv_flat.cu: prototype "flat-shift halo tile" fprop, taken only when TTB_FLAT=1 (not validated on hardware yet)
+bool flat_fprop_supported(const ttb_conv_desc* d);
+int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const float* const* w, float* const* wt,
                              cudaStream_t st);
 int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
@@ -177,6 +180,7 @@ int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, con
               "conv2d_fprop: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
   char* ws = reinterpret_cast<char*>(workspace);
   const void *xa = x, *wa = w;
+  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, bias, y, st);  // TTB_FLAT=1 only
   if (t.stage_ops) {
     if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
     if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, t.p.c, t.bf16, st)) return 1;

@@ -1,0 +1,405 @@
+// PROTOTYPE - compiled, NOT yet validated on hardware, OFF unless TTB_FLAT=1.
+//
+// "Flat-shift halo tile" fprop for stride-1 / dilation-1 convolutions (the 3x3 layers that dominate every ResNet): the
+// production kernel (conv_igemm.cu) loads one im2col A tile per (filter tap, 32-channel slab) - 9 loads of the same
+// pixels for a 3x3 filter - and is bound by operand feed / instruction issue on the 64- and 128-channel layers.  Here
+// output pixels are addressed by a flat index over the ZERO-PADDED image,
+//     f = (n*Hp + p)*Wp + q,   Hp = H + 2*pad_h, Wp = W + 2*pad_w,
+// so that every filter tap is a pure shift of the input: input row = f + r*Wp + s.  A tile of 128 consecutive f needs the
+// padded-flat input rows [f0, f0 + 128 + (R-1)*Wp + (S-1)); they are brought into shared memory ONCE per 32-channel slab,
+// as one tiled-TMA box per padded image row (box = {32 channels, Wp pixels from w = -pad_w}: out-of-bounds zero fill IS
+// the padding), and the R*S taps are R*S UMMA descriptors whose start address moves by whole 128-byte rows.
+// Measured facts this relies on (profiles/r1_umma_row_shift_probe.txt):
+//   * a 128B-swizzled K-major tcgen05.mma operand may start at ANY 128-byte row (base-offset field 0),
+//   * a SWIZZLE_128B TMA box written to a 128-byte-aligned (not 1024-byte-aligned) address takes its XOR phase from the
+//     absolute shared-memory address, so rows of Wp pixels (Wp not a multiple of 8) can be stacked back to back.
+// Outputs at the padding positions (q >= Q or p >= P) are computed and dropped: (Hp*Wp)/(P*Q) - 1 = 13 % extra MMA work at
+// 32x32, 27 % at 16x16 - the kernel is meant for the large-image layers.
+//
+// Structure (persistent, like igemm_fwd_persist_kernel): warp 0 = strip producer (A rows), warps 1-2 = weight-tile
+// producers (alternating K-blocks), warp 3 = MMA issuer + TMEM owner, warps 4-7 = epilogue; two TMEM accumulators.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ttb {
+
+namespace {
+
+constexpr int kFlatTileM = 128;
+constexpr int kFlatMaxTaps = 64;
+constexpr int kFlatStagePitch = 36;  // floats per staged epilogue row
+constexpr int kFlatSlabsPerStrip = 2;  // 32-channel slabs brought in per strip stage (64 channels)
+constexpr int kFlatStripStages = 2;
+constexpr int kFlatBProducers = 2;
+constexpr int kFlatThreads = (1 + kFlatBProducers + 1 + 4) * 32;
+
+struct FlatParams {
+  CUtensorMap tmX;   // 4-D tiled over NHWC x: dims (C, W, H, N), box (32, Wp, 1, 1)
+  CUtensorMap tmB;   // 2-D tiled over the weight matrix [rows = output channels][cols = (tap, c)], box (32, BN)
+  float* out;        // dense NHWC output [N][P][Q][K]
+  const float* bias; // [K] or null
+  int n_img, hp, wp, pad_h, pad_w;   // padded grid
+  int p_out, q_out, k_out;           // valid outputs per image, output channels
+  int taps_r, taps_s;                // filter size
+  int c_blocks;                      // input channels / 32
+  int rows_max;                      // padded rows a strip stage holds per slab
+  int64_t m_flat;                    // n_img * hp * wp
+  int b_koff[kFlatMaxTaps];          // column of tap t's K-slice in the weight matrix (dgrad: flipped taps)
+};
+
+// accumulator (128 lanes x BN fp32 columns in TMEM) -> global rows; rows at padding positions are dropped
+template <int BN>
+__device__ __forceinline__ void flat_epilogue(uint32_t tmem_acc, float* stage_smem, const FlatParams& P, int64_t f0, int n0,
+                                              int ep_warp, int lane_block) {
+  const int lane = threadIdx.x & 31;
+  float* st = stage_smem + ep_warp * (32 * kFlatStagePitch);
+  const int64_t f = f0 + lane_block * 32 + lane;
+  int64_t my_off = -1;
+  if (f < P.m_flat) {
+    const int q = (int)(f % P.wp);
+    const int64_t t = f / P.wp;
+    const int p = (int)(t % P.hp);
+    const int64_t n = t / P.hp;
+    if (q < P.q_out && p < P.p_out) my_off = ((n * P.p_out + p) * P.q_out + q) * (int64_t)P.k_out;
+  }
+#pragma unroll 1
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    const int col0 = n0 + cb * 32;
+    if (col0 >= P.k_out) break;  // warp-uniform
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
+    ptx::tmem_ld_wait();
+    if (P.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < P.k_out) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(P.bias + col0 + j));
+    }
+    float4* srow = reinterpret_cast<float4*>(st + lane * kFlatStagePitch);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+    __syncwarp();
+    const int sub = lane >> 3, c4 = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      const int64_t off = __shfl_sync(0xffffffffu, my_off, rr);
+      const float4 v = *reinterpret_cast<const float4*>(st + rr * kFlatStagePitch + c4 * 4);
+      if (off >= 0 && col0 + c4 * 4 < P.k_out) *reinterpret_cast<float4*>(P.out + off + col0 + c4 * 4) = v;
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN, int NB>
+__global__ void __launch_bounds__(kFlatThreads, 1)
+igemm_flat_kernel(const __grid_constant__ FlatParams P) {
+  static_assert(NB % kFlatBProducers == 0, "a weight stage must always be filled by the same producer");
+  constexpr uint32_t kBBytes = BN * 128;
+  constexpr int kAccCols = BN < 32 ? 32 : BN;
+  constexpr int kTmemCols = 2 * kAccCols;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t slab_bytes = (uint32_t)P.rows_max * (uint32_t)P.wp * 128u;       // one 32-channel slab of a strip
+  const uint32_t strip_bytes = ((kFlatSlabsPerStrip * slab_bytes) + 1023u) & ~1023u;
+  uint8_t* strip0 = smem;                                          // kFlatStripStages strips
+  uint8_t* bring = smem + kFlatStripStages * strip_bytes;           // NB weight tiles
+  float* staging = reinterpret_cast<float*>(bring + NB * kBBytes);  // epilogue staging
+  __shared__ uint64_t strip_full[kFlatStripStages], strip_empty[kFlatStripStages], b_full[NB], b_empty[NB], acc_full[2],
+      acc_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int nt = (P.k_out + BN - 1) / BN;
+  const int64_t mt = (P.m_flat + kFlatTileM - 1) / kFlatTileM;
+  const int64_t tiles = mt * nt;
+  const int taps = P.taps_r * P.taps_s;
+  const int num_groups = (P.c_blocks + kFlatSlabsPerStrip - 1) / kFlatSlabsPerStrip;  // strip loads per tile
+  constexpr int kMmaWarp = 1 + kFlatBProducers;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&P.tmX);
+    ptx::prefetch_tmap(&P.tmB);
+  }
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int s = 0; s < kFlatStripStages; ++s) {
+        ptx::mbar_init(&strip_full[s], 1);
+        ptx::mbar_init(&strip_empty[s], 1);
+      }
+      for (int s = 0; s < NB; ++s) {
+        ptx::mbar_init(&b_full[s], 1);
+        ptx::mbar_init(&b_empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&acc_full[b], 1);
+        ptx::mbar_init(&acc_empty[b], 4);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc<kTmemCols>(&tmem_base_smem);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== strip producer: padded input rows, one TMA box per (slab, padded row) =====================
+    uint32_t g = 0;  // strip stages filled so far
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t f0 = (t / nt) * kFlatTileM;
+      const int64_t row0 = f0 / P.wp;  // first padded row (over n*Hp + hp) the tile touches
+      int64_t last = f0 + kFlatTileM - 1 + (int64_t)(P.taps_r - 1) * P.wp + (P.taps_s - 1);
+      int64_t row1 = last / P.wp;
+      const int64_t rows_total = (int64_t)P.n_img * P.hp;
+      if (row1 >= rows_total) row1 = rows_total - 1;  // rows past the last image only feed dropped outputs
+      const int nrows = (int)(row1 - row0 + 1);
+      for (int grp = 0; grp < num_groups; ++grp, ++g) {
+        const uint32_t stage = g % kFlatStripStages, phase = (g / kFlatStripStages) & 1u;
+        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
+                                                                                     : kFlatSlabsPerStrip;
+        ptx::mbar_wait(&strip_empty[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
+          uint8_t* base = strip0 + stage * strip_bytes;
+          ptx::mbar_expect_tx(&strip_full[stage], (uint32_t)slabs * (uint32_t)nrows * (uint32_t)P.wp * 128u);
+          for (int sl = 0; sl < slabs; ++sl)
+            for (int j = 0; j < nrows; ++j) {
+              const int64_t row = row0 + j;
+              const int n = (int)(row / P.hp);
+              const int hp = (int)(row - (int64_t)n * P.hp);
+              ptx::tma_load_4d(base + sl * slab_bytes + (uint32_t)j * (uint32_t)P.wp * 128u, &P.tmX, &strip_full[stage],
+                               (grp * kFlatSlabsPerStrip + sl) * 32, -P.pad_w, hp - P.pad_h, n);
+            }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kMmaWarp) {
+    // ===================== weight-tile producers (K-block g belongs to producer g % kFlatBProducers) =====================
+    const int me = warp - 1;
+    uint32_t g = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int n0 = (int)(t % nt) * BN;
+      for (int grp = 0; grp < num_groups; ++grp) {
+        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
+                                                                                     : kFlatSlabsPerStrip;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kb0 = P.b_koff[tap];
+          for (int sl = 0; sl < slabs; ++sl, ++g) {
+            if ((int)(g % kFlatBProducers) != me) continue;
+            const uint32_t stage = g % NB, phase = (g / NB) & 1u;
+            ptx::mbar_wait(&b_empty[stage], phase ^ 1u);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(&b_full[stage], kBBytes);
+              ptx::tma_load_2d(bring + stage * kBBytes, &P.tmB, &b_full[stage], kb0 + (grp * kFlatSlabsPerStrip + sl) * 32, n0);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 0, 0, kFlatTileM, BN);
+    uint32_t gs = 0, gb = 0;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int64_t f0 = (t / nt) * kFlatTileM;
+      const int lead = (int)(f0 - (f0 / P.wp) * P.wp);  // tile start inside its first padded row
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kAccCols);
+      bool first = true;
+      for (int grp = 0; grp < num_groups; ++grp, ++gs) {
+        const uint32_t sstage = gs % kFlatStripStages, sphase = (gs / kFlatStripStages) & 1u;
+        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
+                                                                                     : kFlatSlabsPerStrip;
+        ptx::mbar_wait(&strip_full[sstage], sphase);
+        ptx::tc_fence_after();
+        const uint32_t strip = ptx::smem_u32(strip0 + sstage * strip_bytes);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / P.taps_s, s = tap - r * P.taps_s;
+          const uint32_t row_off = (uint32_t)(lead + r * P.wp + s) * 128u;  // the tap is a shift by whole rows
+          for (int sl = 0; sl < slabs; ++sl, ++gb) {
+            const uint32_t bstage = gb % NB, bphase = (gb / NB) & 1u;
+            ptx::mbar_wait(&b_full[bstage], bphase);
+            ptx::tc_fence_after();
+            const uint32_t sa = strip + (uint32_t)sl * slab_bytes + row_off;
+            const uint32_t sb = ptx::smem_u32(bring + bstage * kBBytes);
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+                ptx::mma_tf32(d_tmem, da, db, idesc, !(first && k == 0));
+              }
+              ptx::mma_commit(&b_empty[bstage]);
+            }
+            __syncwarp();
+            first = false;
+          }
+        }
+        if (ptx::elect_one()) ptx::mma_commit(&strip_empty[sstage]);  // every MMA that read this strip has been issued
+        __syncwarp();
+      }
+      if (ptx::elect_one()) ptx::mma_commit(&acc_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - (kMmaWarp + 1);
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int64_t f0 = (t / nt) * kFlatTileM;
+      const int n0 = (int)(t % nt) * BN;
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
+      ptx::tc_fence_after();
+      flat_epilogue<BN>(tmem_base + (uint32_t)(buf * kAccCols), staging, P, f0, n0, ew, warp & 3);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) ptx::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_flat_encode = nullptr;
+
+int flat_load_driver() {
+  if (g_flat_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return 1;
+  }
+  g_flat_encode = (PFN_encodeTiled)fn;
+  return 0;
+}
+
+int flat_rows_max(const ttb_conv_desc* d) {
+  const int wp = d->w + 2 * d->pad_w;
+  // 128 + S - 1 consecutive padded-flat elements starting anywhere inside a row, plus the R - 1 rows below
+  return (wp - 1 + kFlatTileM + d->s - 1 + wp - 1) / wp + (d->r - 1);
+}
+
+template <int BN, int NB>
+int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) {
+  const size_t smem = strip_bytes_total + (size_t)NB * BN * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024;
+  if (smem > 232448) {
+    set_error("conv flat path: %zu bytes of shared memory needed", smem);
+    return 1;
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_flat_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("conv flat path: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+    attr = smem;
+  }
+  const int64_t tiles = ceil_div(P.m_flat, kFlatTileM) * ceil_div(P.k_out, BN);
+  const int sms = sm_count();
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  igemm_flat_kernel<BN, NB><<<grid, kFlatThreads, smem, st>>>(P);
+  return check_launch("igemm_flat_kernel");
+}
+
+}  // namespace
+
+// 1 when TTB_FLAT=1 and the problem fits the prototype: TF32, stride 1, dilation 1, groups 1, C % 32 == 0, K % 8 == 0
+bool flat_fprop_supported(const ttb_conv_desc* d) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("TTB_FLAT");
+    enabled = e ? atoi(e) : 0;
+  }
+  if (!enabled) return false;
+  if (d->math_mode != TTB_MATH_TF32 || d->groups != 1) return false;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return false;
+  if (d->c % 32 != 0 || d->k % 8 != 0 || d->r * d->s > kFlatMaxTaps || d->r * d->s < 2) return false;
+  const int hp = d->h + 2 * d->pad_h, wp = d->w + 2 * d->pad_w;
+  if (wp > 256 || hp - d->r + 1 != d->p || wp - d->s + 1 != d->q || d->p < 1 || d->q < 1) return false;
+  const size_t strips = (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * flat_rows_max(d) * wp * 128 + 1023) & ~(size_t)1023);
+  return strips + 4 * 128 * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024 <= 232448;  // widest weight ring: 4 x (128 x 128 B)
+}
+
+// x: NHWC fp32, w: [K][R][S][C] fp32, y: dense NHWC fp32
+int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+  if (flat_load_driver()) return 1;
+  static thread_local FlatParams P;
+  memset(&P, 0, sizeof(P));
+  const int hp = d->h + 2 * d->pad_h, wp = d->w + 2 * d->pad_w;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->c * 4, (cuuint64_t)d->w * d->c * 4, (cuuint64_t)d->h * d->w * d->c * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)wp, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_flat_encode(&P.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv flat path: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+      return 1;
+    }
+  }
+  // widest N tile that keeps most SMs busy; the weight ring shrinks as the tile grows
+  const int64_t mt = ceil_div((int64_t)d->n * hp * wp, kFlatTileM);
+  int bn = 64;
+  if (d->k > 64 && mt * ceil_div(d->k, 128) * 5 >= (int64_t)sm_count() * 4) bn = 128;
+  if (d->k <= 32) bn = 32;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->r * d->s * d->c, (cuuint64_t)d->k};
+    cuuint64_t strides[1] = {(cuuint64_t)d->r * d->s * d->c * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_flat_encode(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("conv flat path: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+      return 1;
+    }
+  }
+  P.out = y;
+  P.bias = bias;
+  P.n_img = d->n;
+  P.hp = hp;
+  P.wp = wp;
+  P.pad_h = d->pad_h;
+  P.pad_w = d->pad_w;
+  P.p_out = d->p;
+  P.q_out = d->q;
+  P.k_out = d->k;
+  P.taps_r = d->r;
+  P.taps_s = d->s;
+  P.c_blocks = d->c / 32;
+  P.rows_max = flat_rows_max(d);
+  P.m_flat = (int64_t)d->n * hp * wp;
+  for (int t = 0; t < d->r * d->s; ++t) P.b_koff[t] = t * d->c;
+  const size_t strips = (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * P.rows_max * wp * 128 + 1023) & ~(size_t)1023);
+  switch (bn) {
+    case 128: return flat_launch<128, 4>(P, strips, st);
+    case 64: return flat_launch<64, 6>(P, strips, st);
+    default: return flat_launch<32, 6>(P, strips, st);
+  }
+}
+
+}  // namespace ttb

@@ -1,0 +1,55 @@
+"""First thing to run for the flat-shift prototype (csrc/conv_flat.cu) on a B200:
+
+    TTB_FLAT=1 python scripts/flat_check.py
+
+Compares fprop through the prototype (TF32, taken when TTB_FLAT=1 and the problem is stride-1 / dilation-1 with
+C % 32 == 0) with the exact fp32 direct kernels on the same inputs (tolerance 2e-3 of the tensor max), then times both
+the prototype and - in a second process with TTB_FLAT unset - the production kernel from a replayed CUDA graph."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pytortto_b200 as tt
+from pytortto_b200 import ops
+from pytortto_b200.xparray import cparray
+from scripts.conv_sweep import graph_time_us
+
+CASES = [  # n, c, h, w, k, ks, pad, bias
+    (2, 32, 8, 8, 32, 3, 1, False),
+    (3, 64, 12, 10, 64, 3, 1, True),      # W + 2 = 12: rows not a multiple of 8 pixels, ragged last tile
+    (4, 64, 32, 32, 64, 3, 1, False),     # layer-1 shape at a small batch
+    (4, 128, 16, 16, 128, 3, 1, False),   # two strip groups per tile
+    (2, 96, 9, 7, 72, 3, 1, True),        # 3 slabs (a 1-slab last group), K not a multiple of 32
+    (2, 64, 10, 10, 64, 5, 2, False),     # 5x5
+    (2, 64, 8, 8, 40, 3, 0, False),       # no padding
+    (256, 64, 32, 32, 64, 3, 1, False),   # the real layer-1 problem
+    (256, 128, 16, 16, 128, 3, 1, False),
+]
+
+
+def main():
+    flat = os.environ.get("TTB_FLAT") == "1"
+    print("TTB_FLAT =", os.environ.get("TTB_FLAT"), "(prototype path)" if flat else "(production path)")
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for n, c, h, w, k, ks, pad, bias in CASES:
+        x = cparray.from_numpy(rng.standard_normal((n, c, h, w)).astype(np.float32))
+        wt = cparray.from_numpy((rng.standard_normal((k, c, ks, ks)) / np.sqrt(c * ks * ks)).astype(np.float32))
+        b = cparray.from_numpy(rng.standard_normal((k,)).astype(np.float32)) if bias else None
+        tt.set_math_mode("fp32")
+        d32 = ops.conv_desc(x.shape, wt.shape, (1, 1), (pad, pad), (1, 1), 1)
+        ref = ops.conv2d_fprop(x, wt, b, d32).get()
+        tt.set_math_mode("tf32")
+        d = ops.conv_desc(x.shape, wt.shape, (1, 1), (pad, pad), (1, 1), 1)
+        y = ops.conv2d_fprop(x, wt, b, d).get()
+        err = float(np.abs(y - ref).max() / np.abs(ref).max())
+        worst = max(worst, err)
+        t = graph_time_us(lambda: ops.conv2d_fprop(x, wt, b, d))
+        gf = 2.0 * n * d.p * d.q * k * c * ks * ks / 1e9
+        print(f"n{n} c{c} {h}x{w} k{k} f{ks} p{pad} bias={int(bias)}: rel-err {err:.2e} {'OK' if err < 2e-3 else 'FAIL'}"
+              f"   {t:8.1f} us  {gf / t * 1e3:6.0f} TF/s", flush=True)
+    print("worst rel-err", worst)
+    return 0 if worst < 2e-3 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
