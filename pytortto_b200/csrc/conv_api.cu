@@ -31,7 +31,9 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
                 cudaStream_t st, int* splits_out = nullptr);
 // conv_flat.cu: prototype "flat-shift halo tile" fprop, taken only when TTB_FLAT=1 (not validated on hardware yet)
 bool flat_fprop_supported(const ttb_conv_desc* d);
+bool flat_dgrad_supported(const ttb_conv_desc* d);
 int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st);
 int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const float* const* w, float* const* wt,
                              cudaStream_t st);
 int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
@@ -280,6 +282,7 @@ int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const fl
   if (int rc = validate(d, "conv2d_dgrad_prepacked")) return rc;
   TensorPlan t;
   TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops, "conv2d_dgrad_prepacked: problem needs the staged path");
+  if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream));  // TTB_FLAT=1 only
   return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed);
 }
 

@@ -293,12 +293,6 @@ int flat_load_driver() {
   return 0;
 }
 
-int flat_rows_max(const ttb_conv_desc* d) {
-  const int wp = d->w + 2 * d->pad_w;
-  // 128 + S - 1 consecutive padded-flat elements starting anywhere inside a row, plus the R - 1 rows below
-  return (wp - 1 + kFlatTileM + d->s - 1 + wp - 1) / wp + (d->r - 1);
-}
-
 template <int BN, int NB>
 int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) {
   const size_t smem = strip_bytes_total + (size_t)NB * BN * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024;
@@ -324,82 +318,131 @@ int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) 
 
 }  // namespace
 
-// 1 when TTB_FLAT=1 and the problem fits the prototype: TF32, stride 1, dilation 1, groups 1, C % 32 == 0, K % 8 == 0
-bool flat_fprop_supported(const ttb_conv_desc* d) {
+static bool flat_enabled() {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("TTB_FLAT");
     enabled = e ? atoi(e) : 0;
   }
-  if (!enabled) return false;
-  if (d->math_mode != TTB_MATH_TF32 || d->groups != 1) return false;
-  if (d->stride_h != 1 || d->stride_w != 1 || d->dil_h != 1 || d->dil_w != 1) return false;
-  if (d->c % 32 != 0 || d->k % 8 != 0 || d->r * d->s > kFlatMaxTaps || d->r * d->s < 2) return false;
-  const int hp = d->h + 2 * d->pad_h, wp = d->w + 2 * d->pad_w;
-  if (wp > 256 || hp - d->r + 1 != d->p || wp - d->s + 1 != d->q || d->p < 1 || d->q < 1) return false;
-  const size_t strips = (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * flat_rows_max(d) * wp * 128 + 1023) & ~(size_t)1023);
+  return enabled != 0;
+}
+
+// geometry of one flat-shift problem: correlation of `in` (NHWC, c_in channels, zero-padded by pad) with r x s taps
+struct FlatProblem {
+  int n, c_in, h_in, w_in, k_out, r, s, pad_h, pad_w, p_out, q_out;
+};
+
+static int flat_rows_max_of(const FlatProblem& g) {
+  const int wp = g.w_in + 2 * g.pad_w;
+  // 128 + S - 1 consecutive padded-flat elements starting anywhere inside a row, plus the R - 1 rows below
+  return (wp - 1 + kFlatTileM + g.s - 1 + wp - 1) / wp + (g.r - 1);
+}
+
+static bool flat_geometry_ok(const FlatProblem& g) {
+  if (g.c_in % 32 != 0 || g.k_out % 8 != 0 || g.r * g.s > kFlatMaxTaps || g.r * g.s < 2) return false;
+  if (g.pad_h < 0 || g.pad_w < 0) return false;
+  const int hp = g.h_in + 2 * g.pad_h, wp = g.w_in + 2 * g.pad_w;
+  if (wp > 256 || hp - g.r + 1 != g.p_out || wp - g.s + 1 != g.q_out || g.p_out < 1 || g.q_out < 1) return false;
+  const size_t strips =
+      (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * flat_rows_max_of(g) * wp * 128 + 1023) & ~(size_t)1023);
   return strips + 4 * 128 * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024 <= 232448;  // widest weight ring: 4 x (128 x 128 B)
 }
 
-// x: NHWC fp32, w: [K][R][S][C] fp32, y: dense NHWC fp32
-int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+// in: NHWC fp32 [n][h_in][w_in][c_in]; wmat: [k_out rows][r*s*c_in cols] fp32 with tap t's slice at column koff[t];
+// out: dense NHWC fp32 [n][p_out][q_out][k_out]
+static int flat_run(const FlatProblem& g, const float* in, const float* wmat, const int* koff, const float* bias, float* out,
+                    cudaStream_t st) {
   if (flat_load_driver()) return 1;
   static thread_local FlatParams P;
   memset(&P, 0, sizeof(P));
-  const int hp = d->h + 2 * d->pad_h, wp = d->w + 2 * d->pad_w;
+  const int hp = g.h_in + 2 * g.pad_h, wp = g.w_in + 2 * g.pad_w;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d->c, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
-    cuuint64_t strides[3] = {(cuuint64_t)d->c * 4, (cuuint64_t)d->w * d->c * 4, (cuuint64_t)d->h * d->w * d->c * 4};
+    cuuint64_t dims[4] = {(cuuint64_t)g.c_in, (cuuint64_t)g.w_in, (cuuint64_t)g.h_in, (cuuint64_t)g.n};
+    cuuint64_t strides[3] = {(cuuint64_t)g.c_in * 4, (cuuint64_t)g.w_in * g.c_in * 4, (cuuint64_t)g.h_in * g.w_in * g.c_in * 4};
     cuuint32_t box[4] = {32, (cuuint32_t)wp, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_flat_encode(&P.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr,
+    CUresult r = g_flat_encode(&P.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("conv flat path: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+      set_error("conv flat path: cuTensorMapEncodeTiled(activation) failed (%d)", (int)r);
       return 1;
     }
   }
   // widest N tile that keeps most SMs busy; the weight ring shrinks as the tile grows
-  const int64_t mt = ceil_div((int64_t)d->n * hp * wp, kFlatTileM);
+  const int64_t mt = ceil_div((int64_t)g.n * hp * wp, kFlatTileM);
   int bn = 64;
-  if (d->k > 64 && mt * ceil_div(d->k, 128) * 5 >= (int64_t)sm_count() * 4) bn = 128;
-  if (d->k <= 32) bn = 32;
+  if (g.k_out > 64 && mt * ceil_div(g.k_out, 128) * 5 >= (int64_t)sm_count() * 4) bn = 128;
+  if (g.k_out <= 32) bn = 32;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d->r * d->s * d->c, (cuuint64_t)d->k};
-    cuuint64_t strides[1] = {(cuuint64_t)d->r * d->s * d->c * 4};
+    const cuuint64_t cols = (cuuint64_t)g.r * g.s * g.c_in;
+    cuuint64_t dims[2] = {cols, (cuuint64_t)g.k_out};
+    cuuint64_t strides[1] = {cols * 4};
     cuuint32_t box[2] = {32, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_flat_encode(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr,
+    CUresult r = g_flat_encode(&P.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wmat, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("conv flat path: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+      set_error("conv flat path: cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
       return 1;
     }
   }
-  P.out = y;
+  P.out = out;
   P.bias = bias;
-  P.n_img = d->n;
+  P.n_img = g.n;
   P.hp = hp;
   P.wp = wp;
-  P.pad_h = d->pad_h;
-  P.pad_w = d->pad_w;
-  P.p_out = d->p;
-  P.q_out = d->q;
-  P.k_out = d->k;
-  P.taps_r = d->r;
-  P.taps_s = d->s;
-  P.c_blocks = d->c / 32;
-  P.rows_max = flat_rows_max(d);
-  P.m_flat = (int64_t)d->n * hp * wp;
-  for (int t = 0; t < d->r * d->s; ++t) P.b_koff[t] = t * d->c;
+  P.pad_h = g.pad_h;
+  P.pad_w = g.pad_w;
+  P.p_out = g.p_out;
+  P.q_out = g.q_out;
+  P.k_out = g.k_out;
+  P.taps_r = g.r;
+  P.taps_s = g.s;
+  P.c_blocks = g.c_in / 32;
+  P.rows_max = flat_rows_max_of(g);
+  P.m_flat = (int64_t)g.n * hp * wp;
+  for (int t = 0; t < g.r * g.s; ++t) P.b_koff[t] = koff[t];
   const size_t strips = (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * P.rows_max * wp * 128 + 1023) & ~(size_t)1023);
   switch (bn) {
     case 128: return flat_launch<128, 4>(P, strips, st);
     case 64: return flat_launch<64, 6>(P, strips, st);
     default: return flat_launch<32, 6>(P, strips, st);
   }
+}
+
+static bool flat_common_ok(const ttb_conv_desc* d) {
+  return flat_enabled() && d->math_mode == TTB_MATH_TF32 && d->groups == 1 && d->stride_h == 1 && d->stride_w == 1 &&
+         d->dil_h == 1 && d->dil_w == 1;
+}
+
+static FlatProblem flat_fprop_problem(const ttb_conv_desc* d) {
+  return FlatProblem{d->n, d->c, d->h, d->w, d->k, d->r, d->s, d->pad_h, d->pad_w, d->p, d->q};
+}
+
+// dgrad of a stride-1 convolution = the same correlation over dY with the taps flipped and padding R-1-pad
+static FlatProblem flat_dgrad_problem(const ttb_conv_desc* d) {
+  return FlatProblem{d->n, d->k, d->p, d->q, d->c, d->r, d->s, d->r - 1 - d->pad_h, d->s - 1 - d->pad_w, d->h, d->w};
+}
+
+// 1 when TTB_FLAT=1 and the problem fits the prototype: TF32, stride 1, dilation 1, groups 1, C % 32 == 0, K % 8 == 0
+bool flat_fprop_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_geometry_ok(flat_fprop_problem(d)); }
+bool flat_dgrad_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_geometry_ok(flat_dgrad_problem(d)); }
+
+// x: NHWC fp32, w: [K][R][S][C] fp32, y: dense NHWC fp32
+int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+  int koff[kFlatMaxTaps];
+  for (int t = 0; t < d->r * d->s; ++t) koff[t] = t * d->c;
+  return flat_run(flat_fprop_problem(d), x, w, koff, bias, y, st);
+}
+
+// dy: NHWC fp32 [N][P][Q][K], w_packed: [C][R][S][K] fp32 (the dgrad re-ordering), dx: dense NHWC fp32 [N][H][W][C]
+int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st) {
+  int koff[kFlatMaxTaps];
+  for (int r = 0; r < d->r; ++r)
+    for (int s = 0; s < d->s; ++s) koff[r * d->s + s] = ((d->r - 1 - r) * d->s + (d->s - 1 - s)) * d->k;  // flipped taps
+  return flat_run(flat_dgrad_problem(d), dy, w_packed, koff, nullptr, dx, st);
 }
 
 }  // namespace ttb

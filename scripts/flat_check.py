@@ -5,12 +5,12 @@
 Compares fprop through the prototype (TF32, taken when TTB_FLAT=1 and the problem is stride-1 / dilation-1 with
 C % 32 == 0) with the exact fp32 direct kernels on the same inputs (tolerance 2e-3 of the tensor max), then times both
 the prototype and - in a second process with TTB_FLAT unset - the production kernel from a replayed CUDA graph."""
-import os, sys
+import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pytortto_b200 as tt
-from pytortto_b200 import ops
-from pytortto_b200.xparray import cparray
+from pytortto_b200 import _cabi, ops
+from pytortto_b200.xparray import cparray, current_stream_ptr
 from scripts.conv_sweep import graph_time_us
 
 CASES = [  # n, c, h, w, k, ks, pad, bias
@@ -47,6 +47,28 @@ def main():
         gf = 2.0 * n * d.p * d.q * k * c * ks * ks / 1e9
         print(f"n{n} c{c} {h}x{w} k{k} f{ks} p{pad} bias={int(bias)}: rel-err {err:.2e} {'OK' if err < 2e-3 else 'FAIL'}"
               f"   {t:8.1f} us  {gf / t * 1e3:6.0f} TF/s", flush=True)
+        # dgrad through the pre-packed entry points (what a backward sweep calls; the prototype hooks in there)
+        lib = _cabi.load()
+        if k % 32 == 0 and lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d)):
+            dy = cparray.from_numpy(rng.standard_normal((n, k, d.p, d.q)).astype(np.float32))
+            tt.set_math_mode("fp32")
+            dref = ops.conv2d_dgrad(dy, wt, d32).get()
+            tt.set_math_mode("tf32")
+            packed = torch.empty(wt.t.numel(), dtype=torch.float32, device="cuda")
+            descs = (ctypes.POINTER(_cabi.ConvDesc) * 1)(ctypes.pointer(d))
+            src = (ctypes.c_void_p * 1)(wt.t.data_ptr())
+            dst = (ctypes.c_void_p * 1)(packed.data_ptr())
+            _cabi.call("ttb_conv2d_dgrad_pack_weights", 1, descs, src, dst, current_stream_ptr())
+            dx = cparray(torch.empty_like(x.t))
+
+            def run_dgrad():
+                _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), packed.data_ptr(), dx.t.data_ptr(),
+                           current_stream_ptr())
+            run_dgrad()
+            derr = float(np.abs(dx.get() - dref).max() / np.abs(dref).max())
+            worst = max(worst, derr)
+            td = graph_time_us(run_dgrad)
+            print(f"    dgrad: rel-err {derr:.2e} {'OK' if derr < 2e-3 else 'FAIL'}   {td:8.1f} us  {gf / td * 1e3:6.0f} TF/s", flush=True)
     print("worst rel-err", worst)
     return 0 if worst < 2e-3 else 1
 
