@@ -12,7 +12,7 @@ import math
 
 from .. import ops
 from ..xparray import cparray
-from .function import Function
+from .function import AccumulateGrad, Function
 from .helper import build_links, inplace_precheck, inplace_update
 
 prod = math.prod
@@ -97,8 +97,12 @@ class Convolution(Function):
         # 3.92 without the fork - the two tensor-bound kernels cannot share an SM (shared memory) and an HBM-bound
         # BatchNorm pass gains nothing from running beside a wgrad (scripts/overlap_probe.py), so the gain is only
         # the overlap of each kernel's partial last wave / epilogue with the start of the next
+        # The fork is only safe when dW goes straight to a leaf: AccumulateGrad, the DP bucket launch and the end of the
+        # sweep join the wgrad stream before anything reads it.  A non-leaf weight (w * mask, weight standardisation, a
+        # view of a parameter) hands dW to another node's backward on the main stream, so it is computed in order.
         if ctx.needs_input_grad[1]:
-            grad1 = ops.conv2d_wgrad(xd0, gd0, d, overlap=True)
+            to_leaf = ctx.next_functions[1][0].__class__ is AccumulateGrad
+            grad1 = ops.conv2d_wgrad(xd0, gd0, d, overlap=to_leaf)
         if ctx.needs_input_grad[0]:
             grad0 = ops.conv2d_dgrad(gd0, xd1, d)
         return grad0, grad1, grad2
@@ -255,7 +259,8 @@ class _BatchNormBase(Function):
         else:
             ctx.save_for_backward(xt0, xt1)
         ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None,
-                      'sync_key': None if ident is None else (id(ident), 'b')}
+                      'sync_key': None if ident is None else (id(ident), 'b'),
+                      'affine_ids': (None if xt1 is None else id(xt1), None if xt2 is None else id(xt2))}
         return yt0
 
     @classmethod
@@ -265,6 +270,8 @@ class _BatchNormBase(Function):
         relu_out = saved[2] if cls._fuse_relu else None
         from .. import distributed as dist
         hook = dist.bn_backward_hook(ctx.params['sync_key']) if ctx.params['synced'] else None
+        if hook is not None:  # dgamma / dbeta below come from all-reduced sums: the DP layer must not reduce them again
+            dist.note_synced_bn_params(ctx.params['affine_ids'])
         # `_accum0`: a gradient that already reached the input through another branch (the residual shortcut); the
         # engine hands it over (Tensor._sweep) and the dx pass adds it instead of a separate add kernel
         accum = ctx.params.pop('_accum0', None)

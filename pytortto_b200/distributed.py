@@ -189,6 +189,18 @@ def bn_backward_hook(key=None):
     return _make_stat_hook(key) if _sync_bn_active() else None
 
 
+# ids of BatchNorm weight / bias Tensors whose gradient of the CURRENT backward pass was computed from all-reduced sums
+# (a SyncBN layer in training mode).  Decided per step, not per module: a BatchNorm layer in eval mode (frozen
+# statistics) produces rank-local dgamma / dbeta, which must go through the gradient buckets like any other parameter.
+_synced_bn_step = set()
+
+
+def note_synced_bn_params(ids):
+    for i in ids:
+        if i is not None:
+            _synced_bn_step.add(i)
+
+
 def enable_peer_comm():
     """Switch the SyncBN statistic exchange to the NVLink peer-memory path (needs CUDA IPC between the ranks)."""
     if _state.get("peer_comm") is None and _state["initialized"] and _state["world"] > 1 and _state["backend"] == "nccl":
@@ -269,14 +281,8 @@ class DistributedDataParallel:
         if broadcast:
             broadcast_parameters(module)
         self._param_ids = {id(p) for p in module.parameters()}
-        self._synced_bn_params = set()
-        if _state["sync_bn"]:
-            from .nn.modules import _BatchNorm
-            for m in module.modules():
-                if isinstance(m, _BatchNorm):
-                    for p in (m._parameters.get("weight"), m._parameters.get("bias")):
-                        if p is not None:
-                            self._synced_bn_params.add(id(p))
+        # BatchNorm affine parameters whose gradient came out of a SyncBN backward THIS step (see _synced_bn_step)
+        self._synced_bn_params = _synced_bn_step
         self._pending, self._pending_bytes = [], 0
         self._buckets, self._seen = [], set()
         AccumulateGrad.post_hooks.append(self._on_grad_ready)
@@ -350,3 +356,4 @@ class DistributedDataParallel:
         if bn_grads:
             torch._foreach_mul_(bn_grads, inv)  # one multi-tensor launch for the ~2 x (#BatchNorm layers) tiny tensors
         self._buckets, self._seen = [], set()
+        _synced_bn_step.clear()

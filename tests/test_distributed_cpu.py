@@ -57,7 +57,11 @@ def _worker(rank, world, port, q):
 
         # ---- broadcast + bucketed gradient averaging through the AccumulateGrad hook -----------------------------
         tt.manual_seed(100 + rank)  # different init per rank on purpose
-        net = tt.nn.Sequential(tt.nn.Conv2d(3, 4, 3, bias=True), tt.nn.BatchNorm2d(4), tt.nn.Linear(5, 2))
+        # net[1]: a BatchNorm whose backward ran the SyncBN exchange this step (its dgamma / dbeta are already global
+        # sums: scaled by 1/world only); net[2]: a BatchNorm in eval mode (frozen statistics, no exchange) - its affine
+        # gradients are rank-local and must be averaged through the buckets like any other parameter
+        net = tt.nn.Sequential(tt.nn.Conv2d(3, 4, 3, bias=True), tt.nn.BatchNorm2d(4), tt.nn.BatchNorm2d(4),
+                               tt.nn.Linear(5, 2))
         ddp = dist.DistributedDataParallel(net, bucket_mb=1e-4)  # tiny buckets: several collectives in flight
         ref = [np.array(p.data, copy=True) for p in net.parameters()]
         gathered = [torch.zeros(sum(r.size for r in ref)) for _ in range(world)]
@@ -65,6 +69,7 @@ def _worker(rank, world, port, q):
         assert torch.equal(gathered[0], gathered[1]), "broadcast_parameters must equalise the ranks"
 
         params = list(net.parameters())
+        dist.note_synced_bn_params((id(net[1].weight), id(net[1].bias)))  # what BatchNorm.backward does under SyncBN
         local = []
         for i, p in enumerate(reversed(params)):  # backward order
             g = np.random.default_rng(10 * rank + i).standard_normal(p.shape).astype(np.float32)
@@ -82,6 +87,7 @@ def _worker(rank, world, port, q):
             other = np.random.default_rng(10 * (1 - rank) + i).standard_normal(p.shape).astype(np.float32)
             want = local[i] / world if id(p) in bn_ids else (local[i] + other) / world
             np.testing.assert_allclose(p.grad.t.numpy(), want, rtol=1e-6, atol=1e-7)
+        assert not dist._synced_bn_step, "the per-step set must be cleared by reduce_gradients"
         ddp.close()
         assert not AccumulateGrad.post_hooks
         dist.destroy_process_group()
