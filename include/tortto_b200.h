@@ -103,6 +103,27 @@ int ttb_conv2d_wgrad_partial(const ttb_conv_desc* d, const float* x, const float
 int ttb_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
                          float* const* outs, void* stream);
 
+/* bf16-operand forms (TTB_MATH_BF16 descriptors): the operands are ALREADY bf16 in HBM - activations / gradients NHWC
+ * bf16 as co-written by ttb_bn_apply / ttb_bn_bwd_apply / ttb_relu_fwd (or converted by ttb_to_bf16), weights bf16 as
+ * written by ttb_conv2d_pack_weights_bf16 - so one call is exactly one tcgen05 implicit-GEMM launch; accumulation and
+ * outputs stay fp32.  Replaces the same reference sites as ttb_conv2d_fprop / _dgrad / _wgrad (grad_nn.py:595-682).
+ *   ttb_conv2d_bf16_supported       1 if the pass can take bf16 operands as they are (groups == 1, reduction channels in
+ *                                   whole 64-channel K-blocks), else use the fp32-operand entry points
+ *   ttb_conv2d_workspace_size_bf16  bytes of workspace ttb_conv2d_wgrad_bf16 needs (pixel-split partial sums)
+ *   ttb_conv2d_pack_weights_bf16    w[i] fp32 [K][R][S][C] -> w_bf16[i] (same order; fprop) and wt_bf16[i] ([C][R][S][K];
+ *                                   dgrad) for `count` layers in one launch; either destination entry may be NULL
+ *   ttb_to_bf16                     dst[i] = bf16(src[i]), n % 4 == 0 */
+int ttb_conv2d_bf16_supported(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
+size_t ttb_conv2d_workspace_size_bf16(const ttb_conv_desc* d, int pass);
+int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const float* bias, float* y,
+                          void* stream);
+int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, float* dx, void* stream);
+int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int ttb_conv2d_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
+                                 void* const* wt_bf16, void* stream);
+int ttb_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
 /* ---- batch norm (x viewed as [M = N*H*W rows][C channels]) ---------------------------------------------- */
 /* number of row chunks ttb_bn_stats / ttb_bn_bwd_reduce emit partial sums for */
 int ttb_bn_num_chunks(int64_t m, int c);
@@ -112,7 +133,7 @@ int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chu
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream);
 /* from sums[num_chunks][2][C] (per-chunk partials, summed here in fixed order; num_chunks = 1 for an already reduced /
  * all-reduced buffer) over `count` elements per channel: mean, var_eps = biased var + eps, sd = sqrt(var_eps)
- * (what BatchNorm.forward saves, grad_nn.py:962-963), scale = gamma/sd, shift = beta - mean*scale, and, if
+ * (what BatchNorm.forward saves, grad_nn.py:962-963), scale = gamma/sd, shift = beta (0 without affine), and, if
  * running_mean/var != NULL, running = (1-momentum)*running + momentum*{mean, var*count/(count-1)} (:925-930). */
 int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, float eps, float momentum,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
@@ -121,13 +142,16 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
 int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float eps, const float* gamma,
                         const float* beta, float* mean, float* var_eps, float* sd, float* scale, float* shift,
                         void* stream);
-/* y = x*scale[c] + shift[c]; relu != 0 fuses y = max(y, 0) */
-int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale, const float* shift, int relu,
-                 void* stream);
+/* y = (x - mean[c])*scale[c] + beta[c] (the reference's order of operations, grad_nn.py:942-959, with gamma/sd folded
+ * into scale; `beta` = the `shift` row the finalize entry points write); relu != 0 fuses y = max(y, 0).
+ * y_bf16 (may be NULL): the same values rounded to bf16, co-written for the bf16 tensor path (ttb_conv2d_*_bf16). */
+int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* mean, const float* scale, const float* beta,
+                 int relu, void* y_bf16, void* stream);
 /* partials[chunk][2][C]: sum(dy), sum(dy*(x-mean)).  If relu_out != NULL dy is first masked by (relu_out > 0)
  * (fused ReLU backward, grad_nn.py:64-69).  The mask of a fused BatchNorm+ReLU node comes either from relu_out (the
- * saved ReLU output) or - one read per element cheaper - is recomputed as fmaf(x, relu_scale, relu_shift) > 0 with the
- * scale / shift rows forward normalised with (bit-identical to what forward tested); give one of the two or neither. */
+ * saved ReLU output) or - one read per element cheaper - is recomputed as fmaf(x - mean, relu_scale, relu_shift) > 0
+ * with the scale / shift rows forward normalised with (bit-identical to what forward tested); give one of the two or
+ * neither. */
 int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
                       const float* relu_shift, int64_t m, int c, double* partials, int num_chunks, void* stream);
 /* from sums[num_chunks][2][C]: dgamma = sum(dy*(x-mean))/sd, dbeta = sum(dy), and the three per-channel
@@ -136,12 +160,14 @@ int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c
                         const float* sd, float* dgamma, float* dbeta, float* coef /*[3][C]*/, void* stream);
 /* dx = c1*(dy - c2 - (x-mean)*c3) [+ accum]; accum (may be null): a gradient that already reached the same tensor
  * through another branch, i.e. the engine's `grad += new` (tensor.py:597-599) folded into this pass */
+/* dx_bf16 (may be NULL): dx rounded to bf16, co-written for the bf16 tensor path (it is the dY of the producing conv) */
 int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
                      const float* relu_shift, const float* coef, const float* accum, float* dx, int64_t m, int c,
-                     void* stream);
+                     void* dx_bf16, void* stream);
 
 /* ---- relu / elementwise ---------------------------------------------------------------------------------- */
-int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream);              /* y may alias x (in-place) */
+/* y may alias x (in-place); y_bf16 (may be NULL): bf16 copy of y for the bf16 tensor path */
+int ttb_relu_fwd(const float* x, float* y, int64_t n, void* y_bf16, void* stream);
 int ttb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
 int ttb_add(const float* a, const float* b, float* out, int64_t n, void* stream); /* out may alias a or b    */
 int ttb_axpy(float alpha, const float* x, float* y, int64_t n, void* stream);     /* y += alpha*x            */
@@ -157,6 +183,15 @@ int ttb_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n
 int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* bufs,
                        const int64_t* sizes, const unsigned char* first_step, float lr, float momentum, float dampening,
                        float weight_decay, int nesterov, void* stream);
+
+/* Adam / AdamW (optim/_functional.py:25-68, :71-115) for `n_tensors` parameter tensors in as few launches as possible.
+ * `state` = 3 floats on the DEVICE: step, 1 - beta1^step, 1 - beta2^step; ttb_adam_advance increments the step and
+ * refreshes the two bias corrections (one 1-thread kernel per optimizer step), so the update is CUDA-graph safe.
+ * max_exp_avg_sq (amsgrad) may be NULL; decoupled != 0 selects AdamW's p *= 1 - lr*weight_decay. */
+int ttb_adam_advance(float* state, float beta1, float beta2, void* stream);
+int ttb_adam_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, const float* state,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, void* stream);
 
 /* ---- small-message all-reduce over NVLink peer memory (SyncBN statistics; one process per GPU) ------------------- */
 /* cudaMalloc a zeroed communication buffer and export its CUDA-IPC handle (64 bytes) */

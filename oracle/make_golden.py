@@ -176,6 +176,47 @@ def gen_bn():
     print("batch_norm.npz", len(BN_CASES), "cases")
 
 
+def gen_bn_large_mean():
+    """|mean| / sd ~ 1e3 per channel: the regime where one-pass sum(x^2) statistics in fp32 lose the
+    variance.  Stores the REAL reference's fp32 results and a float64 evaluation of the same formulas
+    (grad_nn.py:923-959, 977-988), so a test can hold an implementation to the reference's own distance from the truth."""
+    out = {}
+    rng = np.random.default_rng(777)
+    shape = (16, 8, 16, 16)
+    c = shape[1]
+    offs = (1000.0 * (1.0 + 0.1 * np.arange(c)) * np.where(np.arange(c) % 2, -1.0, 1.0)).reshape(1, c, 1, 1)
+    x = f32(rng.standard_normal(shape) + offs)
+    dy = f32(rng.standard_normal(shape))
+    gamma = f32(rng.standard_normal(c) * 0.5 + 1.0)
+    beta = f32(rng.standard_normal(c) * 0.5)
+    bn = nn.BatchNorm2d(c)
+    bn.weight.data[...] = gamma
+    bn.bias.data[...] = beta
+    bn.train(True)
+    xt = tt.tensor(x, requires_grad=True)
+    y = bn(xt)
+    y.backward(tt.tensor(dy))
+    out.update(x=x, dy=dy, gamma=gamma, beta=beta, y=f32(y.data), dx=f32(xt.grad), dgamma=f32(bn.weight.grad),
+               dbeta=f32(bn.bias.grad), rm=f32(bn.running_mean.data), rv=f32(bn.running_var.data))
+    # float64 evaluation of the same definition
+    x64, dy64, g64, b64 = x.astype(np.float64), dy.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64)
+    n = x64.size // c
+    mu = x64.mean((0, 2, 3), keepdims=True)
+    var = x64.var((0, 2, 3), keepdims=True)
+    sd = np.sqrt(var + bn.eps)
+    xh = (x64 - mu) / sd
+    out["y64"] = xh * g64.reshape(1, c, 1, 1) + b64.reshape(1, c, 1, 1)
+    gg = dy64 * g64.reshape(1, c, 1, 1)
+    out["dx64"] = (n * gg - gg.sum((0, 2, 3), keepdims=True) - xh * (gg * xh).sum((0, 2, 3), keepdims=True)) / n / sd
+    out["dgamma64"] = (dy64 * xh).sum((0, 2, 3))
+    out["dbeta64"] = dy64.sum((0, 2, 3))
+    out["rv64"] = 0.9 * 1.0 + 0.1 * var.reshape(-1) * n / (n - 1)
+    out["rm64"] = 0.1 * mu.reshape(-1)
+    out["eps"] = np.array([bn.eps])
+    np.savez_compressed(os.path.join(OUT, "batch_norm_large_mean.npz"), **out)
+    print("batch_norm_large_mean.npz")
+
+
 def gen_relu():
     out = {}
     rng = np.random.default_rng(400)
@@ -379,6 +420,10 @@ def gen_models():
 
 
 if __name__ == "__main__":
+    if "--only-bn-large-mean" in sys.argv:
+        gen_bn_large_mean()
+        sys.exit(0)
+    gen_bn_large_mean()
     gen_models()
     gen_conv()
     gen_convt()

@@ -69,7 +69,10 @@ def init_buffers(params):
 class StepOracle:
     """forward + backward + SGD of the network on numpy arrays (NCHW float32)."""
 
-    def __init__(self, layers, channels, params, buffers=None, momentum_bn=0.1, eps=1e-5):
+    def __init__(self, layers, channels, params, buffers=None, momentum_bn=0.1, eps=1e-5, dtype=np.float32):
+        # dtype: float32 = the reference's arithmetic; float64 (params / inputs given as float64 too) = the same
+        # formulas evaluated in double, used by tests as the "truth" both fp32 implementations are measured against
+        self.dtype = dtype
         self.layers, self.channels = layers, channels
         self.params = params
         self.buffers = init_buffers(params) if buffers is None else buffers
@@ -130,7 +133,7 @@ class StepOracle:
                 cin = ch
         t_head = []
         a = self._bn_relu(h, "bn.", t_head)
-        pooled = a.mean(axis=(-1, -2), keepdims=True, dtype=np.float32)  # tt.mean(x,(-1,-2),True)
+        pooled = a.mean(axis=(-1, -2), keepdims=True, dtype=self.dtype)  # tt.mean(x,(-1,-2),True)
         flat = pooled.reshape(pooled.shape[0], -1)
         w, bfc = self.params["fc.0.weight"], self.params["fc.0.bias"]
         logits = O.linear_forward(flat, w, bfc)
@@ -138,12 +141,12 @@ class StepOracle:
         loss = O.nll_loss_forward(logp, labels)
 
         # ---- backward ----
-        dlogp = O.nll_loss_backward(np.float32(1.0), logp, labels)
+        dlogp = O.nll_loss_backward(self.dtype(1.0), logp, labels)
         dlogits = O.log_softmax_backward(dlogp, logp)
         dflat, dw, db = O.linear_backward(dlogits, flat, w)
-        grads["fc.0.weight"], grads["fc.0.bias"] = dw.astype(np.float32), db.astype(np.float32)
+        grads["fc.0.weight"], grads["fc.0.bias"] = dw.astype(self.dtype), db.astype(self.dtype)
         hw = a.shape[-1] * a.shape[-2]
-        da = np.broadcast_to(dflat.reshape(pooled.shape) / np.float32(hw), a.shape).astype(np.float32)
+        da = np.broadcast_to(dflat.reshape(pooled.shape) / self.dtype(hw), a.shape).astype(self.dtype)
         dh = t_head[0](da, grads)
         for t_act, t_res, t_sc in reversed(blocks):
             d = dh

@@ -10,6 +10,8 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtortto_b200.so")
+if os.environ.get("TORTTO_B200_LIB") == "tuning":  # the -DTTB_TUNING build (experiment knobs), never the default
+    LIB_PATH = os.path.join(HERE, "libtortto_b200_tuning.so")
 
 TTB_MATH_FP32, TTB_MATH_TF32, TTB_MATH_BF16 = 0, 1, 2
 
@@ -44,16 +46,24 @@ _PROTOS = {
     "ttb_conv2d_dgrad_prepacked": (c_int, [POINTER(ConvDesc), _F, _F, _F, c_void_p]),
     "ttb_conv2d_wgrad_partial": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, POINTER(c_int), POINTER(c_void_p), c_void_p]),
     "ttb_sum_splits_multi": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int64), POINTER(c_void_p), c_void_p]),
+    "ttb_conv2d_bf16_supported": (c_int, [POINTER(ConvDesc), c_int]),
+    "ttb_conv2d_workspace_size_bf16": (c_size_t, [POINTER(ConvDesc), c_int]),
+    "ttb_conv2d_fprop_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_void_p]),
+    "ttb_conv2d_dgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, c_void_p]),
+    "ttb_conv2d_wgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_conv2d_pack_weights_bf16": (c_int, [c_int, POINTER(POINTER(ConvDesc)), POINTER(c_void_p), POINTER(c_void_p),
+                                             POINTER(c_void_p), c_void_p]),
+    "ttb_to_bf16": (c_int, [_F, _F, c_int64, c_void_p]),
     "ttb_bn_num_chunks": (c_int, [c_int64, c_int]),
     "ttb_bn_stats": (c_int, [_F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_reduce_partials": (c_int, [_F, c_int, c_int, _F, c_void_p]),
     "ttb_bn_finalize": (c_int, [_F, c_int, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
-    "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, c_int, c_void_p]),
+    "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, _F, c_int, _F, c_void_p]),
     "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_bwd_finalize": (c_int, [_F, c_int, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
-    "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, c_int64, c_int, c_void_p]),
-    "ttb_relu_fwd": (c_int, [_F, _F, c_int64, c_void_p]),
+    "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_void_p]),
+    "ttb_relu_fwd": (c_int, [_F, _F, c_int64, _F, c_void_p]),
     "ttb_relu_bwd": (c_int, [_F, _F, _F, c_int64, c_void_p]),
     "ttb_add": (c_int, [_F, _F, _F, c_int64, c_void_p]),
     "ttb_axpy": (c_int, [c_float, _F, _F, c_int64, c_void_p]),
@@ -62,6 +72,9 @@ _PROTOS = {
     "ttb_sgd_step": (c_int, [_F, _F, _F, c_int64, c_float, c_float, c_float, c_float, c_int, c_int, c_void_p]),
     "ttb_sgd_step_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_float, c_int, c_void_p]),
+    "ttb_adam_advance": (c_int, [_F, c_float, c_float, c_void_p]),
+    "ttb_adam_step_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _F, c_float, c_float,
+                                    c_float, c_float, c_float, c_int, c_void_p]),
     "ttb_comm_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "ttb_comm_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "ttb_comm_close": (c_int, [c_void_p]),

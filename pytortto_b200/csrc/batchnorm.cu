@@ -9,12 +9,15 @@
 // the grid; per-thread fp32 partials over its share of one wave's rows (tens to a few hundred), block tree in shared memory, one double
 // partial per (chunk, channel) written to HBM, and a tiny second kernel sums chunks in double in a FIXED
 // order (deterministic; no atomics).  The [2][C] double sums are what a data-parallel run all-reduces.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "bn_finalize.cuh"
 
 namespace ttb {
 
 constexpr int kBnThreads = 256;
+constexpr int kBnWaveCtas = 8;  // CTAs per SM the column reductions are sized for (measured choice)
 
 struct ColGeom {
   int tx;        // threads along channel quads (power of two <= 256)
@@ -40,7 +43,12 @@ static ColGeom col_geom(int64_t m, int c) {
   // kernel is a chain of dependent load batches per thread, so its latency is (rows per thread / unroll) x DRAM
   // latency - small tensors want many short threads, not few long ones.  At least kMinRowsPerThread rows per thread.
   constexpr int kMinRowsPerThread = 4;
-  int64_t cap = (int64_t)sm_count() * col_reduce_ctas_per_sm() / g.qblocks;
+  // kBnWaveCtas CTAs per SM are enough to saturate HBM (8 x float4 in flight per thread) and keep the partial buffer the
+  // finalize kernel has to sum small: its latency is (chunks / 128) dependent L2 round trips
+  int per_sm = col_reduce_ctas_per_sm();
+  const int want = tuning_knob("TTB_BN_CTAS_PER_SM", kBnWaveCtas);
+  if (want > 0 && want < per_sm) per_sm = want;
+  int64_t cap = (int64_t)sm_count() * per_sm / g.qblocks;
   // ... but keep the partial buffer [chunks][2][C] doubles under ~1 MB so the finalize kernel stays a few microseconds
   const int64_t cap_bytes = (int64_t)(1 << 20) / ((int64_t)2 * c * 8);
   if (cap > cap_bytes) cap = cap_bytes;
@@ -56,14 +64,19 @@ static ColGeom col_geom(int64_t m, int c) {
 }
 
 // MODE 0: s0 = sum(a), s1 = sum(a*a)                          (forward statistics; a = x)
+//         accumulated per thread as sum(a-K), sum((a-K)^2) with K = the channel's value in row 0 of the tensor (the same
+//         K in every CTA) and converted to the unshifted double sums when the block writes its partial: fp32
+//         accumulation of x^2 loses the variance when |mean| >> sd (sum x^2 - n*mean^2 cancels); shifted sums do not,
+//         and the reference is two-pass (xp.mean, xp.var: grad_nn.py:923-924).
 // MODE 1: s0 = sum(g), s1 = sum(g*(b-mean)), g = a or masked  (backward; a = dy, b = x, mask = relu_out > 0)
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
 col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
                   const float* __restrict__ mask, const float* __restrict__ rscale, const float* __restrict__ rshift,
                   int64_t m, int c, int tx_n, int64_t rows_per_chunk, double* __restrict__ partials) {
+  pdl_entry();
   // ReLU mask of the fused BatchNorm+ReLU node: either read (mask = the ReLU output) or RECOMPUTED from x with the
-  // forward pass's own scale / shift (rscale != null): fmaf(x, scale, shift) > 0 is bit-for-bit what forward tested,
+  // forward pass's own mean / scale / beta (rscale != null): fmaf(x - mean, scale, beta) > 0 is bit-for-bit what forward tested,
   // and it saves one of the three reads of this pass
   extern __shared__ float4 sm[];  // [2][ty][tx]
   const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n, ty_n = kBnThreads / tx_n;
@@ -73,6 +86,14 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
   if (ch < c) {
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = mu, rsh = mu;
     const bool recompute = MODE == 1 && rscale != nullptr;
+    if (MODE == 0) {  // mu = the shift K (row 0 of the tensor)
+      if (VEC) {
+        mu = ld_f4(a + ch);
+      } else {
+        float* pm = &mu.x;
+        for (int j = 0; j < 4 && ch + j < c; ++j) pm[j] = a[ch + j];
+      }
+    }
     if (MODE == 1) {
       if (VEC) {
         mu = ld_f4(mean + ch);
@@ -90,13 +111,14 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
     auto accumulate = [&](float4 va, float4 vb, float4 vm) {
       if (MODE == 0) {
+        va.x -= mu.x; va.y -= mu.y; va.z -= mu.z; va.w -= mu.w;
         s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
         s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
         s1.z = fmaf(va.z, va.z, s1.z); s1.w = fmaf(va.w, va.w, s1.w);
       } else {
-        if (recompute) {
-          vm.x = fmaf(vb.x, rsc.x, rsh.x); vm.y = fmaf(vb.y, rsc.y, rsh.y);
-          vm.z = fmaf(vb.z, rsc.z, rsh.z); vm.w = fmaf(vb.w, rsc.w, rsh.w);
+        if (recompute) {  // exactly forward's expression: fmaf(x - mean, scale, beta)
+          vm.x = fmaf(vb.x - mu.x, rsc.x, rsh.x); vm.y = fmaf(vb.y - mu.y, rsc.y, rsh.y);
+          vm.z = fmaf(vb.z - mu.z, rsc.z, rsh.z); vm.w = fmaf(vb.w - mu.w, rsc.w, rsh.w);
         }
         if (masked) {
           va.x = vm.x > 0.f ? va.x : 0.f; va.y = vm.y > 0.f ? va.y : 0.f;
@@ -162,6 +184,17 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
       d1[0] += q.x; d1[1] += q.y; d1[2] += q.z; d1[3] += q.w;
     }
     double* out = partials + (int64_t)blockIdx.y * 2 * c;
+    if (MODE == 0) {  // shifted -> plain sums, in double: sum x = S0 + n K, sum x^2 = S1 + 2 K S0 + n K^2
+      int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+      int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
+      const double nrows = r1 > r0 ? (double)(r1 - r0) : 0.0;
+      for (int j = 0; j < 4 && ch + j < c; ++j) {
+        const double k = (double)a[ch + j];
+        const double t0 = d0[j], t1 = d1[j];
+        d0[j] = t0 + nrows * k;
+        d1[j] = t1 + 2.0 * k * t0 + nrows * k * k;
+      }
+    }
     for (int j = 0; j < 4 && ch + j < c; ++j) {
       out[ch + j] = d0[j];
       out[c + ch + j] = d1[j];
@@ -209,6 +242,7 @@ static int col_reduce_ctas_per_sm() {
 
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int c2, double* __restrict__ sums) {
+  pdl_entry();
   __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double t = chunk_sum(partials, num_chunks, c2, i, i < c2, sm);
@@ -217,6 +251,7 @@ reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int 
 
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnFwdFinalize fin) {
+  pdl_entry();
   __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double s0 = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
@@ -228,19 +263,20 @@ bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, B
 __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const float* __restrict__ var_in, int c,
                                        float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* mean, float* var_eps, float* sd, float* scale, float* shift) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   float mu = mean_in[i];
   float ve = __fadd_rn(var_in[i], eps);
   float s = sqrtf(ve);
   mean[i] = mu; var_eps[i] = ve; sd[i] = s;
-  float sc = (gamma ? gamma[i] : 1.f) / s;
-  scale[i] = sc;
-  shift[i] = (beta ? beta[i] : 0.f) - mu * sc;
+  scale[i] = (gamma ? gamma[i] : 1.f) / s;
+  shift[i] = beta ? beta[i] : 0.f;  // the additive term of y = (x - mean)*scale + beta
 }
 
 __global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnBwdFinalize fin) {
+  pdl_entry();
   __shared__ double sm[kLanes][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   double sdy = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
@@ -249,13 +285,17 @@ bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, int 
   fin(i, sdy, sdyx);
 }
 
-// y = x*scale + shift (+ReLU).  One float4 = 4 channels; channel quad = i % cq.  Two independent float4 streams per
-// thread per iteration (grid-stride, 2x unrolled) keep more loads in flight.
+// y = (x - mean)*scale + beta (+ReLU) - the reference's own order of operations (grad_nn.py:942-959: subtract the mean,
+// divide by sd, times gamma, plus beta) with gamma/sd folded into `scale`; unlike x*scale + (beta - mean*scale) it does
+// not lose digits when |mean| >> sd.  One float4 = 4 channels; channel quad = i % cq.  Two independent float4 streams
+// per thread per iteration (grid-stride, 2x unrolled) keep more loads in flight.  `yh` (may be null): the same values
+// rounded to bf16, co-written for the bf16 tensor-core path (the next convolution reads them instead of converting).
 template <bool RELU>
-__device__ __forceinline__ float4 bn_apply4(float4 v, const float* __restrict__ scale, const float* __restrict__ shift, int q) {
-  float4 sc = ld_f4(scale + 4 * q), sh = ld_f4(shift + 4 * q);
-  v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-  v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+__device__ __forceinline__ float4 bn_apply4(float4 v, const float* __restrict__ mean, const float* __restrict__ scale,
+                                            const float* __restrict__ beta, int q) {
+  float4 mu = ld_f4(mean + 4 * q), sc = ld_f4(scale + 4 * q), sh = ld_f4(beta + 4 * q);
+  v.x = fmaf(v.x - mu.x, sc.x, sh.x); v.y = fmaf(v.y - mu.y, sc.y, sh.y);
+  v.z = fmaf(v.z - mu.z, sc.z, sh.z); v.w = fmaf(v.w - mu.w, sc.w, sh.w);
   if (RELU) {
     v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
     v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
@@ -263,60 +303,76 @@ __device__ __forceinline__ float4 bn_apply4(float4 v, const float* __restrict__ 
   return v;
 }
 
-template <bool RELU>
+template <bool RELU, bool SHADOW>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n4, int cq,
-                const float* __restrict__ scale, const float* __restrict__ shift) {
+bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ yh, int64_t n4, int cq,
+                const float* __restrict__ mean, const float* __restrict__ scale, const float* __restrict__ beta) {
+  pdl_entry();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + stride < n4; i += 2 * stride) {
     float4 a = ld_f4_stream(x + 4 * i), b = ld_f4_stream(x + 4 * (i + stride));
-    a = bn_apply4<RELU>(a, scale, shift, (int)(i % cq));
-    b = bn_apply4<RELU>(b, scale, shift, (int)((i + stride) % cq));
+    a = bn_apply4<RELU>(a, mean, scale, beta, (int)(i % cq));
+    b = bn_apply4<RELU>(b, mean, scale, beta, (int)((i + stride) % cq));
     st_f4(y + 4 * i, a);
     st_f4(y + 4 * (i + stride), b);
+    if (SHADOW) {
+      st_bf16x4(yh + 4 * i, a);
+      st_bf16x4(yh + 4 * (i + stride), b);
+    }
   }
-  for (; i < n4; i += stride) st_f4(y + 4 * i, bn_apply4<RELU>(ld_f4_stream(x + 4 * i), scale, shift, (int)(i % cq)));
+  for (; i < n4; i += stride) {
+    float4 a = bn_apply4<RELU>(ld_f4_stream(x + 4 * i), mean, scale, beta, (int)(i % cq));
+    st_f4(y + 4 * i, a);
+    if (SHADOW) st_bf16x4(yh + 4 * i, a);
+  }
 }
 
 template <bool RELU>
-__global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
-                                       const float* __restrict__ scale, const float* __restrict__ shift) {
+__global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, __nv_bfloat16* __restrict__ yh,
+                                       int64_t n, int c, const float* __restrict__ mean, const float* __restrict__ scale,
+                                       const float* __restrict__ beta) {
+  pdl_entry();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int ch = (int)(i % c);
-    float v = fmaf(x[i], scale[ch], shift[ch]);
+    float v = fmaf(x[i] - mean[ch], scale[ch], beta[ch]);
     if (RELU) v = v < 0.f ? 0.f : v;
     y[i] = v;
+    if (yh) yh[i] = __float2bfloat16_rn(v);
   }
 }
 
 // dx = c1*(g - c2 - (x-mean)*c3) [+ accum], g = dy (masked by relu_out > 0 when given).  `accum`: a gradient that already
 // reached the same tensor through another branch (the residual shortcut) - added here instead of by a separate kernel.
-// MASK: 0 none, 1 read the ReLU output, 2 recompute it from x (fmaf(x, rscale, rshift), see col_reduce_kernel)
-template <int MASK>
+// MASK: 0 none, 1 read the ReLU output, 2 recompute it from x (fmaf(x - mean, rscale, rbeta), see col_reduce_kernel).
+// `dxh` (may be null): dx rounded to bf16, co-written for the bf16 tensor-core path (dgrad / wgrad of the producing
+// convolution read it as dY).
+template <int MASK, bool SHADOW>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ mask, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                    const float* __restrict__ coef, const float* __restrict__ accum, float* __restrict__ dx, int64_t n4,
-                    int cq, int c) {
+                    const float* __restrict__ coef, const float* __restrict__ accum, float* __restrict__ dx,
+                    __nv_bfloat16* __restrict__ dxh, int64_t n4, int cq, int c) {
+  pdl_entry();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int q = (int)(i % cq);
     float4 g = ld_f4_stream(dy + 4 * i), v = ld_f4_stream(x + 4 * i);
+    float4 mu = ld_f4(mean + 4 * q);
     if (MASK) {
       float4 o;
       if (MASK == 1) {
         o = ld_f4_stream(mask + 4 * i);
       } else {
         float4 sc = ld_f4(rscale + 4 * q), sh = ld_f4(rshift + 4 * q);
-        o.x = fmaf(v.x, sc.x, sh.x); o.y = fmaf(v.y, sc.y, sh.y); o.z = fmaf(v.z, sc.z, sh.z); o.w = fmaf(v.w, sc.w, sh.w);
+        o.x = fmaf(v.x - mu.x, sc.x, sh.x); o.y = fmaf(v.y - mu.y, sc.y, sh.y);
+        o.z = fmaf(v.z - mu.z, sc.z, sh.z); o.w = fmaf(v.w - mu.w, sc.w, sh.w);
       }
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
       g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
-    float4 mu = ld_f4(mean + 4 * q), c1 = ld_f4(coef + 4 * q), c2 = ld_f4(coef + c + 4 * q),
-           c3 = ld_f4(coef + 2 * c + 4 * q);
+    float4 c1 = ld_f4(coef + 4 * q), c2 = ld_f4(coef + c + 4 * q), c3 = ld_f4(coef + 2 * c + 4 * q);
     float4 r;
     r.x = c1.x * (g.x - c2.x - (v.x - mu.x) * c3.x);
     r.y = c1.y * (g.y - c2.y - (v.y - mu.y) * c3.y);
@@ -327,6 +383,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
       r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
     }
     st_f4(dx + 4 * i, r);
+    if (SHADOW) st_bf16x4(dxh + 4 * i, r);
   }
 }
 
@@ -335,15 +392,18 @@ __global__ void bn_bwd_apply_scalar_kernel(const float* __restrict__ dy, const f
                                            const float* __restrict__ mean, const float* __restrict__ mask,
                                            const float* __restrict__ rscale, const float* __restrict__ rshift,
                                            const float* __restrict__ coef, const float* __restrict__ accum,
-                                           float* __restrict__ dx, int64_t n, int c) {
+                                           float* __restrict__ dx, __nv_bfloat16* __restrict__ dxh, int64_t n, int c) {
+  pdl_entry();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     int ch = (int)(i % c);
     float g = dy[i];
     if (MASK == 1) g = mask[i] > 0.f ? g : 0.f;
-    if (MASK == 2) g = fmaf(x[i], rscale[ch], rshift[ch]) > 0.f ? g : 0.f;
+    if (MASK == 2) g = fmaf(x[i] - mean[ch], rscale[ch], rshift[ch]) > 0.f ? g : 0.f;
     float r = coef[ch] * (g - coef[c + ch] - (x[i] - mean[ch]) * coef[2 * c + ch]);
-    dx[i] = accum ? r + accum[i] : r;
+    if (accum) r += accum[i];
+    dx[i] = r;
+    if (dxh) dxh[i] = __float2bfloat16_rn(r);
   }
 }
 
@@ -361,9 +421,9 @@ static int launch_col_reduce(const float* a, const float* b, const float* mean, 
   dim3 grid(g.qblocks, g.chunks);
   size_t smem = sizeof(float4) * 2 * kBnThreads;
   if (vec)
-    col_reduce_kernel<MODE, true><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
+    launch_k(col_reduce_kernel<MODE, true>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
   else
-    col_reduce_kernel<MODE, false><<<grid, kBnThreads, smem, st>>>(a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
+    launch_k(col_reduce_kernel<MODE, false>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
   return check_launch(what);
 }
 
@@ -385,7 +445,7 @@ int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chu
 
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
   if (c2 <= 0) return 0;
-  reduce_partials_kernel<<<(c2 + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(partials, num_chunks, c2, sums);
+  launch_k(reduce_partials_kernel, (c2 + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), partials, num_chunks, c2, sums);
   return check_launch("bn_reduce_partials");
 }
 
@@ -401,7 +461,7 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
   bn_fwd_host_factors(count, momentum, &fin.unbias, &fin.one_minus_momentum);
   fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
   fin.mean = mean; fin.var_eps = var_eps; fin.sd = sd; fin.scale = scale; fin.shift = shift;
-  bn_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
+  launch_k(bn_finalize_kernel, (c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_finalize");
 }
 
@@ -409,24 +469,30 @@ int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float 
                         const float* beta, float* mean, float* var_eps, float* sd, float* scale, float* shift,
                         void* stream) {
   if (c <= 0) return 0;
-  bn_prepare_eval_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(mean_in, var_in, c, eps, gamma, beta, mean,
+  launch_k(bn_prepare_eval_kernel, (c + 127) / 128, 128, 0, as_stream(stream), mean_in, var_in, c, eps, gamma, beta, mean,
                                                                          var_eps, sd, scale, shift);
   return check_launch("bn_prepare_eval");
 }
 
-int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* scale, const float* shift, int relu,
-                 void* stream) {
+int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* mean, const float* scale, const float* beta,
+                 int relu, void* y_bf16, void* stream) {
   int64_t n = m * c;
   if (n <= 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (c % 4 == 0 && a16(x) && a16(y) && a16(scale) && a16(shift)) {
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  if (c % 4 == 0 && a16(x) && a16(y) && a16(mean) && a16(scale) && a16(beta) && (reinterpret_cast<uintptr_t>(yh) & 7) == 0) {
     int grid = elementwise_grid(n / 4, 256);
-    if (relu) bn_apply_kernel<true><<<grid, 256, 0, st>>>(x, y, n / 4, c / 4, scale, shift);
-    else bn_apply_kernel<false><<<grid, 256, 0, st>>>(x, y, n / 4, c / 4, scale, shift);
+    if (relu) {
+      if (yh) launch_k(bn_apply_kernel<true, true>, grid, 256, 0, st, x, y, yh, n / 4, c / 4, mean, scale, beta);
+      else launch_k(bn_apply_kernel<true, false>, grid, 256, 0, st, x, y, yh, n / 4, c / 4, mean, scale, beta);
+    } else {
+      if (yh) launch_k(bn_apply_kernel<false, true>, grid, 256, 0, st, x, y, yh, n / 4, c / 4, mean, scale, beta);
+      else launch_k(bn_apply_kernel<false, false>, grid, 256, 0, st, x, y, yh, n / 4, c / 4, mean, scale, beta);
+    }
   } else {
     int grid = elementwise_grid(n, 256);
-    if (relu) bn_apply_scalar_kernel<true><<<grid, 256, 0, st>>>(x, y, n, c, scale, shift);
-    else bn_apply_scalar_kernel<false><<<grid, 256, 0, st>>>(x, y, n, c, scale, shift);
+    if (relu) launch_k(bn_apply_scalar_kernel<true>, grid, 256, 0, st, x, y, yh, n, c, mean, scale, beta);
+    else launch_k(bn_apply_scalar_kernel<false>, grid, 256, 0, st, x, y, yh, n, c, mean, scale, beta);
   }
   return check_launch("bn_apply");
 }
@@ -445,13 +511,13 @@ int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c
   fin.count = (double)count;
   fin.c = c;
   fin.gamma = gamma; fin.var_eps = var_eps; fin.sd = sd; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.coef = coef;
-  bn_bwd_finalize_kernel<<<(c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream)>>>(sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
+  launch_k(bn_bwd_finalize_kernel, (c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_bwd_finalize");
 }
 
 int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,
                      const float* relu_shift, const float* coef, const float* accum, float* dx, int64_t m, int c,
-                     void* stream) {
+                     void* dx_bf16, void* stream) {
   int64_t n = m * c;
   if (n <= 0) return 0;
   TTB_REQUIRE(!(relu_out && relu_scale) && (!relu_scale == !relu_shift), "bn_bwd_apply: give relu_out OR relu_scale+relu_shift");
@@ -459,16 +525,27 @@ int ttb_bn_bwd_apply(const float* dy, const float* x, const float* mean, const f
   bool vec = c % 4 == 0 && a16(dy) && a16(x) && a16(dx) && a16(mean) && a16(coef) && (!relu_out || a16(relu_out)) &&
              (!accum || a16(accum)) && (!relu_scale || (a16(relu_scale) && a16(relu_shift)));
   const int mode = relu_out ? 1 : (relu_scale ? 2 : 0);
-  if (vec) {
+  __nv_bfloat16* dxh = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+  if (vec && (reinterpret_cast<uintptr_t>(dxh) & 7) == 0) {
     int grid = elementwise_grid(n / 4, 256);
-    if (mode == 1) bn_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
-    else if (mode == 2) bn_bwd_apply_kernel<2><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
-    else bn_bwd_apply_kernel<0><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n / 4, c / 4, c);
+#define TTB_BWD_APPLY(MASK)                                                                                             \
+  do {                                                                                                                  \
+    if (dxh)                                                                                                            \
+      launch_k(bn_bwd_apply_kernel<MASK, true>, grid, 256, 0, st, dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, \
+                                                            dxh, n / 4, c / 4, c);                                      \
+    else                                                                                                                \
+      launch_k(bn_bwd_apply_kernel<MASK, false>, grid, 256, 0, st, dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, \
+                                                             dx, dxh, n / 4, c / 4, c);                                 \
+  } while (0)
+    if (mode == 1) TTB_BWD_APPLY(1);
+    else if (mode == 2) TTB_BWD_APPLY(2);
+    else TTB_BWD_APPLY(0);
+#undef TTB_BWD_APPLY
   } else {
     int grid = elementwise_grid(n, 256);
-    if (mode == 1) bn_bwd_apply_scalar_kernel<1><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
-    else if (mode == 2) bn_bwd_apply_scalar_kernel<2><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
-    else bn_bwd_apply_scalar_kernel<0><<<grid, 256, 0, st>>>(dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, n, c);
+    if (mode == 1) launch_k(bn_bwd_apply_scalar_kernel<1>, grid, 256, 0, st, dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, dxh, n, c);
+    else if (mode == 2) launch_k(bn_bwd_apply_scalar_kernel<2>, grid, 256, 0, st, dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, dxh, n, c);
+    else launch_k(bn_bwd_apply_scalar_kernel<0>, grid, 256, 0, st, dy, x, mean, relu_out, relu_scale, relu_shift, coef, accum, dx, dxh, n, c);
   }
   return check_launch("bn_bwd_apply");
 }

@@ -28,9 +28,8 @@ struct BnFwdFinalize {  // inputs: s0 = sum(x), s1 = sum(x*x) over `count` eleme
     var_eps[i] = ve;
     sd[i] = s;
     float g = gamma ? gamma[i] : 1.f;
-    float sc = g / s;
-    scale[i] = sc;
-    shift[i] = (beta ? beta[i] : 0.f) - muf * sc;
+    scale[i] = g / s;
+    shift[i] = beta ? beta[i] : 0.f;  // the additive term of y = (x - mean)*scale + beta (the kernels centre x first)
   }
 };
 

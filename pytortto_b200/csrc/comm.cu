@@ -50,6 +50,7 @@ constexpr int kMaxWorld = 16;
 __global__ void __launch_bounds__(1024)
 comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n, char* const* __restrict__ peers,
                       int world, int rank, size_t slot_offset, double* __restrict__ out, unsigned long long spin_limit) {
+  pdl_entry();
   __shared__ double sm[32][33];
   char* own = peers[rank] + slot_offset;
   SlotHeader* hdr = reinterpret_cast<SlotHeader*>(own);
@@ -132,6 +133,7 @@ template <class Finalize>
 __global__ void __launch_bounds__(1024)
 comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, char* const* __restrict__ peers, int world,
                         int rank, size_t slot_offset, unsigned long long spin_limit, Finalize fin) {
+  pdl_entry();
   __shared__ double sm0[32][33], sm1[32][33];
   __shared__ double mine_sm[2][32];
   char* own = peers[rank] + slot_offset;
@@ -285,7 +287,7 @@ int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* cons
   TTB_REQUIRE(world > 0 && world <= kMaxWorld && rank >= 0 && rank < world, "comm_allreduce: world size %d not in 1..%d", world,
               kMaxWorld);
   // about a minute of polling before a missing peer is declared lost
-  comm_allreduce_kernel<<<(n + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+  launch_k(comm_allreduce_kernel, (n + 31) / 32, dim3(32, 32), 0, as_stream(stream), 
       partials, num_chunks, n, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, out, 200000000ull);
   return check_launch("comm_allreduce");
 }
@@ -310,7 +312,7 @@ int ttb_comm_bn_finalize(const double* partials, int num_chunks, void* const* pe
   bn_fwd_host_factors(count, momentum, &fin.unbias, &fin.one_minus_momentum);
   fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
   fin.mean = mean; fin.var_eps = var_eps; fin.sd = sd; fin.scale = scale; fin.shift = shift;
-  comm_bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+  launch_k(comm_bn_finalize_kernel<BnFwdFinalize>, (c + 31) / 32, dim3(32, 32), 0, as_stream(stream), 
       partials, num_chunks, c, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, 200000000ull, fin);
   return check_launch("comm_bn_finalize");
 }
@@ -324,7 +326,7 @@ int ttb_comm_bn_bwd_finalize(const double* partials, int num_chunks, void* const
   fin.count = (double)count;
   fin.c = c;
   fin.gamma = gamma; fin.var_eps = var_eps; fin.sd = sd; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.coef = coef;
-  comm_bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(
+  launch_k(comm_bn_finalize_kernel<BnBwdFinalize>, (c + 31) / 32, dim3(32, 32), 0, as_stream(stream), 
       partials, num_chunks, c, reinterpret_cast<char* const*>(peers_dev), world, rank, slot_offset, 200000000ull, fin);
   return check_launch("comm_bn_bwd_finalize");
 }

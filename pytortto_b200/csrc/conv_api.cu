@@ -38,11 +38,14 @@ int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const
                              cudaStream_t st);
 int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
                            float* const* outs, cudaStream_t st);
+int igemm_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
+                            void* const* wt_bf16, cudaStream_t st);
 
 // [rows][c] fp32 -> [rows][cp] OutT (zero-filled channels c..cp-1); 4 output channels per thread
 template <class OutT>
 __global__ void __launch_bounds__(256)
 stage_channels_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int64_t rows, int c, int cp) {
+  pdl_entry();
   const int q = cp / 4;
   const int64_t total = rows * q;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -74,6 +77,7 @@ stage_channels_kernel(const float* __restrict__ src, OutT* __restrict__ dst, int
 
 __global__ void __launch_bounds__(256)
 unpad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int c, int cp) {
+  pdl_entry();
   int64_t total = rows * c;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -88,8 +92,8 @@ static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 static int stage(const float* src, void* dst, int64_t rows, int c, int cp, bool bf16, cudaStream_t st) {
   if (rows <= 0) return 0;
   int grid = elementwise_grid(rows * (cp / 4), 256);
-  if (bf16) stage_channels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, c, cp);
-  else stage_channels_kernel<float><<<grid, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), rows, c, cp);
+  if (bf16) launch_k(stage_channels_kernel<__nv_bfloat16>, grid, 256, 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), rows, c, cp);
+  else launch_k(stage_channels_kernel<float>, grid, 256, 0, st, src, reinterpret_cast<float*>(dst), rows, c, cp);
   return check_launch("stage_channels");
 }
 
@@ -223,7 +227,7 @@ int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, fl
   if (int rc = igemm_dgrad(&t.p, dya, wa, dxa, ws + t.a_bytes + t.b_bytes + t.c_bytes, t.inner, st)) return rc;
   if (t.c_bytes) {
     const int64_t xrows = (int64_t)d->n * d->h * d->w;
-    unpad_channels_kernel<<<elementwise_grid(xrows * d->c, 256), 256, 0, st>>>(dxa, dx, xrows, d->c, t.p.c);
+    launch_k(unpad_channels_kernel, elementwise_grid(xrows * d->c, 256), 256, 0, st, dxa, dx, xrows, d->c, t.p.c);
     return check_launch("unpad_channels");
   }
   return 0;
@@ -253,7 +257,7 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
   if (int rc = igemm_wgrad(&t.p, xa, dya, dwa, ws ? ws + t.a_bytes + t.b_bytes + t.c_bytes : nullptr, t.inner, st)) return rc;
   if (t.c_bytes) {
     const int64_t wrows = (int64_t)d->k * d->r * d->s;
-    unpad_channels_kernel<<<elementwise_grid(wrows * d->c, 256), 256, 0, st>>>(dwa, dw, wrows, d->c, t.p.c);
+    launch_k(unpad_channels_kernel, elementwise_grid(wrows * d->c, 256), 256, 0, st, dwa, dw, wrows, d->c, t.p.c);
     return check_launch("unpad_channels");
   }
   return 0;
@@ -308,6 +312,62 @@ int ttb_sum_splits_multi(int count, const float* const* partials, const int* spl
                          float* const* outs, void* stream) {
   TTB_REQUIRE(count >= 0 && (count == 0 || (partials && splits && sizes && outs)), "sum_splits_multi: bad arguments");
   return igemm_sum_splits_multi(count, partials, splits, sizes, outs, as_stream(stream));
+}
+
+/* ---- bf16-operand forms: operands are ALREADY bf16 in HBM (co-written by the producing kernel or ttb_to_bf16), so
+ * a call is exactly one implicit-GEMM launch - no staging pass.  Outputs and accumulation stay fp32. ---- */
+
+/* 1 if the pass can take bf16 operands as they are: TTB_MATH_BF16, groups == 1, reduction channels in whole 64-channel
+ * K-blocks (fprop / wgrad: C % 64 == 0; dgrad: K % 64 == 0, C % 8 == 0) */
+int ttb_conv2d_bf16_supported(const ttb_conv_desc* d, int pass) {
+  if (!d || d->math_mode != TTB_MATH_BF16) return 0;
+  TensorPlan t;
+  if (!plan_tensor(d, pass, &t)) return 0;
+  return (t.p.c == d->c && t.p.k == d->k) ? 1 : 0;
+}
+
+size_t ttb_conv2d_workspace_size_bf16(const ttb_conv_desc* d, int pass) {
+  if (!ttb_conv2d_bf16_supported(d, pass)) return 0;
+  return pass == 2 ? align256(igemm_workspace_size(d, 2)) : 0;
+}
+
+int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const float* bias, float* y,
+                          void* stream) {
+  if (int rc = validate(d, "conv2d_fprop_bf16")) return rc;
+  TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 0), "conv2d_fprop_bf16: problem needs the staged path (ttb_conv2d_fprop)");
+  return igemm_fprop(d, x_bf16, w_bf16, bias, y, nullptr, 0, as_stream(stream));
+}
+
+int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, float* dx, void* stream) {
+  if (int rc = validate(d, "conv2d_dgrad_bf16")) return rc;
+  TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 1), "conv2d_dgrad_bf16: problem needs the staged path (ttb_conv2d_dgrad)");
+  return igemm_dgrad(d, dy_bf16, nullptr, dx, nullptr, 0, as_stream(stream), w_packed_bf16);
+}
+
+int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (int rc = validate(d, "conv2d_wgrad_bf16")) return rc;
+  TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 2), "conv2d_wgrad_bf16: problem needs the staged path (ttb_conv2d_wgrad)");
+  const size_t need = align256(igemm_workspace_size(d, 2));
+  TTB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
+              "conv2d_wgrad_bf16: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+  return igemm_wgrad(d, x_bf16, dy_bf16, dw, workspace, need, as_stream(stream));
+}
+
+/* w[i] fp32 [K][R][S][C]  ->  w_bf16[i] (same order, may be null) and wt_bf16[i] ([C][R][S][K], may be null): the
+ * fprop and dgrad operands of every conv layer of a step in ONE launch (weights change once per optimizer step) */
+int ttb_conv2d_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
+                                 void* const* wt_bf16, void* stream) {
+  TTB_REQUIRE(count >= 0 && (count == 0 || (descs && w && w_bf16 && wt_bf16)), "pack_weights_bf16: bad arguments");
+  return igemm_pack_weights_bf16(count, descs, w, w_bf16, wt_bf16, as_stream(stream));
+}
+
+/* dst[i] = bf16(src[i]) (round to nearest even) */
+int ttb_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  TTB_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+              "to_bf16: needs a multiple of 4 elements and aligned buffers");
+  return stage(src, dst, n / 4, 4, 4, true, as_stream(stream));
 }
 
 /* diagnostics: device buffer (>= 1100 int64) that CTA (0,0) of every following fprop igemm launch fills with

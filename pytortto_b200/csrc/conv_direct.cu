@@ -18,6 +18,7 @@ namespace ttb {
 __global__ void __launch_bounds__(256)
 direct_fprop_kernel(ttb_conv_desc d, const float* __restrict__ x, const float* __restrict__ w,
                     const float* __restrict__ bias, float* __restrict__ y, int64_t total) {
+  pdl_entry();
   const int cg = d.c / d.groups, kg = d.k / d.groups;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -53,6 +54,7 @@ direct_fprop_kernel(ttb_conv_desc d, const float* __restrict__ x, const float* _
 __global__ void __launch_bounds__(256)
 direct_dgrad_kernel(ttb_conv_desc d, const float* __restrict__ dy, const float* __restrict__ w,
                     float* __restrict__ dx, int64_t total) {
+  pdl_entry();
   const int cg = d.c / d.groups, kg = d.k / d.groups;
   const int64_t wstride_k = (int64_t)d.r * d.s * cg;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -91,6 +93,7 @@ direct_dgrad_kernel(ttb_conv_desc d, const float* __restrict__ dy, const float* 
 __global__ void __launch_bounds__(256)
 direct_wgrad_kernel(ttb_conv_desc d, const float* __restrict__ x, const float* __restrict__ dy,
                     float* __restrict__ partial, int64_t wsize, int64_t pixels_per_chunk) {
+  pdl_entry();
   const int cg = d.c / d.groups, kg = d.k / d.groups;
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= wsize) return;
@@ -120,6 +123,7 @@ direct_wgrad_kernel(ttb_conv_desc d, const float* __restrict__ x, const float* _
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int64_t wsize,
                                     float* __restrict__ dw) {
+  pdl_entry();
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= wsize) return;
   float acc = 0.f;
@@ -130,6 +134,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunk
 // column sum of dy[M][K] -> db[K]: block (32 x 8) tiles, fixed-order partials through the same reduce kernel
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dy, int64_t m, int k, int64_t rows_per_chunk, float* __restrict__ partial) {
+  pdl_entry();
   __shared__ float sm[8][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int col = blockIdx.x * 32 + tx;
@@ -168,14 +173,14 @@ int direct_fprop(const ttb_conv_desc* d, const float* x, const float* w, const f
                  cudaStream_t st) {
   int64_t total = (int64_t)d->n * d->p * d->q * d->k;
   if (total <= 0) return 0;
-  direct_fprop_kernel<<<elementwise_grid(total, 256, 16), 256, 0, st>>>(*d, x, w, bias, y, total);
+  launch_k(direct_fprop_kernel, elementwise_grid(total, 256, 16), 256, 0, st, *d, x, w, bias, y, total);
   return check_launch("conv2d_fprop(direct)");
 }
 
 int direct_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st) {
   int64_t total = (int64_t)d->n * d->h * d->w * d->c;
   if (total <= 0) return 0;
-  direct_dgrad_kernel<<<elementwise_grid(total, 256, 16), 256, 0, st>>>(*d, dy, w, dx, total);
+  launch_k(direct_dgrad_kernel, elementwise_grid(total, 256, 16), 256, 0, st, *d, dy, w, dx, total);
   return check_launch("conv2d_dgrad(direct)");
 }
 
@@ -190,9 +195,9 @@ int direct_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float*
   int64_t m_total = (int64_t)d->n * d->p * d->q;
   int64_t ppc = ceil_div(m_total > 0 ? m_total : 1, chunks);
   dim3 grid((unsigned)ceil_div(wsize, 256), chunks);
-  direct_wgrad_kernel<<<grid, 256, 0, st>>>(*d, x, dy, (float*)ws, wsize, ppc);
+  launch_k(direct_wgrad_kernel, grid, 256, 0, st, *d, x, dy, (float*)ws, wsize, ppc);
   if (check_launch("conv2d_wgrad(direct)")) return 1;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(wsize, 256), 256, 0, st>>>((const float*)ws, chunks, wsize, dw);
+  launch_k(wgrad_reduce_kernel, (unsigned)ceil_div(wsize, 256), 256, 0, st, (const float*)ws, chunks, wsize, dw);
   return check_launch("conv2d_wgrad(direct reduce)");
 }
 
@@ -214,7 +219,7 @@ extern "C" int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void*
   chunks = (int)ceil_div(m > 0 ? m : 1, rpc);
   float* partial = nullptr;
   if (chunks == 1) {
-    colsum_kernel<<<dim3((k + 31) / 32, 1), 256, 0, st>>>(dy, m, k, rpc, db);
+    launch_k(colsum_kernel, dim3((k + 31) / 32, 1), 256, 0, st, dy, m, k, rpc, db);
     return check_launch("bias_grad");
   }
   cudaError_t e = cudaMallocAsync((void**)&partial, (size_t)chunks * k * sizeof(float), st);
@@ -222,10 +227,10 @@ extern "C" int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void*
     set_error("bias_grad: cudaMallocAsync failed: %s", cudaGetErrorString(e));
     return 1;
   }
-  colsum_kernel<<<dim3((k + 31) / 32, chunks), 256, 0, st>>>(dy, m, k, rpc, partial);
+  launch_k(colsum_kernel, dim3((k + 31) / 32, chunks), 256, 0, st, dy, m, k, rpc, partial);
   int rc = check_launch("bias_grad");
   if (!rc) {
-    wgrad_reduce_kernel<<<(k + 255) / 256, 256, 0, st>>>(partial, chunks, k, db);
+    launch_k(wgrad_reduce_kernel, (k + 255) / 256, 256, 0, st, partial, chunks, k, db);
     rc = check_launch("bias_grad(reduce)");
   }
   cudaFreeAsync(partial, st);

@@ -99,6 +99,7 @@ __device__ __forceinline__ void flat_epilogue(uint32_t tmem_acc, float* stage_sm
 template <int BN, int NB>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 igemm_flat_kernel(const __grid_constant__ FlatParams P) {
+  pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   static_assert(NB % kFlatBProducers == 0, "a weight stage must always be filled by the same producer");
   constexpr uint32_t kBBytes = BN * 128;
   constexpr int kAccCols = BN < 32 ? 32 : BN;
@@ -151,6 +152,7 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== strip producer: padded input rows, one TMA box per (slab, padded row) =====================
@@ -312,18 +314,14 @@ int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) 
   const int64_t tiles = ceil_div(P.m_flat, kFlatTileM) * ceil_div(P.k_out, BN);
   const int sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  igemm_flat_kernel<BN, NB><<<grid, kFlatThreads, smem, st>>>(P);
+  launch_k(igemm_flat_kernel<BN, NB>, grid, kFlatThreads, smem, st, P);
   return check_launch("igemm_flat_kernel");
 }
 
 }  // namespace
 
 static bool flat_enabled() {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("TTB_FLAT");
-    enabled = e ? atoi(e) : 0;
-  }
+  static const int enabled = tuning_knob("TTB_FLAT", 0);
   return enabled != 0;
 }
 

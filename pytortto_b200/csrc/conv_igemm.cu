@@ -19,6 +19,7 @@
 // and one pixel range per CTA (igemm_wgrad_kernel).  Producer and MMA loops run warp-uniform with the asynchronous
 // instruction under elect.sync - from an `if (lane == 0)` branch ptxas wraps each one in a divergence waterfall.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -248,6 +249,7 @@ constexpr int kEpilogueStagingBytes = 4 * 32 * kStagePitch * 4;
 template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
 __global__ void __launch_bounds__((NPROD + 5) * 32, 1)
 igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
+  pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   static_assert(NSTAGES % NPROD == 0, "a stage must always be filled by the same producer thread");
   constexpr int kElems = BF16 ? 64 : 32;
   constexpr uint32_t kABytes = kTileM * 128;
@@ -273,7 +275,6 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
   int tiles_total = 0;
   for (int c = 0; c < count; ++c) tiles_total += ((PM.p[c].o.m_total + kTileM - 1) / kTileM) * nt;
   long long* const tr = (PM.p[0].trace && blockIdx.x == 0) ? PM.p[0].trace : nullptr;
-  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0 && ptx::elect_one())
     for (int c = 0; c < count; ++c) {
@@ -299,6 +300,7 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // barriers, TMEM and tensor-map prefetch above overlapped the previous kernel's tail; global memory from here on
   if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   // tile index -> problem, first row, first column
@@ -430,6 +432,7 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
 template <int BN, int KP, int NSTAGES, bool BF16>
 __global__ void __launch_bounds__(kThreadsIgemm)
 igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   constexpr int kSlabCh = BF16 ? 64 : 32;            // channels per 128-byte-wide MN slab
   constexpr int kASlabs = kTileM / kSlabCh;          // 128 output channels
   constexpr int kMmaRows = BF16 ? 16 : 8;            // pixels (K) consumed per MMA
@@ -477,6 +480,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // (see igemm_fwd_persist_kernel)
 
   if (warp == 0) {
     {  // whole warp runs the loop; one elected lane issues (no divergence waterfall around the TMA instructions)
@@ -576,6 +580,7 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
 // w[K][T][C] -> wt[C][T][K]   (T = R*S taps)
 template <class T_>
 __global__ void repack_krsc_to_crsk_kernel(const T_* __restrict__ w, T_* __restrict__ wt, int K, int T, int C) {
+  pdl_entry();
   int64_t total = (int64_t)K * T * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
@@ -588,6 +593,7 @@ __global__ void repack_krsc_to_crsk_kernel(const T_* __restrict__ w, T_* __restr
 }
 
 __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits, int64_t n, float* __restrict__ out) {
+  pdl_entry();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
     float acc = 0.f;
@@ -620,6 +626,7 @@ struct SumBatch {
 // work unit = one 32 x 32 (k, c) tile of one filter tap, transposed through shared memory so that both the read
 // (c contiguous in [K][T][C]) and the write (k contiguous in [C][T][K]) are coalesced; start[i] = first tile of tensor i
 __global__ void __launch_bounds__(256) repack_multi_kernel(const __grid_constant__ RepackBatch B) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int tiles = B.start[B.count];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -650,7 +657,60 @@ __global__ void __launch_bounds__(256) repack_multi_kernel(const __grid_constant
   }
 }
 
+// the same tiling, bf16 outputs: the straight copy (fprop's B operand, [K][T][C]) and the transposed copy (dgrad's,
+// [C][T][K]) of one fp32 tile; either destination may be null
+struct PackBf16Batch {
+  const float* w[kMaxBatch];
+  __nv_bfloat16* wh[kMaxBatch];
+  __nv_bfloat16* wth[kMaxBatch];
+  int K[kMaxBatch], T[kMaxBatch], C[kMaxBatch];
+  int start[kMaxBatch + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) pack_bf16_multi_kernel(const __grid_constant__ PackBf16Batch B) {
+  pdl_entry();
+  __shared__ float tile[32][33];
+  const int tiles = B.start[B.count];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int u = blockIdx.x; u < tiles; u += gridDim.x) {
+    int i = 0;
+    while (i + 1 < B.count && u >= B.start[i + 1]) ++i;
+    const int K = B.K[i], T = B.T[i], C = B.C[i];
+    const int kt = (K + 31) / 32, ct = (C + 31) / 32;
+    int v = u - B.start[i];
+    const int c0 = (v % ct) * 32;
+    v /= ct;
+    const int k0 = (v % kt) * 32;
+    const int t = v / kt;
+    const float* __restrict__ w = B.w[i];
+    __nv_bfloat16* __restrict__ wh = B.wh[i];
+    __nv_bfloat16* __restrict__ wth = B.wth[i];
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int k = k0 + r, c = c0 + tx;
+      float val = 0.f;
+      if (k < K && c < C) {
+        const int64_t e = ((int64_t)k * T + t) * C + c;
+        val = w[e];
+        if (wh) wh[e] = __float2bfloat16_rn(val);
+      }
+      tile[r][tx] = val;
+    }
+    __syncthreads();
+    if (wth) {
+#pragma unroll
+      for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, k = k0 + tx;
+        if (c < C && k < K) wth[((int64_t)c * T + t) * K + k] = __float2bfloat16_rn(tile[tx][r]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(256) sum_splits_multi_kernel(const __grid_constant__ SumBatch B) {
+  pdl_entry();
   const int chunks = B.start[B.count];
   for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
     int i = 0;
@@ -710,8 +770,7 @@ bool igemm_supported(const ttb_conv_desc* d, int pass) {
 
 // Widest N tile that still gives every SM a CTA; narrow channel counts get a matching narrow tile.
 static int pick_bn(int64_t m_total, int n_total) {
-  if (const char* e = getenv("TTB_FORCE_BN")) {  // experiment switch
-    const int v = atoi(e);
+  if (const int v = tuning_knob("TTB_FORCE_BN", 0)) {  // experiment switch (tuning build only)
     if (v == 256 && n_total > 128) return 256;
     if (v >= 128 && n_total > 64) return 128;
     if (v >= 64 && n_total > 32) return 64;
@@ -746,9 +805,9 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
   // narrow tiles leave room for two CTAs per SM (two independent MMA-issue streams: a 64-column K-block is 128
   // tensor-core cycles but ~300 cycles of issue-side latency per CTA)
   int sms = sm_count() * (smem <= 113 * 1024 ? 2 : 1);
-  if (const char* e = getenv("TTB_PERSIST_GRID")) sms = atoi(e);  // experiment switch: cap the number of CTAs
+  sms = tuning_knob("TTB_PERSIST_GRID", sms);  // experiment switch (tuning build only): cap the number of CTAs
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16><<<grid, (NPROD + 5) * 32, smem, st>>>(PM, count);
+  launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16>, grid, (NPROD + 5) * 32, smem, st, PM, count);
   return check_launch("igemm_fwd_persist_kernel");
 }
 
@@ -759,11 +818,7 @@ static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool b
   // tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
   // Two K-blocks per stage (KPS = 2) halve the hand-shakes but the 3-stage ring that fits then hides less latency:
   // measured slower (layer 2: 40.8 vs 38.2 us), kept instantiable for experiments (TTB_KPS2=1).
-  static int kps2 = -1;
-  if (kps2 < 0) {
-    const char* e = getenv("TTB_KPS2");
-    kps2 = e ? atoi(e) : 0;
-  }
+  static const int kps2 = tuning_knob("TTB_KPS2", 0);
   if (bf16) {
     switch (bn) {
       case 256: return launch_persist<256, 4, 2, 1, true>(PM, count, st);
@@ -780,9 +835,9 @@ static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool b
   }
 }
 
-static int wgrad_variant() {  // bring-up / tuning knob: 0 = default
-  const char* e = getenv("TTB_WGRAD_VARIANT");
-  return e ? atoi(e) : 0;
+static int wgrad_variant() {  // bring-up / tuning knob (tuning build only): 0 = default
+  static const int v = tuning_knob("TTB_WGRAD_VARIANT", 0);
+  return v;
 }
 
 static int wgrad_plan(const ttb_conv_desc* d, int* bn, int* splits, int* steps_per_split, int* steps_total) {
@@ -831,12 +886,8 @@ size_t igemm_workspace_size(const ttb_conv_desc* d, int pass) {
 static long long* g_trace = nullptr;
 void igemm_set_trace(long long* p) { g_trace = p; }
 
-static int igemm_dbg() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TTB_IGEMM_DBG");
-    v = e ? atoi(e) : 0;
-  }
+static int igemm_dbg() {  // timing experiments that produce WRONG results: tuning build only, 0 in the release library
+  static const int v = tuning_knob("TTB_IGEMM_DBG", 0);
   return v;
 }
 
@@ -895,10 +946,10 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
   if (!prepacked) {
     int64_t total = (int64_t)d->k * T * d->c;
     if (el.bf16)
-      repack_krsc_to_crsk_kernel<uint16_t><<<elementwise_grid(total, 256), 256, 0, st>>>(
+      launch_k(repack_krsc_to_crsk_kernel<uint16_t>, elementwise_grid(total, 256), 256, 0, st, 
           reinterpret_cast<const uint16_t*>(w), reinterpret_cast<uint16_t*>(ws), d->k, T, d->c);
     else
-      repack_krsc_to_crsk_kernel<float><<<elementwise_grid(total, 256), 256, 0, st>>>(
+      launch_k(repack_krsc_to_crsk_kernel<float>, elementwise_grid(total, 256), 256, 0, st, 
           reinterpret_cast<const float*>(w), reinterpret_cast<float*>(ws), d->k, T, d->c);
     if (check_launch("repack_krsc_to_crsk")) return 1;
   }
@@ -1010,7 +1061,7 @@ static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits
     attr_set = true;
   }
   dim3 grid(ktiles, ntiles, splits);
-  igemm_wgrad_kernel<BN, KP, NSTAGES, BF16><<<grid, kThreadsIgemm, smem, st>>>(P);
+  launch_k(igemm_wgrad_kernel<BN, KP, NSTAGES, BF16>, grid, kThreadsIgemm, smem, st, P);
   return check_launch("igemm_wgrad_kernel");
 }
 
@@ -1031,23 +1082,22 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
   const int64_t m = (int64_t)d->n * d->p * d->q;
   // MN-major operands.  fp32: 128B-span / 32B-atom swizzle (TMA) <-> UMMA layout type 1, 4-row K groups 512 B apart.
   // bf16: plain 128B swizzle <-> layout type 2, 8-row K groups 1024 B apart.  128-byte-wide slabs KP*128 B apart.
-  // (TTB_WGRAD_* env overrides exist for bring-up experiments only.)
+  // (TTB_WGRAD_* overrides exist in the tuning build only.)
   CUtensorMapSwizzle swz = el.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   P.desc_lbo = (uint32_t)KP * 128;
   P.desc_sbo = el.bf16 ? 1024 : 512;
   P.desc_layout = el.bf16 ? 2 : 1;
-  if (const char* e = getenv("TTB_WGRAD_SWIZZLE")) swz = (CUtensorMapSwizzle)atoi(e);
-  if (const char* e = getenv("TTB_WGRAD_LBO")) P.desc_lbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("TTB_WGRAD_SBO")) P.desc_sbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("TTB_WGRAD_LAYOUT")) P.desc_layout = (uint32_t)atoi(e);
+  swz = (CUtensorMapSwizzle)tuning_knob("TTB_WGRAD_SWIZZLE", (int)swz);
+  P.desc_lbo = (uint32_t)tuning_knob("TTB_WGRAD_LBO", (int)P.desc_lbo);
+  P.desc_sbo = (uint32_t)tuning_knob("TTB_WGRAD_SBO", (int)P.desc_sbo);
+  P.desc_layout = (uint32_t)tuning_knob("TTB_WGRAD_LAYOUT", (int)P.desc_layout);
   const int ncols = d->r * d->s * d->c;
   // Rectangular fast path: when the KP output pixels of a step are a box of the (n, p, q) grid and taps / N tiles
   // nest, every tap's channel slabs arrive in ONE 5-D tiled load and dY's slabs in ONE 3-D load.
   const int slab = el.per_row;
   int bw = 0, bh = 0, bnimg = 0;
   {
-    const char* e = getenv("TTB_WGRAD_RECT");
-    bool ok = !(e && atoi(e) == 0) && d->k % slab == 0 && (d->c % bn == 0 || bn % d->c == 0) && m % KP == 0;
+    bool ok = tuning_knob("TTB_WGRAD_RECT", 1) != 0 && d->k % slab == 0 && (d->c % bn == 0 || bn % d->c == 0) && m % KP == 0;
     if (ok) {
       if (d->q >= KP) {
         ok = d->q % KP == 0;
@@ -1150,7 +1200,7 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     return 0;
   }
   if (splits > 1) {
-    sum_splits_kernel<<<elementwise_grid(wsize, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws), splits, wsize, dw);
+    launch_k(sum_splits_kernel, elementwise_grid(wsize, 256), 256, 0, st, reinterpret_cast<const float*>(ws), splits, wsize, dw);
     return check_launch("wgrad sum_splits");
   }
   return 0;
@@ -1175,8 +1225,34 @@ int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const
     B.start[B.count] = chunks;
     if (chunks == 0) continue;
     const int grid = chunks < sm_count() * 8 ? chunks : sm_count() * 8;
-    repack_multi_kernel<<<grid, 256, 0, st>>>(B);
+    launch_k(repack_multi_kernel, grid, 256, 0, st, B);
     if (check_launch("repack_multi")) return 1;
+  }
+  return 0;
+}
+
+int igemm_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
+                            void* const* wt_bf16, cudaStream_t st) {
+  for (int base = 0; base < count; base += kMaxBatch) {
+    static thread_local PackBf16Batch B;
+    B.count = count - base < kMaxBatch ? count - base : kMaxBatch;
+    int chunks = 0;
+    for (int i = 0; i < B.count; ++i) {
+      const ttb_conv_desc* d = descs[base + i];
+      B.w[i] = w[base + i];
+      B.wh[i] = reinterpret_cast<__nv_bfloat16*>(w_bf16[base + i]);
+      B.wth[i] = reinterpret_cast<__nv_bfloat16*>(wt_bf16[base + i]);
+      B.K[i] = d->k;
+      B.T[i] = d->r * d->s;
+      B.C[i] = d->c / d->groups;
+      B.start[i] = chunks;
+      chunks += d->r * d->s * (int)ceil_div(d->k, 32) * (int)ceil_div(B.C[i], 32);
+    }
+    B.start[B.count] = chunks;
+    if (chunks == 0) continue;
+    const int grid = chunks < sm_count() * 8 ? chunks : sm_count() * 8;
+    launch_k(pack_bf16_multi_kernel, grid, 256, 0, st, B);
+    if (check_launch("pack_bf16_multi")) return 1;
   }
   return 0;
 }
@@ -1198,7 +1274,7 @@ int igemm_sum_splits_multi(int count, const float* const* partials, const int* s
     B.start[B.count] = chunks;
     if (chunks == 0) continue;
     const int grid = chunks < sm_count() * 8 ? chunks : sm_count() * 8;
-    sum_splits_multi_kernel<<<grid, 256, 0, st>>>(B);
+    launch_k(sum_splits_multi_kernel, grid, 256, 0, st, B);
     if (check_launch("sum_splits_multi")) return 1;
   }
   return 0;

@@ -9,6 +9,7 @@ constexpr int kThreads = 256;
 // Generic vectorised elementwise driver: `Op` gets float4s (vector body) and floats (tail / unaligned).
 template <class F4, class F1>
 __global__ void __launch_bounds__(kThreads) ew_kernel(int64_t n, F4 f4, F1 f1, bool vec_ok) {
+  pdl_entry();
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (vec_ok) {
@@ -33,7 +34,7 @@ static int launch_ew(const char* what, int64_t n, bool vec_ok, F4 f4, F1 f1, cud
   if (n <= 0) return 0;
   int64_t items = vec_ok ? (n + 3) / 4 : n;
   int grid = elementwise_grid(items, kThreads);
-  ew_kernel<<<grid, kThreads, 0, st>>>(n, f4, f1, vec_ok);
+  launch_k(ew_kernel<F4, F1>, grid, kThreads, 0, st, n, f4, f1, vec_ok);
   return check_launch(what);
 }
 
@@ -44,6 +45,7 @@ __device__ __forceinline__ float relu1(float v) { return v < 0.f ? 0.f : v; }  /
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                         int rows, int cols, int64_t batch_stride) {
+  pdl_entry();
   // src: [batch][rows][cols] -> dst: [batch][cols][rows]
   __shared__ float tile[32][33];
   const float* s = src + (int64_t)blockIdx.z * batch_stride;
@@ -70,7 +72,7 @@ static int transpose_batched(const float* src, float* dst, int batch, int rows, 
     int nb = batch - done < 65535 ? batch - done : 65535;
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, nb);
     int64_t off = (int64_t)done * rows * cols;
-    transpose_kernel<<<grid, 256, 0, st>>>(src + off, dst + off, rows, cols, (int64_t)rows * cols);
+    launch_k(transpose_kernel, grid, 256, 0, st, src + off, dst + off, rows, cols, (int64_t)rows * cols);
     if (check_launch("transpose")) return 1;
     done += nb;
   }
@@ -108,6 +110,7 @@ __device__ __forceinline__ void sgd_elem(float& p, float g, float& b, bool has_b
 }
 
 __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ SgdMulti A) {
+  pdl_entry();
   // locate the tensor this CTA works on
   int t = 0;
   while (t + 1 < A.count && (int)blockIdx.x >= A.block_start[t + 1]) ++t;
@@ -151,11 +154,145 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// multi-tensor Adam / AdamW (optim/_functional.py:25-68 and :71-115), same chunking as the SGD kernel.  The step count
+// lives on the DEVICE (state[0] = step as float, state[1] = 1 - beta1^step, state[2] = 1 - beta2^step, advanced by
+// adam_advance_kernel once per optimizer step) so a captured CUDA graph replays with the right bias corrections.
+// ---------------------------------------------------------------------------------------------------------
+struct AdamMulti {
+  float* p[kMultiMax];
+  const float* g[kMultiMax];
+  float* m[kMultiMax];
+  float* v[kMultiMax];
+  float* vmax[kMultiMax];
+  int64_t n[kMultiMax];
+  int block_start[kMultiMax + 1];
+  int count;
+  float lr, beta1, beta2, eps, weight_decay;
+  int decoupled;  // 0: Adam (L2 term added to the gradient), 1: AdamW (p *= 1 - lr*wd first)
+  const float* state;
+};
+
+__global__ void adam_advance_kernel(float* state, float beta1, float beta2) {
+  pdl_entry();
+  const double step = (double)state[0] + 1.0;
+  state[0] = (float)step;
+  state[1] = (float)(1.0 - pow((double)beta1, step));
+  state[2] = (float)(1.0 - pow((double)beta2, step));
+}
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float* vmax, const AdamMulti& A, float bc1,
+                                          float sqrt_bc2) {
+  if (A.decoupled) {
+    if (A.weight_decay != 0.f) p = __fmul_rn(p, 1.f - A.lr * A.weight_decay);
+  } else if (A.weight_decay != 0.f) {
+    g = __fadd_rn(g, __fmul_rn(p, A.weight_decay));
+  }
+  m = __fadd_rn(__fmul_rn(m, A.beta1), __fmul_rn(1.f - A.beta1, g));
+  v = __fadd_rn(__fmul_rn(v, A.beta2), __fmul_rn(__fmul_rn(g, g), 1.f - A.beta2));
+  float vv = v;
+  if (vmax) {
+    vv = fmaxf(*vmax, v);
+    *vmax = vv;
+  }
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), sqrt_bc2), A.eps);
+  p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-(A.lr / bc1), m), denom));
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMulti A) {
+  pdl_entry();
+  int t = 0;
+  while (t + 1 < A.count && (int)blockIdx.x >= A.block_start[t + 1]) ++t;
+  const int64_t base = (int64_t)(blockIdx.x - A.block_start[t]) * kMultiChunk;
+  const int64_t n = A.n[t];
+  float* __restrict__ p = A.p[t];
+  const float* __restrict__ g = A.g[t];
+  float* __restrict__ m = A.m[t];
+  float* __restrict__ v = A.v[t];
+  float* __restrict__ vm = A.vmax[t];
+  const float bc1 = A.state[1], sqrt_bc2 = sqrtf(A.state[2]);
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vm)) & 15) == 0;
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < kMultiChunk / (256 * 4); ++it) {
+      int64_t i = base + (int64_t)(it * 256 + threadIdx.x) * 4;
+      if (i + 3 < n) {
+        float4 pv = ld_f4(p + i), gv = ld_f4(g + i), mv = ld_f4(m + i), vv = ld_f4(v + i);
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vm) xv = ld_f4(vm + i);
+        adam_elem(pv.x, gv.x, mv.x, vv.x, vm ? &xv.x : nullptr, A, bc1, sqrt_bc2);
+        adam_elem(pv.y, gv.y, mv.y, vv.y, vm ? &xv.y : nullptr, A, bc1, sqrt_bc2);
+        adam_elem(pv.z, gv.z, mv.z, vv.z, vm ? &xv.z : nullptr, A, bc1, sqrt_bc2);
+        adam_elem(pv.w, gv.w, mv.w, vv.w, vm ? &xv.w : nullptr, A, bc1, sqrt_bc2);
+        st_f4(m + i, mv);
+        st_f4(v + i, vv);
+        if (vm) st_f4(vm + i, xv);
+        st_f4(p + i, pv);
+        continue;
+      }
+      for (int64_t j = i; j < n && j < i + 4; ++j) {
+        float pv = p[j], mv = m[j], vv = v[j], xv = vm ? vm[j] : 0.f;
+        adam_elem(pv, g[j], mv, vv, vm ? &xv : nullptr, A, bc1, sqrt_bc2);
+        m[j] = mv; v[j] = vv; p[j] = pv;
+        if (vm) vm[j] = xv;
+      }
+    }
+  } else {
+    for (int64_t j = base + threadIdx.x; j < n && j < base + kMultiChunk; j += 256) {
+      float pv = p[j], mv = m[j], vv = v[j], xv = vm ? vm[j] : 0.f;
+      adam_elem(pv, g[j], mv, vv, vm ? &xv : nullptr, A, bc1, sqrt_bc2);
+      m[j] = mv; v[j] = vv; p[j] = pv;
+      if (vm) vm[j] = xv;
+    }
+  }
+}
+
 }  // namespace ttb
 
 using namespace ttb;
 
 extern "C" {
+
+int ttb_adam_advance(float* state, float beta1, float beta2, void* stream) {
+  TTB_REQUIRE(state != nullptr, "adam_advance: null state");
+  launch_k(adam_advance_kernel, 1, 1, 0, as_stream(stream), state, beta1, beta2);
+  return check_launch("adam_advance");
+}
+
+int ttb_adam_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, const float* state,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, void* stream) {
+  TTB_REQUIRE(n_tensors >= 0 && params && grads && exp_avg && exp_avg_sq && sizes && state, "adam_step_multi: null table");
+  cudaStream_t st = as_stream(stream);
+  int done = 0;
+  while (done < n_tensors) {
+    AdamMulti A;
+    A.count = 0;
+    A.lr = lr; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.weight_decay = weight_decay; A.decoupled = decoupled;
+    A.state = state;
+    int blocks = 0;
+    while (done < n_tensors && A.count < kMultiMax) {
+      if (sizes[done] > 0) {
+        int i = A.count++;
+        A.p[i] = params[done];
+        A.g[i] = grads[done];
+        A.m[i] = exp_avg[done];
+        A.v[i] = exp_avg_sq[done];
+        A.vmax[i] = max_exp_avg_sq ? max_exp_avg_sq[done] : nullptr;
+        A.n[i] = sizes[done];
+        A.block_start[i] = blocks;
+        blocks += (int)ceil_div(sizes[done], kMultiChunk);
+      }
+      ++done;
+    }
+    if (A.count == 0) break;
+    A.block_start[A.count] = blocks;
+    launch_k(adam_multi_kernel, blocks, 256, 0, st, A);
+    if (check_launch("adam_step_multi")) return 1;
+  }
+  return 0;
+}
 
 int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* grads, float* const* bufs,
                        const int64_t* sizes, const unsigned char* first_step, float lr, float momentum, float dampening,
@@ -184,7 +321,7 @@ int ttb_sgd_step_multi(int n_tensors, float* const* params, const float* const* 
     }
     if (A.count == 0) break;
     A.block_start[A.count] = blocks;
-    sgd_multi_kernel<<<blocks, 256, 0, st>>>(A);
+    launch_k(sgd_multi_kernel, blocks, 256, 0, st, A);
     if (check_launch("sgd_step_multi")) return 1;
   }
   return 0;
@@ -198,16 +335,23 @@ int ttb_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, v
   return transpose_batched(src, dst, n, h * w, c, as_stream(stream));
 }
 
-int ttb_relu_fwd(const float* x, float* y, int64_t n, void* stream) {
-  bool v = aligned16(x) && aligned16(y);
+int ttb_relu_fwd(const float* x, float* y, int64_t n, void* y_bf16, void* stream) {
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_bf16);  // optional bf16 copy of y for the bf16 tensor path
+  bool v = aligned16(x) && aligned16(y) && (reinterpret_cast<uintptr_t>(yh) & 7) == 0;
   return launch_ew(
       "relu_fwd", n, v,
       [=] __device__(int64_t i) {
         float4 a = ld_f4(x + 4 * i);
         a.x = relu1(a.x); a.y = relu1(a.y); a.z = relu1(a.z); a.w = relu1(a.w);
         st_f4(y + 4 * i, a);
+        if (yh) st_bf16x4(yh + 4 * i, a);
       },
-      [=] __device__(int64_t i) { y[i] = relu1(x[i]); }, as_stream(stream));
+      [=] __device__(int64_t i) {
+        float r = relu1(x[i]);
+        y[i] = r;
+        if (yh) yh[i] = __float2bfloat16_rn(r);
+      },
+      as_stream(stream));
 }
 
 int ttb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream) {

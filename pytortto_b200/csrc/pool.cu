@@ -16,6 +16,7 @@ namespace ttb {
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(ttb_pool_desc d, const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
                    int64_t total, int cvec) {
+  pdl_entry();
   // one thread per (n, p, q, channel group of `cvec` channels); cvec is 4 (float4) or 1
   const int cg = d.c / cvec;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -65,6 +66,7 @@ template <bool ACCUM>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t* __restrict__ idx,
                    float* __restrict__ dx, int64_t total) {
+  pdl_entry();
   // one thread per input element (n, h, w, c); c fastest -> coalesced
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -118,7 +120,7 @@ int ttb_maxpool2d_fwd(const ttb_pool_desc* d, const float* x, float* y, uint8_t*
   int64_t total = (int64_t)d->n * d->p * d->q * (d->c / cvec);
   if (total <= 0) return 0;
   int grid = elementwise_grid(total, 256);
-  maxpool_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(*d, x, y, idx, total, cvec);
+  launch_k(maxpool_fwd_kernel, grid, 256, 0, as_stream(stream), *d, x, y, idx, total, cvec);
   return check_launch("maxpool2d_fwd");
 }
 
@@ -128,8 +130,8 @@ int ttb_maxpool2d_bwd(const ttb_pool_desc* d, const float* dy, const uint8_t* id
   int64_t total = (int64_t)d->n * d->h * d->w * d->c;
   if (total <= 0) return 0;
   int grid = elementwise_grid(total, 256);
-  if (accumulate) maxpool_bwd_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(*d, dy, idx, dx, total);
-  else maxpool_bwd_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(*d, dy, idx, dx, total);
+  if (accumulate) launch_k(maxpool_bwd_kernel<true>, grid, 256, 0, as_stream(stream), *d, dy, idx, dx, total);
+  else launch_k(maxpool_bwd_kernel<false>, grid, 256, 0, as_stream(stream), *d, dy, idx, dx, total);
   return check_launch("maxpool2d_bwd");
 }
 

@@ -1,5 +1,6 @@
 // Library-level entry points: error text, version, device properties.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -14,6 +15,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+#ifdef TTB_TUNING
+int tuning_knob(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#endif
 
 int sm_count() {
   static int cached[64] = {0};
@@ -33,7 +41,7 @@ extern "C" {
 
 const char* ttb_last_error(void) { return ttb::g_err; }
 
-int ttb_version(void) { return 2; }
+int ttb_version(void) { return 3; }
 
 int ttb_device_sm_count(int* out) {
   if (!out) return 2;

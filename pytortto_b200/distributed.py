@@ -71,6 +71,20 @@ def destroy_process_group():
     _state.update(initialized=False, world=1, rank=0, peer_comm=None)
 
 
+class single_process:
+    """Context manager: inside it this rank behaves like a single-process run (no SyncBN exchange, no gradient
+    all-reduce) although the process group stays up - used to compute the single-process reference of a parity check."""
+
+    def __enter__(self):
+        self._world = _state["world"]
+        _state["world"] = 1
+        return self
+
+    def __exit__(self, *exc):
+        _state["world"] = self._world
+        return False
+
+
 def all_reduce_sum_(t, async_op=False, average=False):
     """In-place SUM (or, with `average` on NCCL, AVG) all-reduce of a torch tensor (no-op for world 1).  Returns the
     work handle when async."""
@@ -230,6 +244,7 @@ def broadcast_parameters(module, src=0):
         d = t.data
         if hasattr(d, "t"):
             dist.broadcast(d.t, src=src)
+            d._touched()
         else:
             buf = torch.from_numpy(np.array(d, copy=True))
             dist.broadcast(buf, src=src)

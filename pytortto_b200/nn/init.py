@@ -12,6 +12,7 @@ def _assign(tensor, values):
     d = tensor.data
     if d.__class__ is cparray:
         d.t.copy_(cparray.from_numpy(values.astype(d.dtype)).t)
+        d._touched()
     else:
         d[...] = values.astype(d.dtype)
     return tensor

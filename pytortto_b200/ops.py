@@ -7,10 +7,12 @@ CUDA stream and never synchronises.
 import ctypes
 import math
 import os
+import weakref
 
 import torch
 
 from . import _cabi
+from . import xparray as _xp
 from .xparray import cparray, current_stream_ptr, empty_device, new_f32
 
 _MATH_MODES = {"fp32": _cabi.TTB_MATH_FP32, "tf32": _cabi.TTB_MATH_TF32, "bf16": _cabi.TTB_MATH_BF16}
@@ -29,6 +31,114 @@ def get_math_mode():
 
 def _ptr(a):
     return None if a is None else a.t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bf16 math mode: operands live in HBM as bf16 "shadows"
+# ---------------------------------------------------------------------------------------------------------
+# In bf16 mode the tensor-core kernels read 2-byte operands.  Converting x / w / dy inside every conv call costs three
+# extra HBM passes per call (what round 1 did: bf16 was no faster than TF32).  Instead
+#   * activations and gradients: the PRODUCING kernel (BatchNorm apply (+ReLU), BatchNorm backward apply, ReLU)
+#     co-writes a bf16 copy next to its fp32 output (`cparray._h`); a conv whose operand has no valid shadow converts it
+#     once with ttb_to_bf16 and caches the copy on the array (fprop's conversion of x is reused by wgrad);
+#   * weights: every conv weight seen so far is re-packed ([K][R][S][C] for fprop, [C][R][S][K] for dgrad, both bf16) by
+#     ONE multi-tensor launch when the first conv after a weight change runs (`xparray.mutation_epoch`: optimizer
+#     steps, copy_, load_state_dict, broadcast).
+# fp32 tensors stay what the API shows; accumulation and every output stay fp32.
+def _bf16_mode():
+    return _math_mode == _cabi.TTB_MATH_BF16
+
+
+def _shadow_wanted(x):
+    return _math_mode == _cabi.TTB_MATH_BF16 and x.ndim == 4 and x.shape[1] % 64 == 0 and x.t.dtype == torch.float32
+
+
+def _new_shadow(a):
+    h = torch.empty_like(a.t, dtype=torch.bfloat16)
+    a._h, a._hver = h, a._version[0]
+    return h
+
+
+def bf16_of(a):
+    """bf16 copy of a device array in the same physical layout: the producer's shadow, else converted now and cached."""
+    h = a._h
+    if h is not None and a._hver == a._version[0]:
+        return h
+    h = _new_shadow(a)
+    _cabi.call("ttb_to_bf16", a.t.data_ptr(), h.data_ptr(), a.size, current_stream_ptr())
+    return h
+
+
+_bf16_ok = {}
+
+
+def conv_bf16_supported(d, pass_):
+    key = (id(d), pass_)
+    ok = _bf16_ok.get(key)
+    if ok is None:
+        ok = _bf16_ok[key] = (d, bool(_cabi.load().ttb_conv2d_bf16_supported(ctypes.byref(d), pass_)))  # keeps d alive
+    return ok[1]
+
+
+_tf32_twins = {}
+
+
+def _tf32_twin(d):
+    """the same problem in TF32 mode (bf16-mode layers whose channel counts do not fit 64-channel K-blocks, e.g. the
+    3-channel stem, run on the TF32 tensor path instead of a 20x zero-padded bf16 one)"""
+    t = _tf32_twins.get(id(d))
+    if t is None:
+        twin = _cabi.ConvDesc.from_buffer_copy(d)
+        twin.math_mode = _cabi.TTB_MATH_TF32
+        t = _tf32_twins[id(d)] = (d, twin)
+    return t[1]
+
+
+class _WeightPack:
+    __slots__ = ("ref", "desc", "wh", "wth", "epoch")
+
+
+_wpack = {}  # weight data_ptr -> _WeightPack
+
+
+def weights_changed():
+    """Call after writing conv weights through anything but cparray / Tensor methods (optimizer kernels do)."""
+    _xp.mutation_epoch[0] += 1
+
+
+def _weight_bf16(w, transposed):
+    epoch = _xp.mutation_epoch[0]
+    ptr = w.t.data_ptr()
+    ent = _wpack.get(ptr)
+    if ent is None or ent.ref() is not w or ent.wh.numel() != w.size:
+        ent = _WeightPack()
+        ent.ref = weakref.ref(w)
+        k, c, r, s_ = w.shape
+        ent.desc = _cabi.ConvDesc(1, c, r, s_, k, r, s_, 1, 1, 0, 0, 1, 1, 1, 1, 1, _cabi.TTB_MATH_BF16)
+        ent.wh = torch.empty(w.size, dtype=torch.bfloat16, device=w.t.device)
+        ent.wth = torch.empty(w.size, dtype=torch.bfloat16, device=w.t.device)
+        ent.epoch = -1
+        _wpack[ptr] = ent
+    if ent.epoch != epoch:  # re-pack every stale weight that is still alive in one launch
+        stale = []
+        for p_, e in list(_wpack.items()):
+            if e.ref() is None:
+                del _wpack[p_]
+            elif e.epoch != epoch:
+                stale.append((p_, e))
+        n = len(stale)
+        descs = (ctypes.POINTER(_cabi.ConvDesc) * n)()
+        src = (ctypes.c_void_p * n)()
+        dst = (ctypes.c_void_p * n)()
+        dstt = (ctypes.c_void_p * n)()
+        for i, (p_, e) in enumerate(stale):
+            descs[i] = ctypes.pointer(e.desc)
+            src[i] = p_
+            dst[i] = e.wh.data_ptr()
+            dstt[i] = e.wth.data_ptr()
+            e.epoch = epoch
+        _cabi.call("ttb_conv2d_pack_weights_bf16", n, descs, src, dst, dstt, current_stream_ptr())
+    return ent.wth if transposed else ent.wh
 
 
 def _workspace(nbytes):
@@ -68,6 +178,12 @@ def conv2d_fprop(x, w, bias, d):
     y = new_f32((d.n, d.k, d.p, d.q))
     if y.size == 0:
         return y
+    if d.math_mode == _cabi.TTB_MATH_BF16:
+        if conv_bf16_supported(d, 0) and w.ndim == 4:
+            _cabi.call("ttb_conv2d_fprop_bf16", ctypes.byref(d), bf16_of(x).data_ptr(), _weight_bf16(w, False).data_ptr(),
+                       _ptr(bias), _ptr(y), current_stream_ptr())
+            return y
+        d = _tf32_twin(d)
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 0))
     _cabi.call("ttb_conv2d_fprop", ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y),
                None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
@@ -131,6 +247,12 @@ def conv2d_dgrad(dy, w, d):
     dx = new_f32((d.n, d.c, d.h, d.w))
     if dx.size == 0:
         return dx
+    if d.math_mode == _cabi.TTB_MATH_BF16:
+        if conv_bf16_supported(d, 1) and w.ndim == 4:
+            _cabi.call("ttb_conv2d_dgrad_bf16", ctypes.byref(d), bf16_of(dy).data_ptr(), _weight_bf16(w, True).data_ptr(),
+                       _ptr(dx), current_stream_ptr())
+            return dx
+        d = _tf32_twin(d)
     if _dgrad_pack["enabled"] and _dgrad_pack["in_sweep"]:  # (a dgrad outside backward = ConvTranspose2d forward)
         _flush_dgrad_pack()
         ent = _dgrad_pack["packed"].get(w.t.data_ptr())
@@ -190,6 +312,23 @@ def conv2d_wgrad(x, dy, d, overlap=False):
     dw = new_f32((d.k, d.c // d.groups, d.r, d.s))
     if dw.size == 0:
         return dw
+    if d.math_mode == _cabi.TTB_MATH_BF16:
+        if conv_bf16_supported(d, 2):
+            # operand copies are made (when the producers did not co-write them) on the CURRENT stream, before the fork:
+            # the dgrad that follows on this stream reuses dy's
+            xh, dyh = bf16_of(x), bf16_of(dy)
+            ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size_bf16(ctypes.byref(d), 2))
+            st = current_stream_ptr()
+            if overlap and _overlap["enabled"]:
+                side = _side_stream()
+                side.wait_stream(torch.cuda.current_stream())
+                st = side.cuda_stream
+                _overlap["keep"].append((x, dy, dw, ws, xh, dyh))
+                _overlap["dirty"] = True
+            _cabi.call("ttb_conv2d_wgrad_bf16", ctypes.byref(d), xh.data_ptr(), dyh.data_ptr(), _ptr(dw),
+                       None if ws is None else ws.data_ptr(), nb, st)
+            return dw
+        d = _tf32_twin(d)
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 2))
     if overlap and _overlap["enabled"]:
         side = _side_stream()
@@ -222,6 +361,7 @@ def bias_grad(dy):
 def add_bias_(y, bias):
     """y (N,K,P,Q) += bias[:, None, None] in place (used where the bias cannot ride the conv epilogue)."""
     y.t.add_(bias.t.view(1, -1, 1, 1))
+    y._h = None
     return y
 
 
@@ -254,7 +394,7 @@ def bn_sums(x, reduce_hook=None):
 
 def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, relu=False, reduce_hook=None):
     m, c = _rows_channels(x)
-    stats = new_f32((5, c))  # rows: mean, var+eps, sd, scale, shift
+    stats = new_f32((5, c))  # rows: mean, var+eps, sd, scale (= gamma/sd), shift (= beta): y = (x - mean)*scale + shift
     base = stats.t.data_ptr()
     row = c * 4
     st = current_stream_ptr()
@@ -273,7 +413,8 @@ def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, r
                    _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row,
                    base + 3 * row, base + 4 * row, st)
     y = cparray(empty_device(x.shape))
-    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base + 3 * row, base + 4 * row, int(relu), st)
+    yh = _new_shadow(y).data_ptr() if _shadow_wanted(x) else None
+    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu), yh, st)
     return y, stats, count
 
 
@@ -286,7 +427,8 @@ def bn_forward_eval(x, gamma, beta, mean, var, eps, relu=False):
     _cabi.call("ttb_bn_prepare_eval", _ptr(mean), _ptr(var), c, eps, _ptr(gamma), _ptr(beta), base, base + row,
                base + 2 * row, base + 3 * row, base + 4 * row, st)
     y = cparray(empty_device(x.shape))
-    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base + 3 * row, base + 4 * row, int(relu), st)
+    yh = _new_shadow(y).data_ptr() if _shadow_wanted(x) else None
+    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu), yh, st)
     return y, stats, m
 
 
@@ -326,7 +468,9 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     dx = None
     if need_dx:
         dx = cparray(empty_device(x.shape))
-        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, _ptr(coef), _ptr(accum), _ptr(dx), m, c, st)
+        dxh = _new_shadow(dx).data_ptr() if _shadow_wanted(x) else None
+        _cabi.call("ttb_bn_bwd_apply", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, _ptr(coef), _ptr(accum), _ptr(dx), m, c,
+                   dxh, st)
     return dx, dgamma, dbeta
 
 
@@ -335,7 +479,9 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
 # ---------------------------------------------------------------------------------------------------------
 def relu_fwd(x, inplace=False):
     y = x if inplace else cparray(empty_device(x.shape))
-    _cabi.call("ttb_relu_fwd", _ptr(x), _ptr(y), x.size, current_stream_ptr())
+    y._h = None  # (in place: the old shadow is stale)
+    yh = _new_shadow(y).data_ptr() if (_shadow_wanted(y) and not inplace) else None
+    _cabi.call("ttb_relu_fwd", _ptr(x), _ptr(y), x.size, yh, current_stream_ptr())
     return y
 
 
@@ -356,12 +502,14 @@ def add_arrays(a, b):
 
 def axpy_(alpha, x, y):
     _cabi.call("ttb_axpy", float(alpha), _ptr(x), _ptr(y), x.size, current_stream_ptr())
+    y._touched()
     return y
 
 
 def sgd_step_(param, grad, buf, lr, momentum, dampening, weight_decay, nesterov, first_step):
     _cabi.call("ttb_sgd_step", _ptr(param), _ptr(grad), _ptr(buf), param.size, float(lr), float(momentum),
                float(dampening), float(weight_decay), int(bool(nesterov)), int(bool(first_step)), current_stream_ptr())
+    weights_changed()
 
 
 def sgd_step_multi_(params, grads, bufs, first_flags, lr, momentum, dampening, weight_decay, nesterov):
@@ -376,6 +524,7 @@ def sgd_step_multi_(params, grads, bufs, first_flags, lr, momentum, dampening, w
     F = (ctypes.c_ubyte * n)(*[1 if f else 0 for f in first_flags])
     _cabi.call("ttb_sgd_step_multi", n, P, G, B, S, F, float(lr), float(momentum), float(dampening),
                float(weight_decay), int(bool(nesterov)), current_stream_ptr())
+    weights_changed()
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,4 +1,4 @@
 from .optimizer import Optimizer
 from .sgd import SGD
-from .adam import Adam
+from .adam import Adam, AdamW
 from . import lr_scheduler

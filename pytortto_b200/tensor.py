@@ -198,6 +198,7 @@ class Tensor:
                 src = cparray.from_numpy(np.asarray(src), dtype=self.data.dtype)
             self.data.t.copy_(src.t.reshape(self.data.t.shape) if src.ndim != self.data.ndim else src.t)
             self.data._version[0] += 1
+            self.data._touched()
         else:
             self.data[...] = src.get() if src.__class__ is cparray else np.asarray(src)
         return self

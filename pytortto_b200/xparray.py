@@ -47,9 +47,17 @@ class _Mem:
         self.ptr = ptr
 
 
+# Bumped by every in-place write to a 4-D device array that does not go through a kernel which maintains the array's
+# bf16 shadow itself: ops.py re-derives the bf16 copies of the conv weights when it has moved (weights change once per
+# optimizer step; anything else that writes a parameter - copy_, load_state_dict, broadcast - lands here too).
+mutation_epoch = [0]
+
+
 class cparray:
-    """Device array.  `t` is the owning torch tensor (logical shape, canonical physical layout)."""
-    __slots__ = ("t", "_version", "base")
+    """Device array.  `t` is the owning torch tensor (logical shape, canonical physical layout).
+    `_h` / `_hver`: optional bf16 shadow of the same values (same physical layout) and the `_version` it was written
+    at - co-written by the producing kernel in bf16 math mode so the next convolution reads 2-byte operands."""
+    __slots__ = ("t", "_version", "base", "_h", "_hver", "__weakref__")
 
     def __init__(self, t, version=None, base=None):
         if t.__class__ is not torch.Tensor:
@@ -61,6 +69,14 @@ class cparray:
         self.t = t
         self._version = [0] if version is None else version
         self.base = base
+        self._h = None
+        self._hver = 0
+
+    def _touched(self):
+        """an in-place write happened outside the shadow-maintaining kernels"""
+        self._h = None
+        if self.t.dim() == 4:
+            mutation_epoch[0] += 1
 
     # ---- construction / transfer --------------------------------------------------------------------------
     @classmethod
@@ -173,6 +189,7 @@ class cparray:
 
     def fill(self, value):
         self.t.fill_(value)
+        self._touched()
 
     def sum(self, axis=None, keepdims=False):
         return cparray(self.t.sum() if axis is None else self.t.sum(dim=axis, keepdim=keepdims))
@@ -199,6 +216,7 @@ class cparray:
         elif isinstance(value, np.ndarray):
             value = torch.from_numpy(np.ascontiguousarray(value)).to(self.t.device)
         self.t[key] = value
+        self._touched()
 
     @staticmethod
     def _operand(o):
@@ -242,18 +260,22 @@ class cparray:
 
     def __iadd__(self, o):
         self.t.add_(self._operand(o))
+        self._touched()
         return self
 
     def __isub__(self, o):
         self.t.sub_(self._operand(o))
+        self._touched()
         return self
 
     def __imul__(self, o):
         self.t.mul_(self._operand(o))
+        self._touched()
         return self
 
     def __itruediv__(self, o):
         self.t.div_(self._operand(o))
+        self._touched()
         return self
 
 

@@ -125,10 +125,10 @@ def test_adam_step_and_eval_mode():
     assert float(sd["down.0.conv.1.num_batches_tracked"]) == 5.0
 
 
-def _layerwise_conv_parity(tt, net, run, tol=3e-3):
+def _layerwise_conv_parity(tt, net, run, tol=3e-3, tol_bf16=1e-2):
     """Run `run(net)` once in TF32 mode recording the input of every Conv2d / ConvTranspose2d call, then replay every
-    recorded call on ITS OWN recorded input in tf32 and in exact-fp32 mode (forward + backward with a fixed upstream
-    gradient) and compare per layer.  Whole-network comparisons of tf32 against fp32 are chaotic for deep nets at a
+    recorded call on ITS OWN recorded input in tf32, in bf16 (north-star tolerance 1e-2) and in exact-fp32 mode
+    (forward + backward with a fixed upstream gradient) and compare per layer against the exact path.  Whole-network comparisons of tf32 against fp32 are chaotic for deep nets at a
     small batch; this is the size-independent form of the same check."""
     from pytortto_b200.nn.modules import Conv2d, ConvTranspose2d
     calls = []
@@ -147,7 +147,7 @@ def _layerwise_conv_parity(tt, net, run, tol=3e-3):
     for idx, (m, xin, kw) in enumerate(calls):
         res = {}
         dy = None
-        for mode in ("tf32", "fp32"):
+        for mode in ("tf32", "bf16", "fp32"):
             tt.set_math_mode(mode)
             leaf = tt.tensor(xin, requires_grad=True)
             m.weight.grad = None
@@ -156,11 +156,12 @@ def _layerwise_conv_parity(tt, net, run, tol=3e-3):
                 dy = rng.standard_normal(y.shape).astype(np.float32)
             y.backward(tt.tensor(dy).cuda())
             res[mode] = (y.data.get(), np.asarray(leaf.grad), m.weight.grad.get())
-        for name, a, b in zip(("y", "dx", "dw"), res["tf32"], res["fp32"]):
-            err = float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
-            key = f"{type(m).__name__} {tuple(m.weight.shape)} s{m.stride[0]} in{tuple(xin.shape)} {name}"
-            worst[key] = max(worst.get(key, 0.0), err)
-            assert err < tol, (idx, key, err)
+        for mode, bound in (("tf32", tol), ("bf16", tol_bf16)):
+            for name, a, b in zip(("y", "dx", "dw"), res[mode], res["fp32"]):
+                err = float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+                key = f"{mode} {type(m).__name__} {tuple(m.weight.shape)} s{m.stride[0]} in{tuple(xin.shape)} {name}"
+                worst[key] = max(worst.get(key, 0.0), err)
+                assert err < bound, (idx, key, err)
         m.weight.grad = None
     tt.set_math_mode("tf32")
     return len(calls), worst
@@ -198,5 +199,5 @@ def test_full_size_resnet50_and_unet_shapes():
     nu, wu = _layerwise_conv_parity(tt, M["UNet"](3, 1, [32, 64, 128, 256]).cuda(), runu)
     assert n50 == 53 and nu == 23
     for k, v in sorted({**w50, **wu}.items(), key=lambda kv: -kv[1])[:8]:
-        print(f"worst layer-wise tf32-vs-fp32 rel-err {v:.2e}  {k}")
+        print(f"worst layer-wise rel-err vs the exact fp32 path {v:.2e}  {k}")
     assert np.isfinite(losses["resnet50"]) and np.isfinite(losses["unet"])

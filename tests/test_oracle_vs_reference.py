@@ -47,6 +47,23 @@ for trial in range(12):
     assert np.array_equal(O.max_pool2d_backward(dyp, idx, x.shape, kk, ss, pp, 1, ceil), xt2.grad), "pool bwd"
 print("WORST", worst)
 assert worst < 2e-5
+# Adam / AdamW (optim/adam.py, adamw.py + _functional.py:25-115) vs the oracle's restatement, 4 steps, with weight decay / amsgrad
+for cls_name, decoupled, amsgrad in (("Adam", False, False), ("Adam", False, True), ("AdamW", True, False)):
+    shapes = [(4, 3, 3, 3), (7,), (5, 6)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    ref_p = [tt.nn.Parameter(tt.tensor(p.copy())) for p in p0]
+    opt = getattr(tt.optim, cls_name)(ref_p, lr=1e-2, weight_decay=1e-2, amsgrad=amsgrad)
+    op = [p.copy() for p in p0]; m = [np.zeros_like(p) for p in p0]; v = [np.zeros_like(p) for p in p0]
+    vm = [np.zeros_like(p) for p in p0] if amsgrad else None
+    for step in range(1, 5):
+        gs = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+        for p, g in zip(ref_p, gs):
+            p.grad = g.copy()
+        opt.step()
+        O.adam_step(op, gs, m, v, [step] * 3, lr=1e-2, weight_decay=1e-2, max_exp_avg_sqs=vm, decoupled=decoupled)
+        for a, b in zip(op, ref_p):
+            assert rel(a, b.data) < 2e-6, (cls_name, amsgrad, step, rel(a, b.data))
+print("ADAM OK")
 '''
 
 
@@ -54,4 +71,4 @@ assert worst < 2e-5
 def test_oracle_matches_live_reference():
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "WORST" in r.stdout
+    assert "WORST" in r.stdout and "ADAM OK" in r.stdout
