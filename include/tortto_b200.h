@@ -67,6 +67,10 @@ int ttb_device_sm_count(int* out);           /* SM count of the current device  
 /* 1 if the tcgen05 tensor path supports this problem in the requested math mode, else 0 (then the FP32 path runs) */
 int ttb_conv2d_tensor_path_supported(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
 
+/* which kernel family a pass runs on: 0 exact fp32 direct kernels, 1 tcgen05 implicit GEMM (im2col-mode TMA), 2 tcgen05
+ * flat-shift halo tile with shared-memory-resident weights (3x3 / stride-1 layers with <= 64 output channels) */
+int ttb_conv2d_kernel_variant(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
+
 /* ---- layout --------------------------------------------------------------------------------------------- */
 int ttb_nchw_to_nhwc(const float* src, float* dst, int n, int c, int h, int w, void* stream);
 int ttb_nhwc_to_nchw(const float* src, float* dst, int n, int c, int h, int w, void* stream);

@@ -34,6 +34,7 @@ _PROTOS = {
     "ttb_version": (c_int, []),
     "ttb_device_sm_count": (c_int, [POINTER(c_int)]),
     "ttb_conv2d_tensor_path_supported": (c_int, [POINTER(ConvDesc), c_int]),
+    "ttb_conv2d_kernel_variant": (c_int, [POINTER(ConvDesc), c_int]),
     "ttb_nchw_to_nhwc": (c_int, [_F, _F, c_int, c_int, c_int, c_int, c_void_p]),
     "ttb_nhwc_to_nchw": (c_int, [_F, _F, c_int, c_int, c_int, c_int, c_void_p]),
     "ttb_conv2d_workspace_size": (c_size_t, [POINTER(ConvDesc), c_int]),

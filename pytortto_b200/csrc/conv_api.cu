@@ -29,7 +29,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
                 cudaStream_t st, const void* prepacked = nullptr);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st, int* splits_out = nullptr);
-// conv_flat.cu: prototype "flat-shift halo tile" fprop, taken only when TTB_FLAT=1 (not validated on hardware yet)
+// conv_flat.cu: "flat-shift halo tile" fprop / dgrad with shared-memory-resident weights (the 64-channel 3x3 layers)
 bool flat_fprop_supported(const ttb_conv_desc* d);
 bool flat_dgrad_supported(const ttb_conv_desc* d);
 int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
@@ -168,6 +168,17 @@ int ttb_conv2d_tensor_path_supported(const ttb_conv_desc* d, int pass) {
   return plan_tensor(d, pass, &t) ? 1 : 0;
 }
 
+/* which kernel family a pass of this problem runs on: 0 = exact fp32 direct kernels, 1 = tcgen05 implicit GEMM (im2col TMA),
+ * 2 = tcgen05 flat-shift halo tile with shared-memory-resident weights (introspection for tests and reports) */
+int ttb_conv2d_kernel_variant(const ttb_conv_desc* d, int pass) {
+  if (!d) return 0;
+  TensorPlan t;
+  if (!plan_tensor(d, pass, &t)) return 0;
+  if (!t.stage_ops && pass == 0 && flat_fprop_supported(&t.p)) return 2;
+  if (!t.stage_ops && pass == 1 && flat_dgrad_supported(&t.p)) return 2;
+  return 1;
+}
+
 size_t ttb_conv2d_workspace_size(const ttb_conv_desc* d, int pass) {
   if (!d) return 0;
   TensorPlan t;
@@ -186,7 +197,7 @@ int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, con
               "conv2d_fprop: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
   char* ws = reinterpret_cast<char*>(workspace);
   const void *xa = x, *wa = w;
-  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, bias, y, st);  // TTB_FLAT=1 only
+  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, bias, y, st);
   if (t.stage_ops) {
     if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
     if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, t.p.c, t.bf16, st)) return 1;
@@ -286,7 +297,7 @@ int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const fl
   if (int rc = validate(d, "conv2d_dgrad_prepacked")) return rc;
   TensorPlan t;
   TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops, "conv2d_dgrad_prepacked: problem needs the staged path");
-  if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream));  // TTB_FLAT=1 only
+  if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream));
   return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed);
 }
 

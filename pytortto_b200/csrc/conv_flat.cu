@@ -1,4 +1,12 @@
-// PROTOTYPE - compiled, NOT yet validated on hardware, OFF unless TTB_FLAT=1.
+// "Flat-shift halo tile" fprop / dgrad.  Validated on B200 (parity vs the exact fp32 kernels on every case of
+// scripts/flat_check.py and tests/test_gpu_flat.py).  Two variants:
+//   * RESIDENT (default path of the 64 -> 64 channel 3x3 layers, TF32): the WHOLE weight matrix (K x R*S*C, 144 KB for
+//     64 x 576 fp32) is loaded into shared memory once per CTA and stays there for all of the CTA's tiles; the main
+//     loop then has no weight hand-shakes at all - per 32-channel slab one strip wait and 9 taps x 4 tcgen05.mma issued
+//     back to back.  The production im2col kernel is issue-bound on these layers (one mbarrier hand-shake per 4 small
+//     N = 64 MMAs: ~340 cycles per 128 tensor-core cycles, measured) and re-reads every input pixel 9 times from L2.
+//   * STREAMED (weight tiles through a ring, any channel count): measured SLOWER than the production kernel (one CTA per
+//     SM, same hand-shake count, 13-27 % dropped outputs) - kept for experiments in the tuning build (TTB_FLAT=1).
 //
 // "Flat-shift halo tile" fprop for stride-1 / dilation-1 convolutions (the 3x3 layers that dominate every ResNet): the
 // production kernel (conv_igemm.cu) loads one im2col A tile per (filter tap, 32-channel slab) - 9 loads of the same
@@ -96,7 +104,9 @@ __device__ __forceinline__ void flat_epilogue(uint32_t tmem_acc, float* stage_sm
   }
 }
 
-template <int BN, int NB>
+// RES: resident weights - NB is ignored, `P.c_blocks * taps` weight tiles live in shared memory for the whole kernel and a
+// strip stage holds ONE 32-channel slab (kSlabsPerStrip = 1)
+template <int BN, int NB, bool RES>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
@@ -104,14 +114,16 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   constexpr uint32_t kBBytes = BN * 128;
   constexpr int kAccCols = BN < 32 ? 32 : BN;
   constexpr int kTmemCols = 2 * kAccCols;
+  constexpr int kSlabsPerStrip = RES ? 1 : kFlatSlabsPerStrip;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t slab_bytes = (uint32_t)P.rows_max * (uint32_t)P.wp * 128u;       // one 32-channel slab of a strip
-  const uint32_t strip_bytes = ((kFlatSlabsPerStrip * slab_bytes) + 1023u) & ~1023u;
+  const uint32_t strip_bytes = ((kSlabsPerStrip * slab_bytes) + 1023u) & ~1023u;
+  const int n_btiles = RES ? P.c_blocks * P.taps_r * P.taps_s : NB;
   uint8_t* strip0 = smem;                                          // kFlatStripStages strips
-  uint8_t* bring = smem + kFlatStripStages * strip_bytes;           // NB weight tiles
-  float* staging = reinterpret_cast<float*>(bring + NB * kBBytes);  // epilogue staging
+  uint8_t* bring = smem + kFlatStripStages * strip_bytes;           // NB weight tiles (RES: every weight tile)
+  float* staging = reinterpret_cast<float*>(bring + (size_t)n_btiles * kBBytes);  // epilogue staging
   __shared__ uint64_t strip_full[kFlatStripStages], strip_empty[kFlatStripStages], b_full[NB], b_empty[NB], acc_full[2],
       acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
@@ -122,7 +134,7 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   const int64_t mt = (P.m_flat + kFlatTileM - 1) / kFlatTileM;
   const int64_t tiles = mt * nt;
   const int taps = P.taps_r * P.taps_s;
-  const int num_groups = (P.c_blocks + kFlatSlabsPerStrip - 1) / kFlatSlabsPerStrip;  // strip loads per tile
+  const int num_groups = (P.c_blocks + kSlabsPerStrip - 1) / kSlabsPerStrip;  // strip loads per tile
   constexpr int kMmaWarp = 1 + kFlatBProducers;
 
   if (warp == 0 && ptx::elect_one()) {
@@ -167,8 +179,8 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
       const int nrows = (int)(row1 - row0 + 1);
       for (int grp = 0; grp < num_groups; ++grp, ++g) {
         const uint32_t stage = g % kFlatStripStages, phase = (g / kFlatStripStages) & 1u;
-        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
-                                                                                     : kFlatSlabsPerStrip;
+        const int slabs = P.c_blocks - grp * kSlabsPerStrip < kSlabsPerStrip ? P.c_blocks - grp * kSlabsPerStrip
+                                                                                     : kSlabsPerStrip;
         ptx::mbar_wait(&strip_empty[stage], phase ^ 1u);
         if (ptx::elect_one()) {
           uint8_t* base = strip0 + stage * strip_bytes;
@@ -179,7 +191,7 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
               const int n = (int)(row / P.hp);
               const int hp = (int)(row - (int64_t)n * P.hp);
               ptx::tma_load_4d(base + sl * slab_bytes + (uint32_t)j * (uint32_t)P.wp * 128u, &P.tmX, &strip_full[stage],
-                               (grp * kFlatSlabsPerStrip + sl) * 32, -P.pad_w, hp - P.pad_h, n);
+                               (grp * kSlabsPerStrip + sl) * 32, -P.pad_w, hp - P.pad_h, n);
             }
         }
         __syncwarp();
@@ -189,11 +201,23 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
     // ===================== weight-tile producers (K-block g belongs to producer g % kFlatBProducers) =====================
     const int me = warp - 1;
     uint32_t g = 0;
+    if (RES) {
+      // resident weights: every (tap, slab) tile once, all on one barrier; tile index = tap * c_blocks + slab
+      if (me == 0 && blockIdx.x < tiles) {
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&b_full[0], (uint32_t)n_btiles * kBBytes);
+          for (int tap = 0; tap < taps; ++tap)
+            for (int sl = 0; sl < P.c_blocks; ++sl)
+              ptx::tma_load_2d(bring + (size_t)(tap * P.c_blocks + sl) * kBBytes, &P.tmB, &b_full[0], P.b_koff[tap] + sl * 32, 0);
+        }
+        __syncwarp();
+      }
+    } else
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int n0 = (int)(t % nt) * BN;
       for (int grp = 0; grp < num_groups; ++grp) {
-        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
-                                                                                     : kFlatSlabsPerStrip;
+        const int slabs = P.c_blocks - grp * kSlabsPerStrip < kSlabsPerStrip ? P.c_blocks - grp * kSlabsPerStrip
+                                                                                     : kSlabsPerStrip;
         for (int tap = 0; tap < taps; ++tap) {
           const int kb0 = P.b_koff[tap];
           for (int sl = 0; sl < slabs; ++sl, ++g) {
@@ -202,7 +226,7 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
             ptx::mbar_wait(&b_empty[stage], phase ^ 1u);
             if (ptx::elect_one()) {
               ptx::mbar_expect_tx(&b_full[stage], kBBytes);
-              ptx::tma_load_2d(bring + stage * kBBytes, &P.tmB, &b_full[stage], kb0 + (grp * kFlatSlabsPerStrip + sl) * 32, n0);
+              ptx::tma_load_2d(bring + stage * kBBytes, &P.tmB, &b_full[stage], kb0 + (grp * kSlabsPerStrip + sl) * 32, n0);
             }
             __syncwarp();
           }
@@ -214,6 +238,10 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
     constexpr uint32_t idesc = ptx::umma_idesc(2 /*tf32*/, 0, 0, kFlatTileM, BN);
     uint32_t gs = 0, gb = 0;
     int it = 0;
+    if (RES && blockIdx.x < tiles) {
+      ptx::mbar_wait(&b_full[0], 0);  // the whole weight matrix is in shared memory from here on
+      ptx::tc_fence_after();
+    }
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int64_t f0 = (t / nt) * kFlatTileM;
       const int lead = (int)(f0 - (f0 / P.wp) * P.wp);  // tile start inside its first padded row
@@ -224,11 +252,38 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
       bool first = true;
       for (int grp = 0; grp < num_groups; ++grp, ++gs) {
         const uint32_t sstage = gs % kFlatStripStages, sphase = (gs / kFlatStripStages) & 1u;
-        const int slabs = P.c_blocks - grp * kFlatSlabsPerStrip < kFlatSlabsPerStrip ? P.c_blocks - grp * kFlatSlabsPerStrip
-                                                                                     : kFlatSlabsPerStrip;
+        const int slabs = P.c_blocks - grp * kSlabsPerStrip < kSlabsPerStrip ? P.c_blocks - grp * kSlabsPerStrip
+                                                                                     : kSlabsPerStrip;
         ptx::mbar_wait(&strip_full[sstage], sphase);
         ptx::tc_fence_after();
         const uint32_t strip = ptx::smem_u32(strip0 + sstage * strip_bytes);
+        if (RES) {
+          // Resident weights, 3x3 taps: no hand-shake per K-block and NO per-tap scalar work - the 9 x 4 MMAs of a slab are
+          // one straight-line block under a single elect (every descriptor is a warp-uniform base plus a compile-time
+          // multiple of the row pitch).  With the tap loop rolled (index arithmetic, elect and reconvergence per tap) the
+          // MMA warp needed ~410 cycles per tap against 128 tensor-core cycles (measured, profiles/r2_flat_resident.md).
+          const uint32_t a0 = strip + (uint32_t)lead * 128u;
+          const uint32_t wp128 = (uint32_t)P.wp * 128u;
+          const uint32_t b0 = ptx::smem_u32(bring) + (uint32_t)grp * kBBytes;
+          const uint32_t bstep = (uint32_t)P.c_blocks * kBBytes;  // weight tiles of consecutive taps
+          const uint32_t acc0 = (uint32_t)grp;                     // 0 only for the first slab of the tile
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t sa = a0 + (uint32_t)(tap / 3) * wp128 + (uint32_t)(tap % 3) * 128u;
+              const uint32_t sb = b0 + (uint32_t)tap * bstep;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = ptx::umma_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t db = ptx::umma_desc_sw128(sb + k * 32, 16, 1024);
+                ptx::mma_tf32(d_tmem, da, db, idesc, acc0 | (uint32_t)(tap | k));
+              }
+            }
+            ptx::mma_commit(&strip_empty[sstage]);
+          }
+          __syncwarp();
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / P.taps_s, s = tap - r * P.taps_s;
           const uint32_t row_off = (uint32_t)(lead + r * P.wp + s) * 128u;  // the tap is a shift by whole rows
@@ -295,16 +350,19 @@ int flat_load_driver() {
   return 0;
 }
 
-template <int BN, int NB>
+constexpr size_t kFlatSmemLimit = 232448 - 512;  // 227 KB per CTA minus the kernel's static barriers
+
+template <int BN, int NB, bool RES>
 int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) {
-  const size_t smem = strip_bytes_total + (size_t)NB * BN * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024;
-  if (smem > 232448) {
+  const size_t btiles = RES ? (size_t)P.c_blocks * P.taps_r * P.taps_s : (size_t)NB;
+  const size_t smem = strip_bytes_total + btiles * BN * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024;
+  if (smem > kFlatSmemLimit) {
     set_error("conv flat path: %zu bytes of shared memory needed", smem);
     return 1;
   }
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_flat_kernel<BN, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_flat_kernel<BN, NB, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv flat path: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return 1;
@@ -314,15 +372,17 @@ int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) 
   const int64_t tiles = ceil_div(P.m_flat, kFlatTileM) * ceil_div(P.k_out, BN);
   const int sms = sm_count();
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  launch_k(igemm_flat_kernel<BN, NB>, grid, kFlatThreads, smem, st, P);
+  launch_k(igemm_flat_kernel<BN, NB, RES>, grid, kFlatThreads, smem, st, P);
   return check_launch("igemm_flat_kernel");
 }
 
 }  // namespace
 
-static bool flat_enabled() {
-  static const int enabled = tuning_knob("TTB_FLAT", 0);
-  return enabled != 0;
+// TTB_FLAT (tuning build): -1 = default (the resident-weight variant where it applies), 0 = never, 1 = every eligible
+// problem (also the streamed variant, which is slower than the production kernel)
+static int flat_mode() {
+  static const int mode = tuning_knob("TTB_FLAT", -1);
+  return mode;
 }
 
 // geometry of one flat-shift problem: correlation of `in` (NHWC, c_in channels, zero-padded by pad) with r x s taps
@@ -336,14 +396,28 @@ static int flat_rows_max_of(const FlatProblem& g) {
   return (wp - 1 + kFlatTileM + g.s - 1 + wp - 1) / wp + (g.r - 1);
 }
 
+static size_t flat_strip_bytes(const FlatProblem& g, int slabs_per_strip) {
+  const int wp = g.w_in + 2 * g.pad_w;
+  return (size_t)kFlatStripStages * (((size_t)slabs_per_strip * flat_rows_max_of(g) * wp * 128 + 1023) & ~(size_t)1023);
+}
+
 static bool flat_geometry_ok(const FlatProblem& g) {
   if (g.c_in % 32 != 0 || g.k_out % 8 != 0 || g.r * g.s > kFlatMaxTaps || g.r * g.s < 2) return false;
   if (g.pad_h < 0 || g.pad_w < 0) return false;
   const int hp = g.h_in + 2 * g.pad_h, wp = g.w_in + 2 * g.pad_w;
   if (wp > 256 || hp - g.r + 1 != g.p_out || wp - g.s + 1 != g.q_out || g.p_out < 1 || g.q_out < 1) return false;
-  const size_t strips =
-      (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * flat_rows_max_of(g) * wp * 128 + 1023) & ~(size_t)1023);
-  return strips + 4 * 128 * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024 <= 232448;  // widest weight ring: 4 x (128 x 128 B)
+  return flat_strip_bytes(g, kFlatSlabsPerStrip) + 4 * 128 * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024 <= kFlatSmemLimit;  // widest weight ring: 4 x (128 x 128 B)
+}
+
+// resident-weight variant: one N tile (K <= 64) whose whole weight matrix fits next to two one-slab strip stages, and
+// enough tiles that loading the weights once per CTA (~150 KB) is amortised
+static bool flat_resident_ok(const FlatProblem& g) {
+  if (!flat_geometry_ok(g) || g.k_out > 64 || g.k_out < 33 || g.r != 3 || g.s != 3) return false;
+  const size_t wbytes = (size_t)(g.c_in / 32) * g.r * g.s * 64 * 128;
+  if (flat_strip_bytes(g, 1) + wbytes + 4 * 32 * kFlatStagePitch * 4 + 1024 > kFlatSmemLimit) return false;
+  const int hp = g.h_in + 2 * g.pad_h, wp = g.w_in + 2 * g.pad_w;
+  const int64_t tiles = ceil_div((int64_t)g.n * hp * wp, kFlatTileM);
+  return tiles >= 4 * (int64_t)sm_count();
 }
 
 // in: NHWC fp32 [n][h_in][w_in][c_in]; wmat: [k_out rows][r*s*c_in cols] fp32 with tap t's slice at column koff[t];
@@ -402,18 +476,21 @@ static int flat_run(const FlatProblem& g, const float* in, const float* wmat, co
   P.rows_max = flat_rows_max_of(g);
   P.m_flat = (int64_t)g.n * hp * wp;
   for (int t = 0; t < g.r * g.s; ++t) P.b_koff[t] = koff[t];
-  const size_t strips = (size_t)kFlatStripStages * (((size_t)kFlatSlabsPerStrip * P.rows_max * wp * 128 + 1023) & ~(size_t)1023);
+  if (flat_resident_ok(g)) return flat_launch<64, 6, true>(P, flat_strip_bytes(g, 1), st);
+  const size_t strips = flat_strip_bytes(g, kFlatSlabsPerStrip);
   switch (bn) {
-    case 128: return flat_launch<128, 4>(P, strips, st);
-    case 64: return flat_launch<64, 6>(P, strips, st);
-    default: return flat_launch<32, 6>(P, strips, st);
+    case 128: return flat_launch<128, 4, false>(P, strips, st);
+    case 64: return flat_launch<64, 6, false>(P, strips, st);
+    default: return flat_launch<32, 6, false>(P, strips, st);
   }
 }
 
 static bool flat_common_ok(const ttb_conv_desc* d) {
-  return flat_enabled() && d->math_mode == TTB_MATH_TF32 && d->groups == 1 && d->stride_h == 1 && d->stride_w == 1 &&
+  return flat_mode() != 0 && d->math_mode == TTB_MATH_TF32 && d->groups == 1 && d->stride_h == 1 && d->stride_w == 1 &&
          d->dil_h == 1 && d->dil_w == 1;
 }
+
+static bool flat_take(const FlatProblem& g) { return flat_mode() == 1 ? flat_geometry_ok(g) : flat_resident_ok(g); }
 
 static FlatProblem flat_fprop_problem(const ttb_conv_desc* d) {
   return FlatProblem{d->n, d->c, d->h, d->w, d->k, d->r, d->s, d->pad_h, d->pad_w, d->p, d->q};
@@ -424,9 +501,10 @@ static FlatProblem flat_dgrad_problem(const ttb_conv_desc* d) {
   return FlatProblem{d->n, d->k, d->p, d->q, d->c, d->r, d->s, d->r - 1 - d->pad_h, d->s - 1 - d->pad_w, d->h, d->w};
 }
 
-// 1 when TTB_FLAT=1 and the problem fits the prototype: TF32, stride 1, dilation 1, groups 1, C % 32 == 0, K % 8 == 0
-bool flat_fprop_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_geometry_ok(flat_fprop_problem(d)); }
-bool flat_dgrad_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_geometry_ok(flat_dgrad_problem(d)); }
+// 1 when the flat-shift kernel takes the problem: TF32, stride 1, dilation 1, groups 1, C % 32 == 0 and the
+// resident-weight variant applies (33..64 output channels, weights + strips fit in shared memory, >= 4 tiles per SM)
+bool flat_fprop_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_take(flat_fprop_problem(d)); }
+bool flat_dgrad_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_take(flat_dgrad_problem(d)); }
 
 // x: NHWC fp32, w: [K][R][S][C] fp32, y: dense NHWC fp32
 int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {

@@ -1,10 +1,11 @@
-"""First thing to run for the flat-shift prototype (csrc/conv_flat.cu) on a B200:
+"""Parity + timing of the flat-shift halo-tile kernels (csrc/conv_flat.cu) on a B200:
 
-    TTB_FLAT=1 python scripts/flat_check.py
+    python scripts/flat_check.py                                        # release library: resident variant where it applies
+    TORTTO_B200_LIB=tuning TTB_FLAT=0 python scripts/flat_check.py      # im2col kernel everywhere (the A/B baseline)
+    TORTTO_B200_LIB=tuning TTB_FLAT=1 python scripts/flat_check.py      # flat-shift everywhere eligible (streamed variant too)
 
-Compares fprop through the prototype (TF32, taken when TTB_FLAT=1 and the problem is stride-1 / dilation-1 with
-C % 32 == 0) with the exact fp32 direct kernels on the same inputs (tolerance 2e-3 of the tensor max), then times both
-the prototype and - in a second process with TTB_FLAT unset - the production kernel from a replayed CUDA graph."""
+Every case is compared with the exact fp32 direct kernels on the same inputs (tolerance 2e-3 of the tensor max) and
+timed from a replayed CUDA graph; the kernel variant each pass took is printed (1 im2col, 2 flat-shift resident)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -27,8 +28,7 @@ CASES = [  # n, c, h, w, k, ks, pad, bias
 
 
 def main():
-    flat = os.environ.get("TTB_FLAT") == "1"
-    print("TTB_FLAT =", os.environ.get("TTB_FLAT"), "(prototype path)" if flat else "(production path)")
+    print("library:", _cabi.LIB_PATH, " TTB_FLAT =", os.environ.get("TTB_FLAT"))
     rng = np.random.default_rng(0)
     worst = 0.0
     for n, c, h, w, k, ks, pad, bias in CASES:
@@ -45,7 +45,8 @@ def main():
         worst = max(worst, err)
         t = graph_time_us(lambda: ops.conv2d_fprop(x, wt, b, d))
         gf = 2.0 * n * d.p * d.q * k * c * ks * ks / 1e9
-        print(f"n{n} c{c} {h}x{w} k{k} f{ks} p{pad} bias={int(bias)}: rel-err {err:.2e} {'OK' if err < 2e-3 else 'FAIL'}"
+        var = [_cabi.load().ttb_conv2d_kernel_variant(ctypes.byref(d), p_) for p_ in (0, 1)]
+        print(f"n{n} c{c} {h}x{w} k{k} f{ks} p{pad} bias={int(bias)} variants fprop/dgrad {var}: rel-err {err:.2e} {'OK' if err < 2e-3 else 'FAIL'}"
               f"   {t:8.1f} us  {gf / t * 1e3:6.0f} TF/s", flush=True)
         # dgrad through the pre-packed entry points (what a backward sweep calls; the prototype hooks in there)
         lib = _cabi.load()
