@@ -197,6 +197,37 @@ int ttb_adam_step_multi(int n_tensors, float* const* params, const float* const*
                         float* const* exp_avg_sq, float* const* max_exp_avg_sq, const int64_t* sizes, const float* state,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, void* stream);
 
+/* ---- the ops between the conv stacks and the loss --------------------------------------------- */
+/* global average pool of an NHWC tensor over H, W (Mean, autograd/grad_fcn.py:1058-1093): y[n][c], dx = dy / (H*W) */
+int ttb_mean_hw_fwd(const float* x, float* y, int n, int hw, int c, void* stream);
+int ttb_mean_hw_bwd(const float* dy, float* dx, int n, int hw, int c, void* stream);
+/* C[m][n] (dense row-major) = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n] if bias != NULL); fp32 CUDA-core GEMM
+ * for the classifier head (Linear = Transpose + Mm + Add, nn/functional.py:54-63) and its two gradients */
+int ttb_matmul(const float* a, const float* b, const float* bias, float* c, int m, int n, int k, int64_t sam, int64_t sak,
+               int64_t sbk, int64_t sbn, void* stream);
+/* LogSoftmax over the last axis of [rows][cols] (autograd/grad_nn.py:373-392) */
+int ttb_log_softmax_fwd(const float* x, float* y, int rows, int cols, void* stream);
+int ttb_log_softmax_bwd(const float* dy, const float* y, float* dx, int rows, int cols, void* stream);
+/* NLL loss (autograd/grad_nn.py:287-349): reduction 0 none (out[rows]), 1 mean, 2 sum (out[1]); rows whose target ==
+ * ignore_index do not contribute; *count (device float) = number of contributing rows, consumed by the backward of mean */
+int ttb_nll_loss_fwd(const float* logp, const int64_t* target, int rows, int cols, int64_t ignore_index, int reduction,
+                     float* out, float* count, void* stream);
+int ttb_nll_loss_bwd(const float* g, const int64_t* target, int rows, int cols, int64_t ignore_index, int reduction,
+                     const float* count, float* dx, void* stream);
+/* BCE with logits (autograd/grad_nn.py:236-285): reduction 0 none (out[n]), 1 mean, 2 sum (out[1], fixed-order two-stage
+ * sum in `workspace` of ttb_bce_logits_workspace_size() bytes); backward dx = (sigmoid(x) - t) * g * scale with g a
+ * device scalar (g_per_elem == 0) or per element */
+size_t ttb_bce_logits_workspace_size(void);
+int ttb_bce_logits_fwd(const float* x, const float* t, int64_t n, int reduction, float* out, void* workspace, void* stream);
+int ttb_bce_logits_bwd(const float* x, const float* t, const float* g, int g_per_elem, float scale, int64_t n, float* dx,
+                       void* stream);
+/* channel-range copy between NHWC tensors viewed as [rows][channels]: dst[r][dst_off + c] = src[r][src_off + c], c < c_copy
+ * (Cat along the channel axis and its backward split, autograd/grad_fcn.py:881-904: UNet skip connections) */
+int ttb_copy_channels(const float* src, float* dst, int64_t rows, int c_src, int c_dst, int src_off, int dst_off, int c_copy,
+                      void* stream);
+/* y[r][c] += bias[c] in place (the bias of ConvTranspose2d, whose contraction is a dgrad pass without a bias epilogue) */
+int ttb_add_bias(float* y, const float* bias, int64_t rows, int c, void* stream);
+
 /* ---- small-message all-reduce over NVLink peer memory (SyncBN statistics; one process per GPU) ------------------- */
 /* cudaMalloc a zeroed communication buffer and export its CUDA-IPC handle (64 bytes) */
 int ttb_comm_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);

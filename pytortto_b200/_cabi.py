@@ -76,6 +76,18 @@ _PROTOS = {
     "ttb_adam_advance": (c_int, [_F, c_float, c_float, c_void_p]),
     "ttb_adam_step_multi": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _F, c_float, c_float,
                                     c_float, c_float, c_float, c_int, c_void_p]),
+    "ttb_mean_hw_fwd": (c_int, [_F, _F, c_int, c_int, c_int, c_void_p]),
+    "ttb_mean_hw_bwd": (c_int, [_F, _F, c_int, c_int, c_int, c_void_p]),
+    "ttb_matmul": (c_int, [_F, _F, _F, _F, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "ttb_log_softmax_fwd": (c_int, [_F, _F, c_int, c_int, c_void_p]),
+    "ttb_log_softmax_bwd": (c_int, [_F, _F, _F, c_int, c_int, c_void_p]),
+    "ttb_nll_loss_fwd": (c_int, [_F, _F, c_int, c_int, c_int64, c_int, _F, _F, c_void_p]),
+    "ttb_nll_loss_bwd": (c_int, [_F, _F, c_int, c_int, c_int64, c_int, _F, _F, c_void_p]),
+    "ttb_bce_logits_workspace_size": (c_size_t, []),
+    "ttb_bce_logits_fwd": (c_int, [_F, _F, c_int64, c_int, _F, _F, c_void_p]),
+    "ttb_bce_logits_bwd": (c_int, [_F, _F, _F, c_int, c_float, c_int64, _F, c_void_p]),
+    "ttb_copy_channels": (c_int, [_F, _F, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ttb_add_bias": (c_int, [_F, c_int64, c_int, c_void_p]) if False else (c_int, [_F, _F, c_int64, c_int, c_void_p]),
     "ttb_comm_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "ttb_comm_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "ttb_comm_close": (c_int, [c_void_p]),

@@ -137,15 +137,21 @@ class Mean(Function):
         xt0, = inputs
         xd0 = xt0.data
         dims = _norm_dims(params['dim'], xd0.ndim)
-        yd0 = cparray(xd0.t.mean(dim=dims, keepdim=params['keepdim']))
         ctx.params['shape'] = xd0.shape
         ctx.params['dims'] = dims
+        ctx.params['hw_kernel'] = xd0.ndim == 4 and dims == (2, 3) and xd0.t.dtype == torch.float32 and xd0.size > 0
+        if ctx.params['hw_kernel']:  # global average pooling of an NHWC activation: one kernel
+            yd0 = ops.mean_hw(xd0, params['keepdim'])
+        else:
+            yd0 = cparray(xd0.t.mean(dim=dims, keepdim=params['keepdim']))
         return build_links(yd0, grad_fn=ctx)
 
     @staticmethod
     def backward(ctx, *grad_outputs):
         gd0, = grad_outputs
         shape, dims = ctx.params['shape'], ctx.params['dims']
+        if ctx.params['hw_kernel'] and gd0.t.dtype == torch.float32:
+            return ops.mean_hw_bwd(gd0, shape)
         count = 1
         for d in dims:
             count *= shape[d]
@@ -207,6 +213,35 @@ class Mm(Function):
         return g0, g1
 
 
+class Linear(Function):
+    """y = x @ W^T (+ b) as ONE node (the reference builds Transpose + Mm + Add, nn/functional.py:54-63): forward and
+    each of the three gradients is one fp32 CUDA-core GEMM / column-sum kernel (ttb_matmul, ttb_bias_grad).
+    inputs = (x (M, K), weight (N, K), bias (N,) | None)."""
+
+    @staticmethod
+    def forward(ctx, *inputs, **params):
+        xt0, xt1, xt2 = inputs
+        xd0, xd1 = xt0.data, xt1.data
+        m, k = xd0.shape
+        n = xd1.shape[0]
+        if xd1.shape[1] != k:
+            raise RuntimeError(f'mat1 and mat2 shapes cannot be multiplied ({m}x{k} and {xd1.shape[1]}x{n})')
+        yd0 = ops.matmul(xd0, xd1, None if xt2 is None else xt2.data, m, n, k, k, 1, 1, k)
+        ctx.save_for_backward(xt0, xt1)
+        return build_links(yd0, grad_fn=ctx)
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        gd0, = grad_outputs
+        xd0, xd1 = ctx.saved_tensors
+        m, k = xd0.shape
+        n = xd1.shape[0]
+        g0 = ops.matmul(gd0, xd1, None, m, k, n, n, 1, k, 1) if ctx.needs_input_grad[0] else None      # g @ W
+        g1 = ops.matmul(gd0, xd0, None, n, k, m, 1, n, k, 1) if ctx.needs_input_grad[1] else None      # g^T @ x
+        g2 = ops.colsum(gd0) if ctx.needs_input_grad[2] else None
+        return g0, g1, g2
+
+
 class Exp(Function):
     @staticmethod
     def forward(ctx, *inputs, **params):
@@ -228,14 +263,22 @@ class Cat(Function):
     @staticmethod
     def forward(ctx, *inputs, **params):
         dim = params['dim']
-        arrs = [t.data.t for t in inputs]
-        out = torch.cat(arrs, dim=dim)
-        ctx.params['sizes'] = [a.shape[dim] for a in arrs]
+        datas = [t.data for t in inputs]
+        ctx.params['sizes'] = [a.shape[dim] for a in datas]
+        nd = datas[0].ndim
+        ctx.params['channel_kernel'] = (nd == 4 and dim % nd == 1 and all(a.__class__ is cparray and a.ndim == 4 and
+                                        a.t.dtype == torch.float32 and a.shape[0] == datas[0].shape[0] and
+                                        a.shape[2:] == datas[0].shape[2:] for a in datas) and datas[0].size > 0)
+        if ctx.params['channel_kernel']:  # NHWC channel concatenation (UNet skip connections): one strided copy per input
+            return build_links(ops.cat_channels(datas), grad_fn=ctx)
+        out = torch.cat([a.t for a in datas], dim=dim)
         return build_links(cparray(out), grad_fn=ctx)
 
     @staticmethod
     def backward(ctx, *grad_outputs):
         gd0, = grad_outputs
+        if ctx.params['channel_kernel'] and gd0.t.dtype == torch.float32:
+            return tuple(ops.split_channels(gd0, ctx.params['sizes'], ctx.needs_input_grad))
         parts = torch.split(gd0.t, ctx.params['sizes'], dim=ctx.params['dim'])
         return tuple(cparray(p.contiguous(memory_format=torch.channels_last) if p.dim() == 4 else p.contiguous())
                      if need else None for p, need in zip(parts, ctx.needs_input_grad))
@@ -249,9 +292,13 @@ class LogSoftmax(Function):
         xt0, = inputs
         x = xt0.data.t
         dim = params['dim']
-        aug = x - x.max(dim=dim, keepdim=True).values
-        y = aug - torch.log(torch.sum(torch.exp(aug), dim=dim, keepdim=True))
-        yt0 = build_links(cparray(y), grad_fn=ctx)
+        ctx.params['row_kernel'] = x.dim() == 2 and dim % 2 == 1 and x.dtype == torch.float32 and x.numel() > 0
+        if ctx.params['row_kernel']:
+            yt0 = build_links(ops.log_softmax(xt0.data), grad_fn=ctx)
+        else:
+            aug = x - x.max(dim=dim, keepdim=True).values
+            y = aug - torch.log(torch.sum(torch.exp(aug), dim=dim, keepdim=True))
+            yt0 = build_links(cparray(y), grad_fn=ctx)
         ctx.save_for_backward(yt0)
         return yt0
 
@@ -259,6 +306,8 @@ class LogSoftmax(Function):
     def backward(ctx, *grad_outputs):
         gd0, = grad_outputs
         yd0, = ctx.saved_tensors
+        if ctx.params['row_kernel'] and gd0.t.dtype == torch.float32:
+            return ops.log_softmax_bwd(gd0, yd0)
         g = gd0.t
         return cparray(g - g.sum(dim=ctx.params['dim'], keepdim=True) * torch.exp(yd0.t))
 
@@ -277,6 +326,14 @@ class NllLoss(Function):
         tgt = target.data.t if target.data.__class__ is cparray else torch.from_numpy(np.asarray(target.data)).to(x.device)
         tgt = tgt.long()
         ignore_index = params.get('ignore_index', -100)
+        if reduction not in ('none', 'mean', 'sum'):
+            raise ValueError(f'{reduction} is not a valid value for reduction')
+        ctx.params['kernel'] = x.dim() == 2 and x.dtype == torch.float32 and x.numel() > 0
+        if ctx.params['kernel']:  # one fixed-order reduction kernel; the row count of the mean stays on the device
+            tgt = tgt.contiguous()
+            y, count = ops.nll_loss(xt0.data, tgt, ignore_index, reduction)
+            ctx.params.update(tgt=tgt, count=count, shape=tuple(x.shape), ignore_index=ignore_index)
+            return build_links(y, grad_fn=ctx)
         picked = -x.gather(1, tgt.clamp(min=0).unsqueeze(1)).squeeze(1)
         w = None
         if ignore_index >= 0:
@@ -304,6 +361,9 @@ class NllLoss(Function):
     @staticmethod
     def backward(ctx, *grad_outputs):
         gd0, = grad_outputs
+        if ctx.params['kernel']:
+            return ops.nll_loss_bwd(gd0, ctx.params['tgt'], ctx.params['shape'], ctx.params['ignore_index'],
+                                    ctx.params['reduction'], ctx.params['count'])
         g = gd0.t
         if ctx.params['reduction'] == 'mean':
             g = g / ctx.params['N']
@@ -325,19 +385,17 @@ class BinaryCrossEntropyWithLogits(Function):
         if params.get('weight') is not None or params.get('pos_weight') is not None:
             raise NotImplementedError("bce_with_logits weights are not on the accelerated path yet")
         x, t = xt0.data.t, xt1.data.t
-        loss = torch.clamp(x, min=0) - x * t + torch.log1p(torch.exp(-torch.abs(x)))
         red = params['reduction']
-        y = loss.mean() if red == 'mean' else (loss.sum() if red == 'sum' else loss)
+        if red not in ('none', 'mean', 'sum'):
+            raise ValueError(f'{red} is not a valid value for reduction')
+        if x.shape != t.shape:
+            raise ValueError(f'Target size ({tuple(t.shape)}) must be the same as input size ({tuple(x.shape)})')
         ctx.save_for_backward(xt0, xt1)
-        return build_links(cparray(y), grad_fn=ctx)
+        return build_links(ops.bce_logits(xt0.data, xt1.data, red), grad_fn=ctx)
 
     @staticmethod
     def backward(ctx, *grad_outputs):
         gd0, = grad_outputs
         xd0, xd1 = ctx.saved_tensors
-        x, t = xd0.t, xd1.t
-        g = (torch.sigmoid(x) - t) * gd0.t
-        if ctx.params['reduction'] == 'mean':
-            g = g / x.numel()
-        g0 = cparray(g) if ctx.needs_input_grad[0] else None
+        g0 = ops.bce_logits_bwd(xd0, xd1, gd0, ctx.params['reduction']) if ctx.needs_input_grad[0] else None
         return g0, None

@@ -1,6 +1,6 @@
 """`tortto.nn.functional` for the conv-net path - the entry points kept verbatim from the reference
 (/root/reference/src/tortto/nn/functional.py:6-11, 54-63, 80-121): same names, argument order, defaults."""
-from ..autograd.grad_fcn import (BinaryCrossEntropyWithLogits, LogSoftmax, NllLoss, View)
+from ..autograd.grad_fcn import (BinaryCrossEntropyWithLogits, Linear, LogSoftmax, NllLoss, View)
 from ..autograd.grad_nn import BatchNorm, BatchNormRelu, Convolution, MaxPool2DWithIndices, Relu, TransposedConvolution
 from ..VariableFunctions import matmul
 
@@ -57,6 +57,8 @@ def batch_norm_relu(input, running_mean, running_var, weight=None, bias=None, tr
 
 
 def linear(input, weight, bias):
+    if input.ndim == 2 and weight.ndim == 2 and input.is_cuda and weight.is_cuda and input.dtype == weight.dtype == 'float32':
+        return Linear.apply(input, weight, bias)  # one fused node: x @ W^T + b
     output = matmul(input, weight.T)
     return output if bias is None else output + bias
 

@@ -360,9 +360,124 @@ def bias_grad(dy):
 
 def add_bias_(y, bias):
     """y (N,K,P,Q) += bias[:, None, None] in place (used where the bias cannot ride the conv epilogue)."""
-    y.t.add_(bias.t.view(1, -1, 1, 1))
+    n, k, p, q = y.shape
+    _cabi.call("ttb_add_bias", _ptr(y), _ptr(bias), n * p * q, k, current_stream_ptr())
     y._h = None
     return y
+
+
+# ---------------------------------------------------------------------------------------------------------
+# head ops: global mean, Linear, LogSoftmax, NLL, BCE-with-logits, channel cat / split
+# ---------------------------------------------------------------------------------------------------------
+def _f32_dense(*arrays):
+    return all(a is not None and a.__class__ is cparray and a.t.dtype == torch.float32 for a in arrays)
+
+
+def mean_hw(x, keepdim):
+    n, c, h, w = x.shape
+    y = new_f32((n, c, 1, 1) if keepdim else (n, c))
+    _cabi.call("ttb_mean_hw_fwd", _ptr(x), _ptr(y), n, h * w, c, current_stream_ptr())
+    return y
+
+
+def mean_hw_bwd(dy, shape):
+    n, c, h, w = shape
+    dx = new_f32(shape)
+    _cabi.call("ttb_mean_hw_bwd", _ptr(dy), _ptr(dx), n, h * w, c, current_stream_ptr())
+    return dx
+
+
+def matmul(a, b, bias, m, n, k, sam, sak, sbk, sbn):
+    c = new_f32((m, n))
+    _cabi.call("ttb_matmul", _ptr(a), _ptr(b), _ptr(bias), _ptr(c), m, n, k, sam, sak, sbk, sbn, current_stream_ptr())
+    return c
+
+
+def colsum(g):
+    """(M, N) -> (N,)"""
+    m, n = g.shape
+    out = new_f32((n,))
+    _cabi.call("ttb_bias_grad", _ptr(g), _ptr(out), m, n, current_stream_ptr())
+    return out
+
+
+def log_softmax(x):
+    rows, cols = x.shape
+    y = new_f32((rows, cols))
+    _cabi.call("ttb_log_softmax_fwd", _ptr(x), _ptr(y), rows, cols, current_stream_ptr())
+    return y
+
+
+def log_softmax_bwd(dy, y):
+    rows, cols = y.shape
+    dx = new_f32((rows, cols))
+    _cabi.call("ttb_log_softmax_bwd", _ptr(dy), _ptr(y), _ptr(dx), rows, cols, current_stream_ptr())
+    return dx
+
+
+_REDUCTIONS = {"none": 0, "mean": 1, "sum": 2}
+
+
+def nll_loss(logp, target, ignore_index, reduction):
+    rows, cols = logp.shape
+    out = new_f32((rows,) if reduction == "none" else ())
+    count = new_f32(())
+    _cabi.call("ttb_nll_loss_fwd", _ptr(logp), target.data_ptr(), rows, cols, int(ignore_index), _REDUCTIONS[reduction],
+               _ptr(out), _ptr(count), current_stream_ptr())
+    return out, count
+
+
+def nll_loss_bwd(g, target, shape, ignore_index, reduction, count):
+    rows, cols = shape
+    dx = new_f32((rows, cols))
+    _cabi.call("ttb_nll_loss_bwd", _ptr(g), target.data_ptr(), rows, cols, int(ignore_index), _REDUCTIONS[reduction],
+               _ptr(count), _ptr(dx), current_stream_ptr())
+    return dx
+
+
+def bce_logits(x, t, reduction):
+    n = x.size
+    out = cparray(empty_device(x.shape)) if reduction == "none" else new_f32(())
+    ws = torch.empty(int(_cabi.load().ttb_bce_logits_workspace_size()), dtype=torch.uint8, device=x.t.device)
+    _cabi.call("ttb_bce_logits_fwd", _ptr(x), _ptr(t), n, _REDUCTIONS[reduction], _ptr(out), ws.data_ptr(), current_stream_ptr())
+    return out
+
+
+def bce_logits_bwd(x, t, g, reduction):
+    n = x.size
+    dx = cparray(empty_device(x.shape))
+    _cabi.call("ttb_bce_logits_bwd", _ptr(x), _ptr(t), _ptr(g), int(reduction == "none"),
+               1.0 / n if reduction == "mean" else 1.0, n, _ptr(dx), current_stream_ptr())
+    return dx
+
+
+def cat_channels(arrays):
+    """NHWC arrays of equal (N, H, W) -> one array with the channels concatenated (logical dim 1)"""
+    n, _, h, w = arrays[0].shape
+    ctot = sum(a.shape[1] for a in arrays)
+    out = new_f32((n, ctot, h, w))
+    off = 0
+    st = current_stream_ptr()
+    for a in arrays:
+        c = a.shape[1]
+        _cabi.call("ttb_copy_channels", _ptr(a), _ptr(out), n * h * w, c, ctot, 0, off, c, st)
+        off += c
+    return out
+
+
+def split_channels(g, sizes, needed):
+    n, ctot, h, w = g.shape
+    outs, off = [], 0
+    st = current_stream_ptr()
+    for c, need in zip(sizes, needed):
+        if need:
+            o = new_f32((n, c, h, w))
+            _cabi.call("ttb_copy_channels", _ptr(g), _ptr(o), n * h * w, ctot, c, off, 0, c, st)
+            outs.append(o)
+        else:
+            outs.append(None)
+        off += c
+    return outs
 
 
 # ---------------------------------------------------------------------------------------------------------

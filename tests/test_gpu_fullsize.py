@@ -1,13 +1,25 @@
 """GPU: the HEADLINE configuration (BASELINE.json configs[1]: preact_resnet18, batch 256, 3x32x32) held to the numpy
 oracle (oracle/resnet_oracle.StepOracle = the reference's algorithm, pinned by tests/test_oracle_golden.py), not to
-itself:
+itself.
 
-  * exact-fp32 mode: loss, log-probs, EVERY parameter gradient (max-abs error / tensor max <= 5e-4) and the BatchNorm
-    running statistics after the step;
-  * TF32 and bf16 tensor-core modes: loss at the north-star tolerance (2e-3 / 1e-2) and per-tensor gradient error
-    bounds that are 3x the values measured on B200 (printed per tensor by the test; DESIGN.md section 4 lists them).
+What "equal" can mean at this size (measured, scripts/relu_flip_analysis.py, profiles/r2_relu_flip_analysis.txt): the
+reference's OWN fp32 arithmetic is 2e-3 (rel-L2) / up to 4e-2 (max-abs / tensor max) away from a float64 evaluation of
+the same formulas on every gradient upstream of the last block.  The cause is not accumulated rounding but single ReLU
+decisions: one pre-activation within 1e-7 of zero lands on the other side, its whole gradient element appears or
+disappears, and that one element is ~2e-3 of the L2 norm of the heavy-tailed gradient field.  TF32 / bf16 operand
+rounding moves ~1e-3 / ~8e-3 of all pre-activations across zero, and the gradient error grows like the square root of
+the number of flips (~0.1 / ~0.3) - in the reference's algorithm with rounded operands exactly as on the GPU.  So:
 
-The oracle step takes ~30 s on the box's host cores and is computed once per module."""
+  * exact-fp32 mode: loss, log-probs and BatchNorm running statistics (forward: no decisions differ) at 1e-5 / 1e-4 /
+    2e-5; EVERY parameter gradient within max(5e-4, 3 x the distance of the reference's own fp32 result from the
+    float64 truth) of that truth - the implementation is held to the reference's own accuracy, tensor by tensor;
+  * TF32 / bf16 modes: loss and log-probs at the north-star tolerances (2e-3 / 1e-2); per-tensor gradient bounds at
+    3x / 2x the values measured on B200 (listing printed by the test, committed as profiles/r2_fullsize_parity.txt).
+    What catches a wrong tap or a mis-padded K-block in ONE layer is the layer-wise replay of all 20 convolutions of
+    this network at batch 256 on recorded activations (tests/test_gpu_models.py::test_preact_resnet18_layerwise_*),
+    per op at 2e-3 / 1e-2 where no ReLU decision is involved.
+
+The two oracle steps (fp32 and float64) take ~1.5 min on the box's host cores and are computed once per module."""
 import numpy as np
 import pytest
 
@@ -41,7 +53,10 @@ def oracle_step():
     params0 = {k: np.array(p.data, copy=True) for k, p in net.named_parameters()}
     orc = StepOracle(LAYERS, CHANNELS, {k: v.copy() for k, v in params0.items()})
     loss, logp, grads = orc.forward_backward(x, lab)
-    return dict(x=x, lab=lab, params0=params0, loss=float(loss), logp=logp, grads=grads, buffers=orc.buffers)
+    o64 = StepOracle(LAYERS, CHANNELS, {k: v.astype(np.float64) for k, v in params0.items()}, dtype=np.float64)
+    loss64, logp64, grads64 = o64.forward_backward(x.astype(np.float64), lab)
+    return dict(x=x, lab=lab, params0=params0, loss=float(loss), logp=logp, grads=grads, buffers=orc.buffers,
+                loss64=float(loss64), logp64=logp64, grads64=grads64)
 
 
 def _gpu_step(mode, o):
@@ -71,13 +86,19 @@ def test_full_size_step_fp32_vs_oracle(oracle_step):
     msg, rel = report("logp", logp, o["logp"])
     print(msg)
     assert rel <= 1e-4, msg
-    worst = 0.0
+    worst, worst_ref, bad = 0.0, 0.0, []
     for k, g in grads.items():
-        msg, rel = report(f"grad {k}", g, o["grads"][k])
-        worst = max(worst, rel)
-        assert rel <= 5e-4, msg
-    print(f"[fp32 vs oracle, batch {BATCH}] loss {loss:.6f} (oracle {o['loss']:.6f}), worst gradient rel-err {worst:.3e} "
-          f"over {len(grads)} tensors (gate 5e-4)")
+        truth = o["grads64"][k]
+        _, ours = report(f"grad {k}", g, truth)
+        _, ref = report(f"oracle fp32 grad {k}", o["grads"][k], truth)
+        bound = max(5e-4, 3.0 * ref)
+        print(f"  [fp32] {k}: vs float64 truth - ours {ours:.3e}, the reference's fp32 algorithm {ref:.3e}, bound {bound:.3e}")
+        worst, worst_ref = max(worst, ours), max(worst_ref, ref)
+        if ours > bound:
+            bad.append((k, ours, ref))
+    print(f"[fp32 vs float64 oracle, batch {BATCH}] loss {loss:.6f} (oracle fp32 {o['loss']:.6f}, float64 {o['loss64']:.6f}); worst "
+          f"gradient error over {len(grads)} tensors: ours {worst:.3e}, reference fp32 algorithm {worst_ref:.3e}")
+    assert not bad, bad
     sd = net.state_dict()
     worst_rs = 0.0
     for k, v in o["buffers"].items():
@@ -90,10 +111,11 @@ def test_full_size_step_fp32_vs_oracle(oracle_step):
     print(f"[fp32 vs oracle] worst BatchNorm running-statistic rel-err {worst_rs:.3e} (gate 2e-5)")
 
 
-# Per-tensor gradient gates of the tensor-core modes = 3 x the worst value measured on B200 for this exact step
-# (profiles/r2_fullsize_parity.txt holds the per-tensor listing the test prints): (max-abs / tensor max, rel-L2).
-# A wrong filter tap or a mis-padded K-block in ONE layer moves that layer's gradient by O(1) and trips these.
-GATES = {"tf32": dict(loss=2e-3, maxabs=3e-2, l2=3e-2), "bf16": dict(loss=1e-2, maxabs=1e-1, l2=1e-1)}
+# Per-tensor gradient gates of the tensor-core modes = 3 x (tf32) / 2 x (bf16) the worst value measured on B200 for this
+# exact step (measured: tf32 0.119 / 0.112, bf16 0.314 / 0.266 as max-abs / tensor max and rel-L2;
+# profiles/r2_fullsize_parity.txt holds the per-tensor listing the test prints).  The error is ReLU-decision noise (module
+# docstring); single-layer correctness is held at 2e-3 / 1e-2 by the layer-wise replay in tests/test_gpu_models.py.
+GATES = {"tf32": dict(loss=2e-3, maxabs=0.36, l2=0.34), "bf16": dict(loss=1e-2, maxabs=0.63, l2=0.55)}
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
@@ -101,13 +123,13 @@ def test_full_size_step_tensor_modes_vs_oracle(oracle_step, mode):
     o = oracle_step
     gate = GATES[mode]
     _, loss, logp, grads = _gpu_step(mode, o)
-    assert abs(loss - o["loss"]) <= gate["loss"] * max(1.0, abs(o["loss"])), (loss, o["loss"])
-    _, rel_logp = report("logp", logp, o["logp"])
+    assert abs(loss - o["loss64"]) <= gate["loss"] * max(1.0, abs(o["loss64"])), (loss, o["loss64"])
+    _, rel_logp = report("logp", logp, o["logp64"])
     worst, worst_l2, names = 0.0, 0.0, ("", "")
     for k, g in grads.items():
         assert np.isfinite(g).all(), k
-        _, rel = report(k, g, o["grads"][k])
-        l2 = _rel_l2(g, o["grads"][k])
+        _, rel = report(k, g, o["grads64"][k])
+        l2 = _rel_l2(g, o["grads64"][k])
         print(f"  [{mode}] {k}: max-abs/max {rel:.3e}  rel-L2 {l2:.3e}")
         if rel > worst:
             worst, names = rel, (k, names[1])
@@ -115,5 +137,5 @@ def test_full_size_step_tensor_modes_vs_oracle(oracle_step, mode):
             worst_l2, names = l2, (names[0], k)
     print(f"[{mode} vs oracle, batch {BATCH}] loss {loss:.6f} (oracle {o['loss']:.6f}, rel {abs(loss - o['loss']) / abs(o['loss']):.2e}), "
           f"logp rel {rel_logp:.3e}, worst grad max-abs/max {worst:.3e} ({names[0]}), worst rel-L2 {worst_l2:.3e} ({names[1]})")
-    assert rel_logp <= gate["loss"] * 5
+    assert rel_logp <= gate["loss"]
     assert worst <= gate["maxabs"] and worst_l2 <= gate["l2"], (worst, worst_l2, names)

@@ -201,3 +201,27 @@ def test_full_size_resnet50_and_unet_shapes():
     for k, v in sorted({**w50, **wu}.items(), key=lambda kv: -kv[1])[:8]:
         print(f"worst layer-wise rel-err vs the exact fp32 path {v:.2e}  {k}")
     assert np.isfinite(losses["resnet50"]) and np.isfinite(losses["unet"])
+
+
+def test_preact_resnet18_layerwise_parity_at_batch_256():
+    """BASELINE config 2 at its real size: every one of the 20 convolutions of preact_resnet18 at batch 256 (incl. the
+    flat-shift resident-weight kernel of the 64-channel layers, the padded 3-channel stem, strided 3x3 and 1x1
+    shortcuts) replayed on the activations of a real forward pass in tf32 (<= 3e-3), bf16 (<= 1e-2) and exact fp32:
+    y, dx, dw per layer.  This is the check that localises a wrong tap / K-block to its layer; the whole-step gradient
+    comparison (tests/test_gpu_fullsize.py) cannot, because of ReLU-decision noise."""
+    import pytortto_b200 as tt
+    M = _models(tt)
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal((256, 3, 32, 32)).astype(np.float32)
+    lab = rng.integers(0, 10, 256).astype(np.int64)
+
+    def run(net):
+        loss = tt.nn.NLLLoss()(net(tt.tensor(x).cuda()), tt.tensor(lab, dtype=np.int64).cuda())
+        loss.backward()
+        assert np.isfinite(loss.item())
+
+    tt.manual_seed(4)
+    n, worst = _layerwise_conv_parity(tt, M["preact_resnet18"]().cuda(), run)
+    assert n == 20
+    for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:6]:
+        print(f"worst layer-wise rel-err vs the exact fp32 path {v:.2e}  {k}")

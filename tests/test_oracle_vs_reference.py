@@ -64,6 +64,24 @@ for cls_name, decoupled, amsgrad in (("Adam", False, False), ("Adam", False, Tru
         for a, b in zip(op, ref_p):
             assert rel(a, b.data) < 2e-6, (cls_name, amsgrad, step, rel(a, b.data))
 print("ADAM OK")
+# loss functions with reductions / ignore_index (autograd/grad_nn.py:236-349) vs the oracle's restatements
+F = tt.nn.functional
+for red in ("mean", "sum", "none"):
+    x = rng.standard_normal((6, 3, 5, 4)).astype(np.float32) * 3; t = (rng.random((6, 3, 5, 4)) < 0.5).astype(np.float32)
+    xt = tt.tensor(x, requires_grad=True)
+    y = F.binary_cross_entropy_with_logits(xt, tt.tensor(t), reduction=red)
+    g = rng.standard_normal(np.shape(y.data)).astype(np.float32)
+    y.backward(tt.tensor(g))
+    assert rel(O.bce_with_logits_forward(x, t, red), y.data) < 1e-6 and rel(O.bce_with_logits_backward(g, x, t, red), xt.grad) < 1e-6, red
+    for ign in (-100, 2):
+        lp = O.log_softmax_forward(rng.standard_normal((9, 5)).astype(np.float32)); tg = rng.integers(0, 5, 9)
+        lt = tt.tensor(lp, requires_grad=True)
+        y = F.nll_loss(lt, tt.tensor(tg, dtype=np.int64), ignore_index=ign, reduction=red)
+        g = rng.standard_normal(np.shape(y.data)).astype(np.float32)
+        y.backward(tt.tensor(g.copy()))
+        yo, n = O.nll_loss_forward_ex(lp, tg, ign, red)
+        assert rel(yo, y.data) < 1e-6 and rel(O.nll_loss_backward_ex(g, lp, tg, ign, red, n), lt.grad) < 1e-6, (red, ign)
+print("LOSSES OK")
 '''
 
 
@@ -71,4 +89,4 @@ print("ADAM OK")
 def test_oracle_matches_live_reference():
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "WORST" in r.stdout and "ADAM OK" in r.stdout
+    assert "WORST" in r.stdout and "ADAM OK" in r.stdout and "LOSSES OK" in r.stdout
