@@ -11,8 +11,9 @@ rounding moves ~1e-3 / ~8e-3 of all pre-activations across zero, and the gradien
 the number of flips (~0.1 / ~0.3) - in the reference's algorithm with rounded operands exactly as on the GPU.  So:
 
   * exact-fp32 mode: loss, log-probs and BatchNorm running statistics (forward: no decisions differ) at 1e-5 / 1e-4 /
-    2e-5; EVERY parameter gradient within max(5e-4, 3 x the distance of the reference's own fp32 result from the
-    float64 truth) of that truth - the implementation is held to the reference's own accuracy, tensor by tensor;
+    2e-5; EVERY parameter gradient within 3 x the largest distance the reference's own fp32 result shows from the
+    float64 truth on any tensor of the step (which decisions flip differs between two summation orders, so the
+    comparison is per step, not per tensor) - the implementation is held to the reference's own accuracy;
   * TF32 / bf16 modes: loss and log-probs at the north-star tolerances (2e-3 / 1e-2); per-tensor gradient bounds at
     3x / 2x the values measured on B200 (listing printed by the test, committed as profiles/r2_fullsize_parity.txt).
     What catches a wrong tap or a mis-padded K-block in ONE layer is the layer-wise replay of all 20 convolutions of
@@ -86,18 +87,22 @@ def test_full_size_step_fp32_vs_oracle(oracle_step):
     msg, rel = report("logp", logp, o["logp"])
     print(msg)
     assert rel <= 1e-4, msg
-    worst, worst_ref, bad = 0.0, 0.0, []
+    # WHICH ~20 of the 1.4e8 ReLU decisions land on the other side is a property of each arithmetic's summation order, so
+    # the two fp32 results deviate from the truth on different tensors: each of our tensors is held to 3 x the LARGEST
+    # deviation the reference's own fp32 arithmetic shows on any tensor of this step (both metrics)
+    ours, ref = {}, {}
     for k, g in grads.items():
         truth = o["grads64"][k]
-        _, ours = report(f"grad {k}", g, truth)
-        _, ref = report(f"oracle fp32 grad {k}", o["grads"][k], truth)
-        bound = max(5e-4, 3.0 * ref)
-        print(f"  [fp32] {k}: vs float64 truth - ours {ours:.3e}, the reference's fp32 algorithm {ref:.3e}, bound {bound:.3e}")
-        worst, worst_ref = max(worst, ours), max(worst_ref, ref)
-        if ours > bound:
-            bad.append((k, ours, ref))
+        ours[k] = (report(k, g, truth)[1], _rel_l2(g, truth))
+        ref[k] = (report(k, o["grads"][k], truth)[1], _rel_l2(o["grads"][k], truth))
+        print(f"  [fp32] {k}: vs float64 truth (max-abs/max, rel-L2) - ours {ours[k][0]:.3e} {ours[k][1]:.3e}, the reference's fp32 "
+              f"algorithm {ref[k][0]:.3e} {ref[k][1]:.3e}")
+    ref_max, ref_l2 = max(v[0] for v in ref.values()), max(v[1] for v in ref.values())
+    our_max, our_l2 = max(v[0] for v in ours.values()), max(v[1] for v in ours.values())
     print(f"[fp32 vs float64 oracle, batch {BATCH}] loss {loss:.6f} (oracle fp32 {o['loss']:.6f}, float64 {o['loss64']:.6f}); worst "
-          f"gradient error over {len(grads)} tensors: ours {worst:.3e}, reference fp32 algorithm {worst_ref:.3e}")
+          f"gradient error over {len(grads)} tensors (max-abs/max, rel-L2): ours {our_max:.3e} {our_l2:.3e}, reference fp32 "
+          f"algorithm {ref_max:.3e} {ref_l2:.3e}")
+    bad = [(k, v) for k, v in ours.items() if v[0] > 3.0 * max(ref_max, 5e-4) or v[1] > 3.0 * max(ref_l2, 5e-4)]
     assert not bad, bad
     sd = net.state_dict()
     worst_rs = 0.0
