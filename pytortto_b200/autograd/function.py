@@ -76,6 +76,18 @@ class AccumulateGrad(BackwardFunction):
             hook(var)
 
 
+def grad_slot(ctx, i):
+    """Where the gradient of input `i` should be written, if anyone cares: the data-parallel layer gives every parameter a
+    view into a flat gradient bucket (`Parameter._grad_slot`); a backward that produces the gradient of a LEAF parameter
+    which has no gradient yet writes straight into it (AccumulateGrad then just stores that view)."""
+    fn = ctx.next_functions[i][0]
+    if fn.__class__ is AccumulateGrad:
+        var = fn.variable
+        if var.grad is None:
+            return getattr(var, '_grad_slot', None)
+    return None
+
+
 class Function(FunctionBase):
     __slots__ = ()
     _backward_cls = None

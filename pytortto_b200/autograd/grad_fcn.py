@@ -11,7 +11,7 @@ import torch
 
 from .. import ops
 from ..xparray import cparray
-from .function import Function
+from .function import Function, grad_slot
 from .helper import build_links
 
 
@@ -237,8 +237,8 @@ class Linear(Function):
         m, k = xd0.shape
         n = xd1.shape[0]
         g0 = ops.matmul(gd0, xd1, None, m, k, n, n, 1, k, 1) if ctx.needs_input_grad[0] else None      # g @ W
-        g1 = ops.matmul(gd0, xd0, None, n, k, m, 1, n, k, 1) if ctx.needs_input_grad[1] else None      # g^T @ x
-        g2 = ops.colsum(gd0) if ctx.needs_input_grad[2] else None
+        g1 = ops.matmul(gd0, xd0, None, n, k, m, 1, n, k, 1, out=grad_slot(ctx, 1)) if ctx.needs_input_grad[1] else None  # g^T @ x
+        g2 = ops.colsum(gd0, out=grad_slot(ctx, 2)) if ctx.needs_input_grad[2] else None
         return g0, g1, g2
 
 

@@ -12,7 +12,7 @@ import math
 
 from .. import ops
 from ..xparray import cparray
-from .function import AccumulateGrad, Function
+from .function import AccumulateGrad, Function, grad_slot
 from .helper import build_links, inplace_precheck, inplace_update
 
 prod = math.prod
@@ -91,7 +91,7 @@ class Convolution(Function):
         d = ctx.params['desc']
         grad0, grad1, grad2 = None, None, None
         if ctx.needs_input_grad[2]:
-            grad2 = ops.bias_grad(gd0)
+            grad2 = ops.bias_grad(gd0, out=grad_slot(ctx, 2))
         # wgrad forks to a second stream (joined at the end of backward), dgrad stays on the critical path.  Measured on
         # B200 (preact_resnet18, batch 256, graph replay): 3.81 ms/step in this order, 3.89 with dgrad queued first,
         # 3.92 without the fork - the two tensor-bound kernels cannot share an SM (shared memory) and an HBM-bound
@@ -102,7 +102,7 @@ class Convolution(Function):
         # view of a parameter) hands dW to another node's backward on the main stream, so it is computed in order.
         if ctx.needs_input_grad[1]:
             to_leaf = ctx.next_functions[1][0].__class__ is AccumulateGrad
-            grad1 = ops.conv2d_wgrad(xd0, gd0, d, overlap=to_leaf)
+            grad1 = ops.conv2d_wgrad(xd0, gd0, d, overlap=to_leaf, out=grad_slot(ctx, 1))
         if ctx.needs_input_grad[0]:
             grad0 = ops.conv2d_dgrad(gd0, xd1, d)
         return grad0, grad1, grad2
@@ -154,9 +154,9 @@ class TransposedConvolution(Function):
         d = ctx.params['desc']
         grad0, grad1, grad2 = None, None, None
         if ctx.needs_input_grad[2]:
-            grad2 = ops.bias_grad(gd0)
+            grad2 = ops.bias_grad(gd0, out=grad_slot(ctx, 2))
         if ctx.needs_input_grad[1]:
-            grad1 = ops.conv2d_wgrad(gd0, xd0, d)
+            grad1 = ops.conv2d_wgrad(gd0, xd0, d, out=grad_slot(ctx, 1))
         if ctx.needs_input_grad[0]:
             grad0 = ops.conv2d_fprop(gd0, xd1, None, d)
         return grad0, grad1, grad2
@@ -278,7 +278,9 @@ class _BatchNormBase(Function):
         return ops.bn_backward(gd0, xd0, xd1, ctx.params['stats'], ctx.params['count'], relu_out=relu_out,
                                need_dx=ctx.needs_input_grad[0], need_dgamma=ctx.needs_input_grad[1],
                                need_dbeta=ctx.needs_input_grad[2], reduce_hook=hook, accum=accum,
-                               fused_relu=cls._fuse_relu)
+                               fused_relu=cls._fuse_relu,
+                               out_dgamma=grad_slot(ctx, 1) if ctx.needs_input_grad[1] else None,
+                               out_dbeta=grad_slot(ctx, 2) if ctx.needs_input_grad[2] else None)
 
 
 # its backward can fold the pending gradient of input 0 into dx (TORTTO_B200_FOLD_ACCUM=0: separate add kernel)

@@ -427,6 +427,40 @@ static int launch_col_reduce(const float* a, const float* b, const float* mean, 
   return check_launch(what);
 }
 
+// out[i] = sum over chunks of partials[chunk][i] (i < c: the plain column sums of a MODE 0 reduction), as float
+__global__ void __launch_bounds__(1024)
+colsum_finish_kernel(const double* __restrict__ partials, int num_chunks, int c, float* __restrict__ out) {
+  pdl_entry();
+  __shared__ double sm[kLanes][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  double t = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
+  if (threadIdx.y == 0 && i < c) out[i] = (float)t;
+}
+
+// column sums of x[m][c] -> out[c] (float) with the BatchNorm statistics kernel (float4 loads, one wave of CTAs, double
+// partials, fixed order); the partial buffer is a stream-ordered temporary.  Used for conv bias gradients.
+int column_sums(const float* x, int64_t m, int c, float* out, cudaStream_t st) {
+  if (c <= 0) return 0;
+  if (m <= 0) {
+    cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st);
+    return 0;
+  }
+  const int chunks = col_geom(m, c).chunks;
+  double* partials = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&partials, (size_t)chunks * 2 * c * sizeof(double), st);
+  if (e != cudaSuccess) {
+    set_error("column_sums: cudaMallocAsync failed: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  int rc = launch_col_reduce<0>(x, nullptr, nullptr, nullptr, nullptr, nullptr, m, c, partials, chunks, st, "column_sums");
+  if (!rc) {
+    launch_k(colsum_finish_kernel, (c + 31) / 32, dim3(32, kLanes), 0, st, partials, chunks, c, out);
+    rc = check_launch("column_sums(finish)");
+  }
+  cudaFreeAsync(partials, st);
+  return rc;
+}
+
 }  // namespace ttb
 
 using namespace ttb;

@@ -131,27 +131,6 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int chunk
   dw[e] = acc;
 }
 
-// column sum of dy[M][K] -> db[K]: block (32 x 8) tiles, fixed-order partials through the same reduce kernel
-__global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ dy, int64_t m, int k, int64_t rows_per_chunk, float* __restrict__ partial) {
-  pdl_entry();
-  __shared__ float sm[8][33];
-  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  int col = blockIdx.x * 32 + tx;
-  int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
-  int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
-  float acc = 0.f;
-  if (col < k)
-    for (int64_t r = r0 + ty; r < r1; r += 8) acc += dy[r * k + col];
-  sm[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && col < k) {
-    float s = 0.f;
-    for (int j = 0; j < 8; ++j) s += sm[j][tx];
-    partial[(int64_t)blockIdx.y * k + col] = s;
-  }
-}
-
 static int wgrad_chunks(const ttb_conv_desc* d) {
   int64_t wsize = (int64_t)d->k * d->r * d->s * (d->c / d->groups);
   int64_t m_total = (int64_t)d->n * d->p * d->q;
@@ -205,34 +184,11 @@ int direct_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float*
 
 using namespace ttb;
 
+namespace ttb {
+int column_sums(const float* x, int64_t m, int c, float* out, cudaStream_t st);  // batchnorm.cu
+}
+
 extern "C" int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void* stream) {
   if (k <= 0) return 0;
-  cudaStream_t st = as_stream(stream);
-  // small fixed-size partial buffer carved from a static per-device scratch would need state; instead use a
-  // two-level scheme entirely inside db when m is small, else chunked partials in a temporary stream-ordered buffer.
-  int chunks = (int)ceil_div(m > 0 ? m : 1, 2048);
-  int cap = sm_count() * 4;
-  if (chunks > cap) chunks = cap;
-  if (chunks < 1) chunks = 1;
-  int64_t rpc = ceil_div(m > 0 ? m : 1, chunks);
-  rpc = ceil_div(rpc, 8) * 8;
-  chunks = (int)ceil_div(m > 0 ? m : 1, rpc);
-  float* partial = nullptr;
-  if (chunks == 1) {
-    launch_k(colsum_kernel, dim3((k + 31) / 32, 1), 256, 0, st, dy, m, k, rpc, db);
-    return check_launch("bias_grad");
-  }
-  cudaError_t e = cudaMallocAsync((void**)&partial, (size_t)chunks * k * sizeof(float), st);
-  if (e != cudaSuccess) {
-    set_error("bias_grad: cudaMallocAsync failed: %s", cudaGetErrorString(e));
-    return 1;
-  }
-  launch_k(colsum_kernel, dim3((k + 31) / 32, chunks), 256, 0, st, dy, m, k, rpc, partial);
-  int rc = check_launch("bias_grad");
-  if (!rc) {
-    launch_k(wgrad_reduce_kernel, (k + 255) / 256, 256, 0, st, partial, chunks, k, db);
-    rc = check_launch("bias_grad(reduce)");
-  }
-  cudaFreeAsync(partial, st);
-  return rc;
+  return ttb::column_sums(dy, m, k, db, as_stream(stream));
 }

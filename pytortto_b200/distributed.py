@@ -258,36 +258,47 @@ def _flat_view(t):
     return t.reshape(-1)
 
 
-class _Bucket:
-    __slots__ = ("params", "flat", "work", "averaged")
+class _FlatBucket:
+    """A contiguous fp32 buffer holding the gradients of a fixed set of parameters.  Every parameter of the bucket owns a
+    `cparray` VIEW of its slice (`p._grad_slot`, physical layout of the parameter itself: NHWC for conv weights): the
+    kernels that produce parameter gradients (wgrad, bias / BatchNorm / Linear gradients) write straight into it, the
+    bucket's all-reduce runs in place on the buffer, and the optimizer reads `p.grad` = the same view - no pack, no
+    unpack, no copy."""
+    __slots__ = ("params", "flat", "slots", "ready", "work", "dirty")
 
-    def __init__(self, params):
+    def __init__(self, params, device):
+        from .xparray import cparray
         self.params = params
-        self.flat = torch.cat([_flat_view(p.grad.t) for p in params])
-        self.averaged = _state["backend"] == "nccl"  # NCCL divides by the world size inside the collective
-        self.work = all_reduce_sum_(self.flat, async_op=True, average=True)
-
-    def finish(self, inv_world, skip=()):
-        if self.work is not None:
-            self.work.wait()  # makes the current stream wait for the collective
-        if not self.averaged:
-            self.flat.mul_(inv_world)
+        total = sum(p.data.size for p in params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.slots = {}
         off = 0
-        dsts, srcs = [], []
-        for p in self.params:
-            v = _flat_view(p.grad.t)
-            n = v.numel()
-            if id(p) not in skip:
-                dsts.append(v)
-                srcs.append(self.flat[off:off + n])
+        for p in params:
+            n = p.data.size
+            shp = tuple(p.data.shape)
+            chunk = self.flat[off:off + n]
+            if len(shp) == 4:
+                k, c, r, s_ = shp
+                view = chunk.view(k, r, s_, c).permute(0, 3, 1, 2)  # logical (K, C, R, S) over [K][R][S][C] storage
+            else:
+                view = chunk.view(shp)
+            slot = cparray(view)
+            assert slot.t.data_ptr() == chunk.data_ptr(), "gradient slot must alias the flat buffer"
+            self.slots[id(p)] = slot
+            p._grad_slot = slot
             off += n
-        if dsts:
-            torch._foreach_copy_(dsts, srcs)  # one multi-tensor launch instead of one copy per parameter
+        self.ready, self.work, self.dirty = set(), None, False
+
+    def reset(self):
+        self.ready, self.work, self.dirty = set(), None, False
 
 
 class DistributedDataParallel:
-    """Wraps a Module.  Forward is unchanged; gradients are all-reduced in buckets that start during backward
-    (AccumulateGrad hook) and complete in `reduce_gradients()`."""
+    """Wraps a Module.  Forward is unchanged.  Parameters are assigned once to flat gradient buckets (`bucket_mb`, reverse
+    parameter order = the order backward produces them); a bucket's all-reduce (NCCL AVG, in place on the flat buffer)
+    starts from the AccumulateGrad hook as soon as its last gradient exists - issued from the wgrad side stream so that
+    the collective waits for the weight-gradient kernels without the main stream having to - and `reduce_gradients()`
+    (between `loss.backward()` and `optimizer.step()`) only waits for the outstanding collectives."""
 
     def __init__(self, module, bucket_mb=10, broadcast=True, overlap=True):
         self.module = module
@@ -295,16 +306,37 @@ class DistributedDataParallel:
         self.overlap = overlap
         if broadcast:
             broadcast_parameters(module)
-        self._param_ids = {id(p) for p in module.parameters()}
+        params = [p for p in module.parameters() if p.requires_grad]
+        self._param_ids = {id(p) for p in params}
         # BatchNorm affine parameters whose gradient came out of a SyncBN backward THIS step (see _synced_bn_step)
         self._synced_bn_params = _synced_bn_step
-        self._pending, self._pending_bytes = [], 0
-        self._buckets, self._seen = [], set()
+        self._buckets, self._bucket_of = [], {}
+        cur, size = [], 0
+        for p in reversed(params):
+            cur.append(p)
+            size += p.data.nbytes
+            if size >= self.bucket_bytes:
+                self._add_bucket(cur)
+                cur, size = [], 0
+        if cur:
+            self._add_bucket(cur)
         AccumulateGrad.post_hooks.append(self._on_grad_ready)
+
+    def _add_bucket(self, params):
+        d0 = params[0].data
+        dev = d0.t.device if hasattr(d0, "t") else torch.device("cpu")  # (host parameters: the gloo host-logic tests)
+        b = _FlatBucket(params, dev)
+        self._buckets.append(b)
+        for p in params:
+            self._bucket_of[id(p)] = b
 
     def close(self):
         if self._on_grad_ready in AccumulateGrad.post_hooks:
             AccumulateGrad.post_hooks.remove(self._on_grad_ready)
+        for b in self._buckets:
+            for p in b.params:
+                if getattr(p, "_grad_slot", None) is b.slots[id(p)]:
+                    p._grad_slot = None
 
     def __call__(self, *a, **k):
         return self.module(*a, **k)
@@ -317,25 +349,35 @@ class DistributedDataParallel:
 
     # ---- backward-time hook ---------------------------------------------------------------------------------
     def _on_grad_ready(self, p):
-        if not (self.overlap and _state["initialized"] and _state["world"] > 1):
+        if not (_state["initialized"] and _state["world"] > 1):
             return
         pid = id(p)
-        if pid not in self._param_ids or pid in self._synced_bn_params:
+        b = self._bucket_of.get(pid)
+        if b is None:
             return
-        if pid in self._seen:  # a parameter used twice in the graph: its gradient is not final yet - reduce at the end
-            self._seen.add(("dirty", pid))
+        slot = b.slots[pid]
+        if p.grad is not slot:  # produced by an op that does not write into the slot (or accumulated): move it there
+            if p.grad.t.is_cuda:
+                ops.join_wgrad()
+            slot.t.copy_(p.grad.t)
+            p.grad = slot
+        if pid in b.ready or b.work is not None:  # a second gradient for the same parameter / after the bucket went out
+            b.dirty = True
             return
-        self._seen.add(pid)
-        self._pending.append(p)
-        self._pending_bytes += p.grad.nbytes
-        if self._pending_bytes >= self.bucket_bytes:
-            self._launch_pending()
+        b.ready.add(pid)
+        if self.overlap and len(b.ready) == len(b.params):
+            self._launch(b)
 
-    def _launch_pending(self):
-        if self._pending:
-            ops.join_wgrad()  # weight gradients still in flight on the wgrad stream are packed below
-            self._buckets.append(_Bucket(self._pending))
-            self._pending, self._pending_bytes = [], 0
+    def _launch(self, b):
+        """all-reduce the bucket in place; the collective is ordered after BOTH compute streams without stalling the main one"""
+        if b.flat.is_cuda:
+            side = ops._side_stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                b.work = all_reduce_sum_(b.flat, async_op=True, average=True)
+            ops.mark_side_stream_used()
+        else:
+            b.work = all_reduce_sum_(b.flat, async_op=True, average=True)
 
     # ---- after backward ----------------------------------------------------------------------------------------
     def reduce_gradients(self):
@@ -343,32 +385,33 @@ class DistributedDataParallel:
         if not (_state["initialized"] and world > 1):
             return
         inv = 1.0 / world
-        dirty = {k[1] for k in self._seen if isinstance(k, tuple)}
-        self._launch_pending()
-        done = set()
+        averaged = _state["backend"] == "nccl"  # NCCL divides by the world size inside the collective
+        leftovers = []
         for b in self._buckets:
-            b.finish(inv, skip=dirty)
-            done.update(id(p) for p in b.params)
-        # whatever was not bucketed during backward (overlap off, re-used parameters, grads set by hand)
-        rest, size = [], 0
-        bn_grads = []
-        for p in reversed(list(self.module.parameters())):
-            if p.grad is None:
-                continue
-            pid = id(p)
-            if pid in self._synced_bn_params:
-                bn_grads.append(p.grad.t)  # identical on all ranks and already the sum over ranks (module docstring)
-                continue
-            if pid in done and pid not in dirty:
-                continue
-            rest.append(p)
-            size += p.grad.nbytes
-            if size >= self.bucket_bytes:
-                _Bucket(rest).finish(inv)
-                rest, size = [], 0
-        if rest:
-            _Bucket(rest).finish(inv)
+            if b.work is None and not b.dirty and len(b.ready) == len(b.params):
+                self._launch(b)  # overlap off
+            if b.work is not None:
+                b.work.wait()  # makes the current stream wait for the collective
+                if not averaged:
+                    b.flat.mul_(inv)
+            if b.work is None or b.dirty:
+                # incomplete bucket (a parameter without a gradient this step) or a gradient that changed after the
+                # bucket went out: reduce what exists parameter by parameter (rare path)
+                leftovers.extend(p for p in b.params if p.grad is not None and (b.work is None or b.dirty))
+        if leftovers:
+            ops.join_wgrad()
+        for p in leftovers:
+            g = _flat_view(p.grad.t)
+            all_reduce_sum_(g, average=True)
+            if not averaged:
+                g.mul_(inv)
+        ops.join_wgrad()
+        # dgamma / dbeta of SyncBN layers were computed from all-reduced sums: identical on every rank and equal to the SUM
+        # over ranks of the local-loss gradients - the AVG all-reduce left them unchanged, they still need the 1/world
+        bn_grads = [p.grad.t for b in self._buckets for p in b.params
+                    if id(p) in self._synced_bn_params and p.grad is not None]
         if bn_grads:
             torch._foreach_mul_(bn_grads, inv)  # one multi-tensor launch for the ~2 x (#BatchNorm layers) tiny tensors
-        self._buckets, self._seen = [], set()
+        for b in self._buckets:
+            b.reset()
         _synced_bn_step.clear()

@@ -291,6 +291,11 @@ def _side_stream():
     return st
 
 
+def mark_side_stream_used():
+    """work other than a wgrad was queued on the side stream (the DP layer issues bucket all-reduces from it)"""
+    _overlap["dirty"] = True
+
+
 def join_wgrad():
     if _overlap["dirty"]:
         side = _side_stream()
@@ -308,8 +313,9 @@ def join_wgrad():
         _overlap["dirty"] = False
 
 
-def conv2d_wgrad(x, dy, d, overlap=False):
-    dw = new_f32((d.k, d.c // d.groups, d.r, d.s))
+def conv2d_wgrad(x, dy, d, overlap=False, out=None):
+    """`out`: where the caller wants dW (a parameter's slot in a flat gradient bucket of the data-parallel layer)"""
+    dw = out if out is not None else new_f32((d.k, d.c // d.groups, d.r, d.s))
     if dw.size == 0:
         return dw
     if d.math_mode == _cabi.TTB_MATH_BF16:
@@ -350,10 +356,10 @@ def conv2d_wgrad(x, dy, d, overlap=False):
     return dw
 
 
-def bias_grad(dy):
+def bias_grad(dy, out=None):
     """dy (N,K,P,Q) -> (K,)   (gd0.sum((0,2,3)), reference grad_nn.py:727-728)"""
     n, k, p, q = dy.shape
-    db = new_f32((k,))
+    db = out if out is not None else new_f32((k,))
     _cabi.call("ttb_bias_grad", _ptr(dy), _ptr(db), n * p * q, k, current_stream_ptr())
     return db
 
@@ -387,16 +393,16 @@ def mean_hw_bwd(dy, shape):
     return dx
 
 
-def matmul(a, b, bias, m, n, k, sam, sak, sbk, sbn):
-    c = new_f32((m, n))
+def matmul(a, b, bias, m, n, k, sam, sak, sbk, sbn, out=None):
+    c = out if out is not None else new_f32((m, n))
     _cabi.call("ttb_matmul", _ptr(a), _ptr(b), _ptr(bias), _ptr(c), m, n, k, sam, sak, sbk, sbn, current_stream_ptr())
     return c
 
 
-def colsum(g):
+def colsum(g, out=None):
     """(M, N) -> (N,)"""
     m, n = g.shape
-    out = new_f32((n,))
+    out = out if out is not None else new_f32((n,))
     _cabi.call("ttb_bias_grad", _ptr(g), _ptr(out), m, n, current_stream_ptr())
     return out
 
@@ -551,7 +557,7 @@ _RECOMPUTE_RELU_MASK = os.environ.get("TORTTO_B200_RECOMPUTE_RELU_MASK", "1") !=
 
 
 def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dgamma=True, need_dbeta=True,
-                reduce_hook=None, accum=None, fused_relu=False):
+                reduce_hook=None, accum=None, fused_relu=False, out_dgamma=None, out_dbeta=None):
     """-> (dx, dgamma, dbeta).  `count` is the (global) number of elements per channel used in forward.
     `accum`: an array of x's shape that is added to dx inside the apply pass (never written).
     `fused_relu`: the node is BatchNorm+ReLU; the mask (y > 0) is recomputed from x with the scale / shift rows of
@@ -566,8 +572,8 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     if fused_relu and _RECOMPUTE_RELU_MASK:
         relu_out, rsc, rsh = None, base + 3 * row, base + 4 * row
     _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, m, c, partials.data_ptr(), chunks, st)
-    dgamma = new_f32((c,)) if need_dgamma else None
-    dbeta = new_f32((c,)) if need_dbeta else None
+    dgamma = (out_dgamma if out_dgamma is not None else new_f32((c,))) if need_dgamma else None
+    dbeta = (out_dbeta if out_dbeta is not None else new_f32((c,))) if need_dbeta else None
     coef = new_f32((3, c))
     fused = getattr(reduce_hook, "fused", None)
     if fused is not None and x.t.is_cuda and fused.fits(2 * c):

@@ -70,9 +70,11 @@ def _worker(rank, world, port, q):
 
         params = list(net.parameters())
         dist.note_synced_bn_params((id(net[1].weight), id(net[1].bias)))  # what BatchNorm.backward does under SyncBN
+        bn_ids = {id(net[1].weight), id(net[1].bias)}
         local = []
         for i, p in enumerate(reversed(params)):  # backward order
-            g = np.random.default_rng(10 * rank + i).standard_normal(p.shape).astype(np.float32)
+            # (SyncBN affine gradients come out of all-reduced sums: bit-identical on every rank)
+            g = np.random.default_rng(i if id(p) in bn_ids else 10 * rank + i).standard_normal(p.shape).astype(np.float32)
             local.append(g)
             acc = AccumulateGrad()
             acc.variable = p
@@ -82,7 +84,9 @@ def _worker(rank, world, port, q):
             acc.grad = [cparray(t)]
             acc.apply(acc.grad[0])  # fires the DDP hook exactly like the engine does
         ddp.reduce_gradients()
-        bn_ids = {id(net[1].weight), id(net[1].bias)}
+        for b in ddp._buckets:  # gradients live in the flat buckets: p.grad IS the parameter's view of the bucket buffer
+            for p in b.params:
+                assert p.grad is b.slots[id(p)]
         for i, p in enumerate(reversed(params)):
             other = np.random.default_rng(10 * (1 - rank) + i).standard_normal(p.shape).astype(np.float32)
             want = local[i] / world if id(p) in bn_ids else (local[i] + other) / world
