@@ -215,21 +215,35 @@ def build_workload(tt, args, rank):
 
 
 def dp_parity_check(tt, dist, world, rank):
-    """N ranks on a global batch == one process on the same batch (exact-fp32 mode, full preact_resnet18, 16 images per
-    rank, one step: every parameter gradient and BatchNorm running statistic).  Raises if it does not hold."""
+    """N ranks on a global batch == one process on the same batch (exact-fp32 mode, full preact_resnet18, 32 images per
+    rank, one step), in two variants:
+      * the network as it is: loss and every BatchNorm running statistic (forward: the SyncBN exchange of every layer) to
+        1e-5; every parameter gradient to 2e-2 rel-L2.  The gradients cannot be held tighter: the two runs group the
+        BatchNorm sums differently, a last-bit difference can put single ReLU decisions on the other side, and one decision
+        moves every gradient upstream of it by ~2e-3 (the mechanism measured in profiles/r2_relu_flip_analysis.txt);
+      * the same network with its ReLUs replaced by the identity (no decisions: a smooth function of the statistics):
+        every parameter gradient to 2e-3 of the tensor max (median ~3e-6) - this is the check of the gradient plumbing (flat
+        buckets, in-place AVG all-reduce, 1/world of the SyncBN affine gradients, backward statistic exchange).
+    Raises if either does not hold."""
     import torch
     from pytortto_b200.examples import make_models
     M = make_models(tt)
     mode0 = tt.get_math_mode()
     tt.set_math_mode("fp32")
-    per = 16
+    per = 32
     rng = np.random.default_rng(99)
     x = rng.standard_normal((per * world, 3, 32, 32)).astype(np.float32)
     lab = rng.integers(0, 10, per * world).astype(np.int64)
 
-    def one(dp):
+    def one(dp, relu):
         tt.manual_seed(3)
-        net = M["preact_resnet18"]().cuda().train()
+        net = M["preact_resnet18"]()
+        if not relu:
+            for m in list(net.modules()):
+                for name, child in list(m._modules.items()):
+                    if isinstance(child, tt.nn.ReLU):
+                        m._modules[name] = tt.nn.Sequential()
+        net.cuda().train()
         ddp = dist.DistributedDataParallel(net, bucket_mb=4) if dp else None
         xs, ls = dist.shard_batch(x, lab) if dp else (x, lab)
         loss = tt.nn.NLLLoss()(net(tt.tensor(xs).cuda()), tt.tensor(ls, dtype=np.int64).cuda())
@@ -237,26 +251,43 @@ def dp_parity_check(tt, dist, world, rank):
         if ddp is not None:
             ddp.reduce_gradients()
             ddp.close()
-        out = {"grad/" + k: p.grad.get() for k, p in net.named_parameters()}
-        out.update({"buf/" + k: np.asarray(v) for k, v in net.state_dict().items() if "running" in k})
-        return out
-    dp = one(True)
-    with dist.single_process():
-        single = one(False)
-    worst, name = 0.0, ""
-    for k, b in single.items():
-        a = dp[k]
-        rel = float(np.abs(a.astype(np.float64) - b).max() / max(float(np.abs(b).max()), 1e-30))
-        if rel > worst:
-            worst, name = rel, k
-    t = torch.tensor([worst], device="cuda", dtype=torch.float64)
-    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    worst = float(t.item())
+        lv = torch.tensor([loss.item()], device="cuda", dtype=torch.float64)
+        if dp:  # the global loss is the mean of the per-rank local-mean losses
+            torch.distributed.all_reduce(lv)
+            lv /= world
+        grads = {k: p.grad.get() for k, p in net.named_parameters()}
+        bufs = {k: np.asarray(v) for k, v in net.state_dict().items() if "running" in k}
+        return float(lv.item()), grads, bufs
+
+    def rel(a, b):
+        return float(np.abs(a.astype(np.float64) - b).max() / max(float(np.abs(b).max()), 1e-30))
+
+    def rel_l2(a, b):
+        return float(np.linalg.norm(a.astype(np.float64) - b) / max(float(np.linalg.norm(b.astype(np.float64))), 1e-30))
+
+    out = {}
+    for relu in (True, False):
+        l_dp, g_dp, b_dp = one(True, relu)
+        with dist.single_process():
+            l_1, g_1, b_1 = one(False, relu)
+        fwd = max([abs(l_dp - l_1) / max(abs(l_1), 1e-30)] + [rel(b_dp[k], b_1[k]) for k in b_1])
+        errs = {k: (rel_l2 if relu else rel)(g_dp[k], g_1[k]) for k in g_1}
+        worst_name = max(errs, key=errs.get)
+        stats = torch.tensor([fwd, errs[worst_name], float(np.median(list(errs.values())))], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(stats, op=torch.distributed.ReduceOp.MAX)
+        fwd, worst, med = (float(v) for v in stats.tolist())
+        # (without ReLU the activations are not halved layer by layer: plain fp32 rounding of the deep linear net is ~1e-5
+        # on the forward statistics and ~2e-4 on the worst cancellation-prone BatchNorm bias gradient, measured; median 3e-6)
+        tol, ftol = (2e-2, 1e-5) if relu else (2e-3, 1e-4)
+        out["with_relu" if relu else "relu_as_identity"] = {
+            "forward_worst_rel_err": fwd, "forward_tol": ftol, "grad_worst_err": worst, "grad_median_err": med,
+            "grad_metric": "rel-L2" if relu else "max-abs / tensor max", "grad_tol": tol, "grad_worst_tensor": worst_name,
+            "ok": fwd <= ftol and worst <= tol}
     tt.set_math_mode(mode0)
-    tol = 2e-4
-    res = {"worst_rel_err": worst, "tensor": name, "tol": tol, "ok": worst <= tol, "mode": "fp32",
-           "global_batch": per * world, "tensors": len(single),
-           "what": f"{world}-rank step (gradient buckets + SyncBN) vs single-process step on the same global batch"}
+    res = {"ok": all(v["ok"] for v in out.values()), "mode": "fp32", "global_batch": per * world, "tensors": len(g_1),
+           "running_stats": len(b_1), **out,
+           "what": f"{world}-rank step (flat gradient buckets + SyncBN) vs single-process step on the same global batch: loss + "
+                   f"BatchNorm running statistics (forward) and every parameter gradient"}
     if not res["ok"]:
         raise RuntimeError(f"data-parallel parity check failed: {res}")
     return res

@@ -240,8 +240,12 @@ class _BatchNormBase(Function):
         gamma = None if xt1 is None else xt1.data
         beta = None if xt2 is None else xt2.data
         from .. import distributed as dist
-        ident = xt1 if xt1 is not None else running_mean  # a stable per-layer object keys the SyncBN slot
-        hook = dist.bn_forward_hook(None if ident is None else (id(ident), 'f')) if training else None
+        # the SyncBN slot of a layer is keyed by the module's construction index (identical on every rank; an id() would
+        # differ between ranks and can be reused after garbage collection); functional calls without a module tag take
+        # the library all-reduce
+        ident = xt1 if xt1 is not None else running_mean
+        sid = getattr(ident, '_bn_sync_id', None)
+        hook = dist.bn_forward_hook(None if sid is None else (sid, 'f')) if training else None
         relu = cls._fuse_relu
         if training:
             _verify_batch_size(xd0.shape)
@@ -259,7 +263,7 @@ class _BatchNormBase(Function):
         else:
             ctx.save_for_backward(xt0, xt1)
         ctx.params = {'stats': stats, 'count': count, 'synced': hook is not None,
-                      'sync_key': None if ident is None else (id(ident), 'b'),
+                      'sync_key': None if sid is None else (sid, 'b'),
                       'affine_ids': (None if xt1 is None else id(xt1), None if xt2 is None else id(xt2))}
         return yt0
 

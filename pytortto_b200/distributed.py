@@ -133,20 +133,43 @@ class PeerComm:
             bases.append(pp.value)
             self._opened.append(pp.value)
         self.peers_dev = torch.tensor(bases, dtype=torch.int64, device="cuda")
-        self.slots = {}
+        self.slots = {}                      # key -> slot index, assigned in first-call order (the same on every rank)
+        self.free = []                       # indices released by `release` (deterministic program points only)
+        self.next = 0
         dist.barrier()
 
-    def slot_offset(self, key):
+    def slot_index(self, key):
+        """Slot of a call site, or None when the buffer is exhausted (the caller then takes the library all-reduce).
+        Keys are (BatchNorm module construction index, direction): identical on every rank by construction."""
         idx = self.slots.get(key)
         if idx is None:
-            idx = len(self.slots)
-            if idx >= self.SLOTS:
-                raise RuntimeError("PeerComm: out of SyncBN slots")
+            if self.free:
+                idx = self.free.pop()
+            elif self.next < self.SLOTS:
+                idx = self.next
+                self.next += 1
+            else:
+                return None
             self.slots[key] = idx
+        return idx
+
+    def slot_offset(self, key):
+        idx = self.slot_index(key)
+        if idx is None:
+            raise RuntimeError("PeerComm: out of SyncBN slots")
         return idx * self.slot_bytes
 
-    def fits(self, n):
-        return n <= self.MAX_VALUES
+    def release(self, sync_ids):
+        """Give the slots of these BatchNorm layers back (called at the same program point on every rank, e.g.
+        DistributedDataParallel.close(), in module order - never from a finaliser, whose timing differs between ranks)."""
+        for sid in sync_ids:
+            for d in ('f', 'b'):
+                idx = self.slots.pop((sid, d), None)
+                if idx is not None:
+                    self.free.append(idx)
+
+    def fits(self, n, key=None):
+        return n <= self.MAX_VALUES and (key is None or self.slot_index(key) is not None)
 
     def call(self, entry, key, partials, chunks, *rest):
         """Fused exchange + BatchNorm finalize (ttb_comm_bn_finalize / ttb_comm_bn_bwd_finalize): `rest` = the
@@ -174,7 +197,7 @@ def _make_stat_hook(key):
     def hook(partials, chunks, n, local_count):
         comm = _state.get("peer_comm")
         sums = None
-        if comm is not None and key is not None and partials.is_cuda:
+        if comm is not None and key is not None and partials.is_cuda and comm.fits(n, key):
             sums = comm.all_reduce_partials(partials, chunks, n, key)
         if sums is None:  # generic path: collapse the chunks locally, then a library all-reduce (NCCL / gloo)
             sums = partials.reshape(chunks, n).sum(dim=0) if not partials.is_cuda else _collapse(partials, chunks, n)
@@ -333,6 +356,10 @@ class DistributedDataParallel:
     def close(self):
         if self._on_grad_ready in AccumulateGrad.post_hooks:
             AccumulateGrad.post_hooks.remove(self._on_grad_ready)
+        comm = _state.get("peer_comm")
+        if comm is not None:  # this module's SyncBN slots can serve the next model (same order on every rank)
+            from .nn.modules import _BatchNorm
+            comm.release([m._sync_id for m in self.module.modules() if isinstance(m, _BatchNorm)])
         for b in self._buckets:
             for p in b.params:
                 if getattr(p, "_grad_slot", None) is b.slots[id(p)]:

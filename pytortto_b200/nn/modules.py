@@ -533,8 +533,12 @@ class MaxPool2d(_MaxPoolNd):
 class _BatchNorm(Module):
     """reference nn/modules/batchnorm.py:8-93"""
 
+    _sync_counter = [0]  # construction order is the same on every rank (SPMD): a deterministic per-layer SyncBN identity
+
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
+        _BatchNorm._sync_counter[0] += 1
+        self._sync_id = _BatchNorm._sync_counter[0]
         self.num_features, self.eps, self.momentum = num_features, eps, momentum
         self.affine, self.track_running_stats = affine, track_running_stats
         if affine:
@@ -592,6 +596,9 @@ class _BatchNorm(Module):
         else:
             factor = None
         bn_training = True if self.training else (self.running_mean is None and self.running_var is None)
+        ident = self.weight if self.weight is not None else self.running_mean
+        if ident is not None:  # (Module._apply replaces Parameter objects on .cuda(): tag whatever object is current)
+            ident._bn_sync_id = self._sync_id
         fn = F.batch_norm_relu if fuse_relu else F.batch_norm
         return fn(inpt,
                             self.running_mean if not self.training or self.track_running_stats else None,

@@ -520,7 +520,7 @@ def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, r
     row = c * 4
     st = current_stream_ptr()
     fused = getattr(reduce_hook, "fused", None)  # SyncBN over NVLink peer memory: exchange + finalize are one kernel
-    if fused is not None and x.t.is_cuda and fused.fits(2 * c):
+    if fused is not None and x.t.is_cuda and fused.fits(2 * c, reduce_hook.key):
         chunks = _cabi.load().ttb_bn_num_chunks(m, c)
         partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
         _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
@@ -576,7 +576,7 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     dbeta = (out_dbeta if out_dbeta is not None else new_f32((c,))) if need_dbeta else None
     coef = new_f32((3, c))
     fused = getattr(reduce_hook, "fused", None)
-    if fused is not None and x.t.is_cuda and fused.fits(2 * c):
+    if fused is not None and x.t.is_cuda and fused.fits(2 * c, reduce_hook.key):
         fused.call("ttb_comm_bn_bwd_finalize", reduce_hook.key, partials, chunks, count, c, _ptr(gamma), base + row,
                    base + 2 * row, _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
     else:
