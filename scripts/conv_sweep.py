@@ -5,6 +5,7 @@ N = 128, H = W mirroring the nets (32,32,32,16,8,4).  Per pass (fprop / dgrad / 
   * this library (C ABI, TF32 tensor path or the exact direct kernels where the tensor path does not apply),
   * an explicit im2col + cuBLAS GEMM (`torch.nn.functional.unfold` + `matmul`, TF32 on) - the stand-in for the
     reference's CuPy path (`_conv2d` cupy branch = window view + einsum, grad_nn.py:623-642), which cannot run here,
+  * the numpy oracle (port of the reference's algorithm) on the host cores at batch 8, scaled to the sweep's batch,
   * cuDNN through `torch.nn.functional.conv2d` / `torch.nn.grad.*` (channels_last, TF32 on) as a library yard-stick.
 
 Every candidate is captured in a CUDA graph holding REPS back-to-back calls and replayed, so host dispatch is
@@ -19,6 +20,7 @@ import torch.nn.functional as F
 import pytortto_b200 as tt
 from pytortto_b200 import ops
 from pytortto_b200.xparray import cparray
+from oracle import tortto_oracle as O  # (the numpy column only: the reference's CPU algorithm as a baseline)
 
 REPS = 10
 N = 128
@@ -103,7 +105,16 @@ def main():
                 print("im2col skipped:", type(e).__name__, e)
                 i2c = [float("nan")] * 3
             tensor_path = bool(ops.tensor_path_supported(d)) if hasattr(ops, "tensor_path_supported") else None
-            rows.append((c, cin, k, s, h, n, gf, ours, i2c, cud, tensor_path))
+            # the reference's own numpy algorithm (oracle port) on the host cores, at a reduced batch, scaled to n images
+            nn_ = 4 if k == 7 else 8
+            cpu = []
+            import time as _t
+            for fn_ in (lambda: O.conv2d_forward(xn[:nn_], wn, None, s, p), lambda: O.conv2d_backward_input(dyn[:nn_], wn, (h, h), s, p),
+                        lambda: O.conv2d_backward_weight(xn[:nn_], dyn[:nn_], wn.shape, s, p)):
+                t0 = _t.perf_counter()
+                fn_()
+                cpu.append((_t.perf_counter() - t0) * 1e6 * n / nn_)
+            rows.append((c, cin, k, s, h, n, gf, ours, i2c, cud, tensor_path, cpu))
             print(f"C={cin}->{c} k{k} s{s} H{h} N{n} {gf:7.2f} GF  ours {ours[0]:7.1f}/{ours[1]:7.1f}/{ours[2]:7.1f} us  "
                   f"im2col {i2c[0]:7.1f}/{i2c[1]:7.1f}/{i2c[2]:7.1f}  cudnn {cud[0]:7.1f}/{cud[1]:7.1f}/{cud[2]:7.1f}", flush=True)
             del x, w, dy, xt, wt_, dyt, xc, w2, dy2
@@ -114,13 +125,15 @@ def main():
                 "reference's CuPy window-view + einsum path); `cudnn` = torch.nn.functional.conv2d / torch.nn.grad.* on\n"
                 "channels_last tensors with TF32 allowed.  TF/s = 2*N*P*Q*K*C*R*S / time.  fprop / dgrad / wgrad.\n\n")
         f.write("| Cin->Cout | k | s | H | GFLOP/pass | ours us (f/d/w) | ours TF/s (f/d/w) | im2col us (f/d/w) | cudnn us (f/d/w) | "
-                "ours vs im2col (f/d/w) | ours vs cudnn (f/d/w) |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
-        for c, cin, k, s, h, n, gf, o, i, q, tp in rows:
+                "ours vs im2col (f/d/w) | ours vs cudnn (f/d/w) | numpy oracle ms (f/d/w; host cores, batch 8 scaled) |\n"
+                "|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+        for c, cin, k, s, h, n, gf, o, i, q, tp, cpu in rows:
             fmt = lambda v: "/".join(f"{a:.1f}" for a in v)
             tf = "/".join(f"{gf / a * 1e3:.0f}" for a in o)
             r1 = "/".join(f"{b / a:.2f}x" for a, b in zip(o, i))
             r2 = "/".join(f"{b / a:.2f}x" for a, b in zip(o, q))
-            f.write(f"| {cin}->{c} | {k} | {s} | {h} | {gf:.2f} | {fmt(o)} | {tf} | {fmt(i)} | {fmt(q)} | {r1} | {r2} |\n")
+            cp = "/".join(f"{a / 1e3:.0f}" for a in cpu)
+            f.write(f"| {cin}->{c} | {k} | {s} | {h} | {gf:.2f} | {fmt(o)} | {tf} | {fmt(i)} | {fmt(q)} | {r1} | {r2} | {cp} |\n")
     print("wrote", out_path)
 
 
