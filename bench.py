@@ -322,6 +322,12 @@ def profile_families(step, x_dev, y_dev, steps=3):
             work["hbm_bytes"] += 4.0 * m * c * ((3 + 5) + ((2 + 3) if relu else 0))
         elif name == "ttb_relu_fwd":
             work["hbm_bytes"] += 4.0 * a[2] * (2 + 3)
+        elif name == "ttb_add":             # residual add / gradient accumulation: 2R + 1W
+            work["hbm_bytes"] += 4.0 * a[3] * 3
+        elif name == "ttb_add_bias":        # y += bias[c] in place: 1R + 1W
+            work["hbm_bytes"] += 4.0 * a[2] * a[3] * 2
+        elif name == "ttb_add_bn_stats":    # the residual add that also emits the next BatchNorm's statistics: 2R + 1W
+            work["hbm_bytes"] += 4.0 * a[3] * a[4] * 3  # (the statistics read it replaces is credited with ttb_bn_apply)
         elif name == "ttb_maxpool2d_fwd":   # fwd reads x, writes y; bwd reads dy, writes dx (index bytes not credited)
             d = a[0]._obj
             work["hbm_bytes"] += 4.0 * 2 * (d.n * d.c * d.h * d.w + d.n * d.c * d.p * d.q)
@@ -348,7 +354,7 @@ def profile_families(step, x_dev, y_dev, steps=3):
         fam[name] = fam.get(name, 0.0) + e0.elapsed_time(e1)
     fam = {k: v / steps for k, v in fam.items()}
     conv = sum(v for k, v in fam.items() if k.startswith("ttb_conv2d"))
-    hbm = sum(v for k, v in fam.items() if k.startswith(("ttb_bn_", "ttb_relu", "ttb_maxpool", "ttb_comm_bn_")))
+    hbm = sum(v for k, v in fam.items() if k.startswith(("ttb_bn_", "ttb_relu", "ttb_maxpool", "ttb_comm_bn_", "ttb_add")))
     return {"conv_ms": conv, "bn_relu_pool_ms": hbm, "step_ms_serialised": s0.elapsed_time(s1) / steps,
             "conv_flops_per_step": work["conv_flops"] / steps, "hbm_bytes_per_step": work["hbm_bytes"] / steps,
             "by_entry_point": {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}}
@@ -367,8 +373,9 @@ def roofline_of(prof, peaks, math, traffic=None, traffic_note=None):
          "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                  "frac": achieved_gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_step": prof["hbm_bytes_per_step"],
                  "family_ms_per_step": prof["bn_relu_pool_ms"],
-                 "kernel": "ttb_bn_* (+ ttb_comm_bn_* under SyncBN) + ttb_relu_* + ttb_maxpool2d_* calls of one step; fused "
-                           "passes credited with the unfused algorithmic bytes (SURVEY.md 8(d))"}}
+                 "kernel": "ttb_bn_* (+ ttb_comm_bn_* under SyncBN) + ttb_relu_* + ttb_maxpool2d_* + ttb_add* calls of one "
+                           "step; fused passes credited with the unfused algorithmic bytes (SURVEY.md 8(d)): BatchNorm "
+                           "statistics emitted by a conv epilogue / the fused add count as the read they replace"}}
     if traffic_note:
         r["traffic_note"] = traffic_note
     return r
@@ -495,7 +502,9 @@ def run_ours(args):
     # probe step sizes the batch, then 1 warm-up + 3 timed steps of that batch
     cpu_ips = None
     cpu_sample = "skipped (reported at N = 1 only)"
-    if world == 1 and cfg["oracle"] is not None:
+    if not args.cpu_baseline:
+        cpu_sample = "skipped (--cpu-baseline 0)"
+    elif world == 1 and cfg["oracle"] is not None:
         cpu_batch = cpu_sample_batch(args.model, args.batch, 10.5, 3)
         cpu_ips, cpu_s = oracle_images_per_sec(args.model, cpu_batch, 3, 1)
         cpu_sample = (f"3 steps of batch {cpu_batch} after 1 warm-up ({cpu_s:.1f} s per step) of the same model, numpy oracle "
@@ -553,6 +562,7 @@ def main():
     ap.add_argument("--math", default="", choices=["", "tf32", "bf16", "fp32"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as a CUDA graph, 0: eager dispatch")
     ap.add_argument("--extra-bf16", type=int, default=1, help="default workload: also measure the step in bf16 mode")
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the CPU (numpy oracle) leg - for quick A/B runs")
     args = ap.parse_args()
     args.batch = args.batch or MODELS[args.model]["batch"]
     args.math = args.math or MODELS[args.model]["math"]

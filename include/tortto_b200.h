@@ -68,7 +68,7 @@ int ttb_device_sm_count(int* out);           /* SM count of the current device  
 int ttb_conv2d_tensor_path_supported(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
 
 /* which kernel family a pass runs on: 0 exact fp32 direct kernels, 1 tcgen05 implicit GEMM (im2col-mode TMA), 2 tcgen05
- * flat-shift halo tile with shared-memory-resident weights (3x3 / stride-1 layers with <= 64 output channels) */
+ * flat-shift halo tile with shared-memory-resident weights (an experiment: tuning build only, never in the release library) */
 int ttb_conv2d_kernel_variant(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
 
 /* ---- layout --------------------------------------------------------------------------------------------- */
@@ -86,6 +86,27 @@ int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, fl
 /* dw[K,R,S,C/g] = weight gradient (overwritten, not accumulated) */
 int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Fused epilogue of the forward convolution on the tensor path ("fused bias/BN-scale/ReLU epilogues"): what happens to an
+ * accumulator element of output channel k before it is stored, in this order.  Replaces the separate full-tensor passes
+ * of the reference that follow a convolution: the bias add (autograd/grad_nn.py:714-715), an eval-mode BatchNorm folded
+ * to per-channel scale / shift (:942-959), the residual `Add` (tensor.py:597-599), `Relu` (:58), and the two statistics
+ * reductions of the training-mode BatchNorm that reads the output next (xp.mean / xp.var, :923-924). */
+typedef struct ttb_conv_epilogue {
+  const float* scale;    /* [K] or NULL: v = acc * scale[k]                                                          */
+  const float* bias;     /* [K] or NULL: v += bias[k]                                                                */
+  const float* residual; /* [N,P,Q,K] or NULL: v += residual[same element] (may alias y: in-place accumulate)        */
+  int32_t relu;          /* != 0: v = max(v, 0)                                                                      */
+  double* stats;         /* NULL, or [ttb_conv2d_fprop_stats_chunks(d)][2][K]: per-chunk sum(v), sum(v*v) of the stored
+                            values - the partial buffer ttb_bn_finalize / ttb_comm_bn_finalize take instead of running
+                            ttb_bn_stats over y (fixed tile -> chunk assignment: deterministic)                         */
+} ttb_conv_epilogue;
+/* 1 if fprop of this problem runs on the tensor path (TF32 / BF16 math, groups == 1, ...), i.e. can take an epilogue */
+int ttb_conv2d_fused_epilogue_supported(const ttb_conv_desc* d);
+/* number of chunks (rows of the statistics partial buffer) fprop of this problem writes; 0 = no fused epilogue */
+int ttb_conv2d_fprop_stats_chunks(const ttb_conv_desc* d);
+/* ttb_conv2d_fprop with a fused epilogue (ep == NULL: plain store); same workspace as ttb_conv2d_fprop */
+int ttb_conv2d_fprop_fused(const ttb_conv_desc* d, const float* x, const float* w, const ttb_conv_epilogue* ep, float* y,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* db[K] = sum over rows of dy[M,K] */
 int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void* stream);
 
@@ -94,14 +115,17 @@ int ttb_bias_grad(const float* dy, float* db, int64_t m, int k, void* stream);
  *   ttb_conv2d_dgrad_prepacked_supported  1 if dgrad of this problem can take pre-packed weights (tensor path without a
  *                                         staged copy), else use ttb_conv2d_dgrad
  *   ttb_conv2d_dgrad_pack_weights         w[i] ([K][R][S][C]) -> w_packed[i] ([C][R][S][K], same size) for count layers
- *   ttb_conv2d_dgrad_prepacked            ttb_conv2d_dgrad on weights packed by the call above (no workspace)
+ *   ttb_conv2d_dgrad_prepacked            ttb_conv2d_dgrad on weights packed by the call above (no workspace); accum (may be
+ *                                         NULL, may alias dx): a gradient already pending for the same tensor, added in the
+ *                                         epilogue (the engine's `grad += new`, tensor.py:597-599, without its own pass)
  *   ttb_conv2d_wgrad_partial              ttb_conv2d_wgrad without the split reduction: leaves *splits_out partial
  *                                         buffers of K*R*S*C floats at *partials_out (inside workspace); <= 1: dw is final
  *   ttb_sum_splits_multi                  outs[i][e] = sum_s partials[i][s*sizes[i] + e], fixed order, count tensors   */
 int ttb_conv2d_dgrad_prepacked_supported(const ttb_conv_desc* d);
 int ttb_conv2d_dgrad_pack_weights(int count, const ttb_conv_desc* const* descs, const float* const* w,
                                   float* const* w_packed, void* stream);
-int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, void* stream);
+int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, const float* accum, float* dx,
+                               void* stream);
 int ttb_conv2d_wgrad_partial(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* workspace,
                              size_t workspace_bytes, int* splits_out, const float** partials_out, void* stream);
 int ttb_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
@@ -119,9 +143,10 @@ int ttb_sum_splits_multi(int count, const float* const* partials, const int* spl
  *   ttb_to_bf16                     dst[i] = bf16(src[i]), n % 4 == 0 */
 int ttb_conv2d_bf16_supported(const ttb_conv_desc* d, int pass /*0 fprop, 1 dgrad, 2 wgrad*/);
 size_t ttb_conv2d_workspace_size_bf16(const ttb_conv_desc* d, int pass);
-int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const float* bias, float* y,
-                          void* stream);
-int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, float* dx, void* stream);
+int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const ttb_conv_epilogue* ep /*or NULL*/,
+                          float* y, void* stream);
+int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, const float* accum /*or NULL*/,
+                          float* dx, void* stream);
 int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,
                           size_t workspace_bytes, void* stream);
 int ttb_conv2d_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
@@ -133,6 +158,10 @@ int ttb_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int ttb_bn_num_chunks(int64_t m, int c);
 /* partials[chunk][2][C] (double): per-chunk sum(x), sum(x*x) */
 int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chunks, void* stream);
+/* out = a + b (the residual `Add`, tensor.py:597-599; out must not alias a or b) AND the statistics partials of the sum, as
+ * ttb_bn_stats(out, ...) would write them, in one pass: for the BatchNorm that reads the sum next */
+int ttb_add_bn_stats(const float* a, const float* b, float* out, int64_t m, int c, double* partials, int num_chunks,
+                     void* stream);
 /* sums[2][C] = sum over chunks (double).  This is the buffer a data-parallel run all-reduces (SyncBN). */
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream);
 /* from sums[num_chunks][2][C] (per-chunk partials, summed here in fixed order; num_chunks = 1 for an already reduced /
@@ -146,6 +175,10 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
 int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float eps, const float* gamma,
                         const float* beta, float* mean, float* var_eps, float* sd, float* scale, float* shift,
                         void* stream);
+/* eval-mode BatchNorm behind a convolution folded to the conv epilogue's per-channel scale / bias (ttb_conv_epilogue):
+ * scale = gamma / sqrt(var + eps), bias = beta + (conv_bias - mean) * scale; gamma, beta, conv_bias may be NULL */
+int ttb_bn_fold_eval(const float* mean, const float* var, int c, float eps, const float* gamma, const float* beta,
+                     const float* conv_bias, float* scale, float* bias, void* stream);
 /* y = (x - mean[c])*scale[c] + beta[c] (the reference's order of operations, grad_nn.py:942-959, with gamma/sd folded
  * into scale; `beta` = the `shift` row the finalize entry points write); relu != 0 fuses y = max(y, 0).
  * y_bf16 (may be NULL): the same values rounded to bf16, co-written for the bf16 tensor path (ttb_conv2d_*_bf16). */

@@ -28,6 +28,11 @@ class PoolDesc(ctypes.Structure):
                                        "dil_h", "dil_w", "p", "q")]
 
 
+class ConvEpilogue(ctypes.Structure):
+    """struct ttb_conv_epilogue (device pointers as plain integers, None = NULL)"""
+    _fields_ = [("scale", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("relu", c_int32), ("stats", c_void_p)]
+
+
 _F = c_void_p  # device pointers travel as plain integers
 _PROTOS = {
     "ttb_last_error": (c_char_p, []),
@@ -41,25 +46,30 @@ _PROTOS = {
     "ttb_conv2d_fprop": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, _F, c_size_t, c_void_p]),
     "ttb_conv2d_dgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
     "ttb_conv2d_wgrad": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_conv2d_fused_epilogue_supported": (c_int, [POINTER(ConvDesc)]),
+    "ttb_conv2d_fprop_stats_chunks": (c_int, [POINTER(ConvDesc)]),
+    "ttb_conv2d_fprop_fused": (c_int, [POINTER(ConvDesc), _F, _F, POINTER(ConvEpilogue), _F, _F, c_size_t, c_void_p]),
     "ttb_bias_grad": (c_int, [_F, _F, c_int64, c_int, c_void_p]),
     "ttb_conv2d_dgrad_prepacked_supported": (c_int, [POINTER(ConvDesc)]),
     "ttb_conv2d_dgrad_pack_weights": (c_int, [c_int, POINTER(POINTER(ConvDesc)), POINTER(c_void_p), POINTER(c_void_p), c_void_p]),
-    "ttb_conv2d_dgrad_prepacked": (c_int, [POINTER(ConvDesc), _F, _F, _F, c_void_p]),
+    "ttb_conv2d_dgrad_prepacked": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_void_p]),
     "ttb_conv2d_wgrad_partial": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, POINTER(c_int), POINTER(c_void_p), c_void_p]),
     "ttb_sum_splits_multi": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int64), POINTER(c_void_p), c_void_p]),
     "ttb_conv2d_bf16_supported": (c_int, [POINTER(ConvDesc), c_int]),
     "ttb_conv2d_workspace_size_bf16": (c_size_t, [POINTER(ConvDesc), c_int]),
-    "ttb_conv2d_fprop_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_void_p]),
-    "ttb_conv2d_dgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, c_void_p]),
+    "ttb_conv2d_fprop_bf16": (c_int, [POINTER(ConvDesc), _F, _F, POINTER(ConvEpilogue), _F, c_void_p]),
+    "ttb_conv2d_dgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_void_p]),
     "ttb_conv2d_wgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
     "ttb_conv2d_pack_weights_bf16": (c_int, [c_int, POINTER(POINTER(ConvDesc)), POINTER(c_void_p), POINTER(c_void_p),
                                              POINTER(c_void_p), c_void_p]),
     "ttb_to_bf16": (c_int, [_F, _F, c_int64, c_void_p]),
     "ttb_bn_num_chunks": (c_int, [c_int64, c_int]),
     "ttb_bn_stats": (c_int, [_F, c_int64, c_int, _F, c_int, c_void_p]),
+    "ttb_add_bn_stats": (c_int, [_F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_reduce_partials": (c_int, [_F, c_int, c_int, _F, c_void_p]),
     "ttb_bn_finalize": (c_int, [_F, c_int, c_int64, c_int, c_float, c_float, _F, _F, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
+    "ttb_bn_fold_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, _F, c_int, _F, c_void_p]),
     "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_bwd_finalize": (c_int, [_F, c_int, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),

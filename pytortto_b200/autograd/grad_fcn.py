@@ -12,6 +12,7 @@ import torch
 from .. import ops
 from ..xparray import cparray
 from .function import Function, grad_slot
+from .grad_mode import is_grad_enabled
 from .helper import build_links
 
 
@@ -67,7 +68,8 @@ class Add(Function):
         xd0, xd1 = xt0.data, xt1.data
         if xd0.__class__ is not cparray or xd1.__class__ is not cparray:
             raise RuntimeError("add: both operands must be on the CUDA device")
-        yd0 = ops.add_arrays(xd0, xd1)
+        # (training forward of 4-D operands: the same pass emits the statistics of the sum for the BatchNorm that follows)
+        yd0 = ops.add_arrays(xd0, xd1, stats=is_grad_enabled() and xd0.ndim == 4)
         ctx.params['shapes'] = (xd0.shape, xd1.shape)
         return build_links(yd0, grad_fn=ctx)
 

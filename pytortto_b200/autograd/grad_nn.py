@@ -13,6 +13,7 @@ import math
 from .. import ops
 from ..xparray import cparray
 from .function import AccumulateGrad, Function, grad_slot
+from .grad_mode import is_grad_enabled
 from .helper import build_links, inplace_precheck, inplace_update
 
 prod = math.prod
@@ -76,7 +77,10 @@ class Convolution(Function):
                                f'but got {xd0.shape[-3]} channels instead')
         _require_cuda('conv2d', xd0)
         d = ops.conv_desc(xd0.shape, xd1.shape, stride, padding, dilation, groups)
-        yd0 = ops.conv2d_fprop(xd0, xd1, xd2, d)
+        # while a graph is being recorded (training forward) the epilogue also emits the per-channel sum / sum of squares
+        # of the output: the BatchNorm that reads it next (grad_nn.py:923-924 of the reference) skips its statistics pass
+        want_stats = is_grad_enabled() and ops.conv_fused_info(d)[0]
+        yd0 = ops.conv2d_fprop(xd0, xd1, xd2, d, stats=want_stats)
         yt0 = build_links(yd0, grad_fn=ctx)
         ctx.save_for_backward(xt0, xt1)
         ctx.params['desc'] = d
@@ -103,9 +107,15 @@ class Convolution(Function):
         if ctx.needs_input_grad[1]:
             to_leaf = ctx.next_functions[1][0].__class__ is AccumulateGrad
             grad1 = ops.conv2d_wgrad(xd0, gd0, d, overlap=to_leaf, out=grad_slot(ctx, 1))
+        # `_accum0`: a gradient that already reached the input through another branch (a ResNet block's identity shortcut);
+        # the engine hands it over (Tensor._sweep) and the dgrad epilogue adds it instead of a separate add kernel
+        accum = ctx.params.pop('_accum0', None)
         if ctx.needs_input_grad[0]:
-            grad0 = ops.conv2d_dgrad(gd0, xd1, d)
+            grad0 = ops.conv2d_dgrad(gd0, xd1, d, accum=accum)
         return grad0, grad1, grad2
+
+
+Convolution._accumulates_input0 = os.environ.get("TORTTO_B200_FOLD_ACCUM", "1") != "0"
 
 
 class TransposedConvolution(Function):

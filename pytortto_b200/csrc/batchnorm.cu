@@ -69,11 +69,14 @@ static ColGeom col_geom(int64_t m, int c) {
 //         accumulation of x^2 loses the variance when |mean| >> sd (sum x^2 - n*mean^2 cancels); shifted sums do not,
 //         and the reference is two-pass (xp.mean, xp.var: grad_nn.py:923-924).
 // MODE 1: s0 = sum(g), s1 = sum(g*(b-mean)), g = a or masked  (backward; a = dy, b = x, mask = relu_out > 0)
+// MODE 2: MODE 0 over the sum a + b, which is also written to `sum_out` (must NOT alias a or b - the shift K is row 0 of
+//         the inputs, read by every CTA): the residual `Add` and the
+//         statistics pass of the BatchNorm that reads the sum, in one pass (2 reads + 1 write instead of 3 reads + 1 write)
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(kBnThreads)
 col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
                   const float* __restrict__ mask, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                  int64_t m, int c, int tx_n, int64_t rows_per_chunk, double* __restrict__ partials) {
+                  int64_t m, int c, int tx_n, int64_t rows_per_chunk, double* __restrict__ partials, float* __restrict__ sum_out) {
   pdl_entry();
   // ReLU mask of the fused BatchNorm+ReLU node: either read (mask = the ReLU output) or RECOMPUTED from x with the
   // forward pass's own mean / scale / beta (rscale != null): fmaf(x - mean, scale, beta) > 0 is bit-for-bit what forward tested,
@@ -86,12 +89,13 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
   if (ch < c) {
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = mu, rsh = mu;
     const bool recompute = MODE == 1 && rscale != nullptr;
-    if (MODE == 0) {  // mu = the shift K (row 0 of the tensor)
+    if (MODE == 0 || MODE == 2) {  // mu = the shift K (row 0 of the tensor)
       if (VEC) {
         mu = ld_f4(a + ch);
+        if (MODE == 2) { const float4 t = ld_f4(b + ch); mu.x += t.x; mu.y += t.y; mu.z += t.z; mu.w += t.w; }
       } else {
         float* pm = &mu.x;
-        for (int j = 0; j < 4 && ch + j < c; ++j) pm[j] = a[ch + j];
+        for (int j = 0; j < 4 && ch + j < c; ++j) pm[j] = MODE == 2 ? a[ch + j] + b[ch + j] : a[ch + j];
       }
     }
     if (MODE == 1) {
@@ -110,7 +114,7 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
     int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
     int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
     auto accumulate = [&](float4 va, float4 vb, float4 vm) {
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 2) {
         va.x -= mu.x; va.y -= mu.y; va.z -= mu.z; va.w -= mu.w;
         s0.x += va.x; s0.y += va.y; s0.z += va.z; s0.w += va.w;
         s1.x = fmaf(va.x, va.x, s1.x); s1.y = fmaf(va.y, va.y, s1.y);
@@ -140,9 +144,17 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
         for (int u = 0; u < U; ++u) {
           const int64_t off = (r + u * ty_n) * c + ch;
           va[u] = ld_f4_stream(a + off);
+          if (MODE == 2) vb[u] = ld_f4_stream(b + off);
           if (MODE == 1) {
             vb[u] = ld_f4_stream(b + off);
             if (mask) vm[u] = ld_f4_stream(mask + off);
+          }
+        }
+        if (MODE == 2) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            va[u].x += vb[u].x; va[u].y += vb[u].y; va[u].z += vb[u].z; va[u].w += vb[u].w;
+            st_f4(sum_out + (r + u * ty_n) * c + ch, va[u]);
           }
         }
 #pragma unroll
@@ -154,6 +166,11 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
       float4 va, vb = make_float4(0.f, 0.f, 0.f, 0.f), vm = make_float4(1.f, 1.f, 1.f, 1.f);
       if (VEC) {
         va = ld_f4_stream(a + off);
+        if (MODE == 2) {
+          vb = ld_f4_stream(b + off);
+          va.x += vb.x; va.y += vb.y; va.z += vb.z; va.w += vb.w;
+          st_f4(sum_out + off, va);
+        }
         if (MODE == 1) {
           vb = ld_f4_stream(b + off);
           if (mask) vm = ld_f4_stream(mask + off);
@@ -163,6 +180,10 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
         float* pa = &va.x; float* pb = &vb.x; float* pm = &vm.x;
         for (int j = 0; j < 4 && ch + j < c; ++j) {
           pa[j] = a[off + j];
+          if (MODE == 2) {
+            pa[j] += b[off + j];
+            sum_out[off + j] = pa[j];
+          }
           if (MODE == 1) {
             pb[j] = b[off + j];
             if (mask) pm[j] = mask[off + j];
@@ -184,12 +205,12 @@ col_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, cons
       d1[0] += q.x; d1[1] += q.y; d1[2] += q.z; d1[3] += q.w;
     }
     double* out = partials + (int64_t)blockIdx.y * 2 * c;
-    if (MODE == 0) {  // shifted -> plain sums, in double: sum x = S0 + n K, sum x^2 = S1 + 2 K S0 + n K^2
+    if (MODE == 0 || MODE == 2) {  // shifted -> plain sums, in double: sum x = S0 + n K, sum x^2 = S1 + 2 K S0 + n K^2
       int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
       int64_t r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
       const double nrows = r1 > r0 ? (double)(r1 - r0) : 0.0;
       for (int j = 0; j < 4 && ch + j < c; ++j) {
-        const double k = (double)a[ch + j];
+        const double k = MODE == 2 ? (double)(a[ch + j] + b[ch + j]) : (double)a[ch + j];
         const double t0 = d0[j], t1 = d1[j];
         d0[j] = t0 + nrows * k;
         d1[j] = t1 + 2.0 * k * t0 + nrows * k * k;
@@ -249,13 +270,48 @@ reduce_partials_kernel(const double* __restrict__ partials, int num_chunks, int 
   if (threadIdx.y == 0 && i < c2) sums[i] = t;
 }
 
-__global__ void __launch_bounds__(1024)
+// Both sums of the per-chunk partials [chunks][2][c] for 8 channels per block: blockDim = (8 channels, 128 chunk lanes).
+// The finalize kernels sit between two HBM passes of every BatchNorm layer (34 launches per ResNet-18 step), so their
+// latency is on the critical path: many small blocks (c / 8) and 128 lanes per channel make it ONE round of independent L2
+// loads per thread (a few hundred chunks) instead of three dependent rounds per sum; fixed-order tree => deterministic.
+constexpr int kFinCh = 8, kFinLanes = 128;
+__device__ __forceinline__ void chunk_sum2(const double* __restrict__ partials, int num_chunks, int c, int i, bool valid,
+                                           double (*sm)[2][kFinCh], double* out0, double* out1) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  if (valid) {
+    int k = threadIdx.y;
+    for (; k + kFinLanes < num_chunks; k += 2 * kFinLanes) {
+      const double* p = partials + (int64_t)k * 2 * c + i;
+      const double* q = p + (int64_t)kFinLanes * 2 * c;
+      a0 += p[0]; a1 += p[c];
+      b0 += q[0]; b1 += q[c];
+    }
+    if (k < num_chunks) {
+      const double* p = partials + (int64_t)k * 2 * c + i;
+      a0 += p[0]; a1 += p[c];
+    }
+  }
+  sm[threadIdx.y][0][threadIdx.x] = a0 + b0;
+  sm[threadIdx.y][1][threadIdx.x] = a1 + b1;
+  __syncthreads();
+  for (int o = kFinLanes / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.y < o) {
+      sm[threadIdx.y][0][threadIdx.x] += sm[threadIdx.y + o][0][threadIdx.x];
+      sm[threadIdx.y][1][threadIdx.x] += sm[threadIdx.y + o][1][threadIdx.x];
+    }
+    __syncthreads();
+  }
+  *out0 = sm[0][0][threadIdx.x];
+  *out1 = sm[0][1][threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kFinCh * kFinLanes)
 bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnFwdFinalize fin) {
   pdl_entry();
-  __shared__ double sm[kLanes][33];
-  int i = blockIdx.x * 32 + threadIdx.x;
-  double s0 = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
-  double s1 = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
+  __shared__ double sm[kFinLanes][2][kFinCh];
+  int i = blockIdx.x * kFinCh + threadIdx.x;
+  double s0, s1;
+  chunk_sum2(partials, num_chunks, c, i, i < c, sm, &s0, &s1);
   if (threadIdx.y != 0 || i >= c) return;
   fin(i, s0, s1);
 }
@@ -274,13 +330,26 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ mean_in, const 
   shift[i] = beta ? beta[i] : 0.f;  // the additive term of y = (x - mean)*scale + beta
 }
 
-__global__ void __launch_bounds__(1024)
+// eval-mode BatchNorm folded into the epilogue of the convolution in front of it:
+//   bn(conv + b) = (conv + b - mean) * gamma / sqrt(var + eps) + beta = conv * scale + bias
+__global__ void bn_fold_eval_kernel(const float* __restrict__ mean, const float* __restrict__ var, int c, float eps,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ conv_bias, float* scale, float* bias) {
+  pdl_entry();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float s = (gamma ? gamma[i] : 1.f) / sqrtf(__fadd_rn(var[i], eps));
+  scale[i] = s;
+  bias[i] = fmaf((conv_bias ? conv_bias[i] : 0.f) - mean[i], s, beta ? beta[i] : 0.f);
+}
+
+__global__ void __launch_bounds__(kFinCh * kFinLanes)
 bn_bwd_finalize_kernel(const double* __restrict__ partials, int num_chunks, int c, BnBwdFinalize fin) {
   pdl_entry();
-  __shared__ double sm[kLanes][33];
-  int i = blockIdx.x * 32 + threadIdx.x;
-  double sdy = chunk_sum(partials, num_chunks, 2 * c, i, i < c, sm);
-  double sdyx = chunk_sum(partials, num_chunks, 2 * c, c + i, i < c, sm);
+  __shared__ double sm[kFinLanes][2][kFinCh];
+  int i = blockIdx.x * kFinCh + threadIdx.x;
+  double sdy, sdyx;
+  chunk_sum2(partials, num_chunks, c, i, i < c, sm, &sdy, &sdyx);
   if (threadIdx.y != 0 || i >= c) return;
   fin(i, sdy, sdyx);
 }
@@ -412,18 +481,19 @@ static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) ==
 template <int MODE>
 static int launch_col_reduce(const float* a, const float* b, const float* mean, const float* mask, const float* rscale,
                              const float* rshift, int64_t m, int c, double* partials, int num_chunks, cudaStream_t st,
-                             const char* what) {
+                             const char* what, float* sum_out = nullptr) {
   if (m <= 0 || c <= 0) return 0;
   ColGeom g = col_geom(m, c);
   TTB_REQUIRE(num_chunks == g.chunks, "%s: num_chunks=%d but ttb_bn_num_chunks gives %d", what, num_chunks, g.chunks);
   bool vec = (c % 4 == 0) && a16(a) &&
-             (MODE == 0 || (a16(b) && a16(mean) && (!mask || a16(mask)) && (!rscale || (a16(rscale) && a16(rshift)))));
+             (MODE == 0 || (MODE == 2 && a16(b) && a16(sum_out)) ||
+              (MODE == 1 && a16(b) && a16(mean) && (!mask || a16(mask)) && (!rscale || (a16(rscale) && a16(rshift)))));
   dim3 grid(g.qblocks, g.chunks);
   size_t smem = sizeof(float4) * 2 * kBnThreads;
   if (vec)
-    launch_k(col_reduce_kernel<MODE, true>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
+    launch_k(col_reduce_kernel<MODE, true>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials, sum_out);
   else
-    launch_k(col_reduce_kernel<MODE, false>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials);
+    launch_k(col_reduce_kernel<MODE, false>, grid, kBnThreads, smem, st, a, b, mean, mask, rscale, rshift, m, c, g.tx, g.rows_per_chunk, partials, sum_out);
   return check_launch(what);
 }
 
@@ -477,6 +547,13 @@ int ttb_bn_stats(const float* x, int64_t m, int c, double* partials, int num_chu
                               "bn_stats");
 }
 
+int ttb_add_bn_stats(const float* a, const float* b, float* out, int64_t m, int c, double* partials, int num_chunks,
+                     void* stream) {
+  TTB_REQUIRE(out != a && out != b, "add_bn_stats: the output must not alias an input");
+  return launch_col_reduce<2>(a, b, nullptr, nullptr, nullptr, nullptr, m, c, partials, num_chunks, as_stream(stream),
+                              "add_bn_stats", out);
+}
+
 int ttb_bn_reduce_partials(const double* partials, int num_chunks, int c2, double* sums, void* stream) {
   if (c2 <= 0) return 0;
   launch_k(reduce_partials_kernel, (c2 + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), partials, num_chunks, c2, sums);
@@ -495,7 +572,7 @@ int ttb_bn_finalize(const double* sums, int num_chunks, int64_t count, int c, fl
   bn_fwd_host_factors(count, momentum, &fin.unbias, &fin.one_minus_momentum);
   fin.gamma = gamma; fin.beta = beta; fin.running_mean = running_mean; fin.running_var = running_var;
   fin.mean = mean; fin.var_eps = var_eps; fin.sd = sd; fin.scale = scale; fin.shift = shift;
-  launch_k(bn_finalize_kernel, (c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
+  launch_k(bn_finalize_kernel, (c + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_finalize");
 }
 
@@ -506,6 +583,13 @@ int ttb_bn_prepare_eval(const float* mean_in, const float* var_in, int c, float 
   launch_k(bn_prepare_eval_kernel, (c + 127) / 128, 128, 0, as_stream(stream), mean_in, var_in, c, eps, gamma, beta, mean,
                                                                          var_eps, sd, scale, shift);
   return check_launch("bn_prepare_eval");
+}
+
+int ttb_bn_fold_eval(const float* mean, const float* var, int c, float eps, const float* gamma, const float* beta,
+                     const float* conv_bias, float* scale, float* bias, void* stream) {
+  if (c <= 0) return 0;
+  launch_k(bn_fold_eval_kernel, (c + 127) / 128, 128, 0, as_stream(stream), mean, var, c, eps, gamma, beta, conv_bias, scale, bias);
+  return check_launch("bn_fold_eval");
 }
 
 int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* mean, const float* scale, const float* beta,
@@ -545,7 +629,7 @@ int ttb_bn_bwd_finalize(const double* sums, int num_chunks, int64_t count, int c
   fin.count = (double)count;
   fin.c = c;
   fin.gamma = gamma; fin.var_eps = var_eps; fin.sd = sd; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.coef = coef;
-  launch_k(bn_bwd_finalize_kernel, (c + 31) / 32, dim3(32, kLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
+  launch_k(bn_bwd_finalize_kernel, (c + kFinCh - 1) / kFinCh, dim3(kFinCh, kFinLanes), 0, as_stream(stream), sums, num_chunks < 1 ? 1 : num_chunks, c, fin);
   return check_launch("bn_bwd_finalize");
 }
 

@@ -79,6 +79,21 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through check_launch (cudaGetLastError)
 }
 
+// What a convolution epilogue does to an accumulator element of output channel k before it is stored (the device-side
+// form of ttb_conv_epilogue):
+//   v = acc * scale[k] + bias[k]   (either may be null)     - conv bias, or an eval-mode BatchNorm folded to scale / shift
+//   v += accum[same element]       (accum may be null)      - a residual / a gradient already pending for the same tensor
+//   v = max(v, 0)                  (relu != 0)
+//   stats (may be null): per-chunk partial sums [chunks][2][K] (double) of v and v*v for the BatchNorm that follows
+struct Epilogue {
+  const float* scale;
+  const float* bias;
+  const float* accum;
+  int relu;
+  double* stats;
+};
+inline Epilogue bias_epilogue(const float* bias) { return Epilogue{nullptr, bias, nullptr, 0, nullptr}; }
+
 #define TTB_REQUIRE(cond, ...)          \
   do {                                  \
     if (!(cond)) {                      \

@@ -23,17 +23,20 @@ bool igemm_supported(const ttb_conv_desc* d, int pass);
 int igemm_channel_block(const ttb_conv_desc* d);
 void igemm_set_trace(long long* p);
 size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
-int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* ws,
+int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, void* ws,
                 size_t ws_bytes, cudaStream_t st);
+int igemm_fprop_stats_chunks(const ttb_conv_desc* d);
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st, const void* prepacked = nullptr);
+                cudaStream_t st, const void* prepacked = nullptr, const float* accum = nullptr);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st, int* splits_out = nullptr);
 // conv_flat.cu: "flat-shift halo tile" fprop / dgrad with shared-memory-resident weights (the 64-channel 3x3 layers)
 bool flat_fprop_supported(const ttb_conv_desc* d);
 bool flat_dgrad_supported(const ttb_conv_desc* d);
-int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
-int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st);
+int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const Epilogue& ep, float* y, cudaStream_t st);
+int flat_fprop_stats_chunks(const ttb_conv_desc* d);
+int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st,
+               const float* accum = nullptr);
 int igemm_pack_dgrad_weights(int count, const ttb_conv_desc* const* descs, const float* const* w, float* const* wt,
                              cudaStream_t st);
 int igemm_sum_splits_multi(int count, const float* const* partials, const int* splits, const int64_t* sizes,
@@ -186,25 +189,59 @@ size_t ttb_conv2d_workspace_size(const ttb_conv_desc* d, int pass) {
   return direct_workspace_size(d, pass);
 }
 
-int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
-                     void* workspace, size_t workspace_bytes, void* stream) {
-  if (int rc = validate(d, "conv2d_fprop")) return rc;
-  cudaStream_t st = as_stream(stream);
-  TensorPlan t;
-  if (!plan_tensor(d, 0, &t)) return direct_fprop(d, x, w, bias, y, st);
+static Epilogue to_epilogue(const ttb_conv_epilogue* e) {
+  if (!e) return Epilogue{nullptr, nullptr, nullptr, 0, nullptr};
+  return Epilogue{e->scale, e->bias, e->residual, e->relu, e->stats};
+}
+
+static int fprop_tensor(const ttb_conv_desc* d, const TensorPlan& t, const float* x, const float* w, const Epilogue& ep,
+                        float* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const size_t need = t.a_bytes + t.b_bytes + t.c_bytes + t.inner;
   TTB_REQUIRE(need == 0 || (workspace != nullptr && workspace_bytes >= need),
               "conv2d_fprop: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
   char* ws = reinterpret_cast<char*>(workspace);
   const void *xa = x, *wa = w;
-  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, bias, y, st);
+  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, ep, y, st);
   if (t.stage_ops) {
     if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
     if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, t.p.c, t.bf16, st)) return 1;
     xa = ws;
     wa = ws + t.a_bytes;
   }
-  return igemm_fprop(&t.p, xa, wa, bias, y, ws ? ws + t.a_bytes + t.b_bytes : nullptr, t.inner, st);
+  return igemm_fprop(&t.p, xa, wa, ep, y, ws ? ws + t.a_bytes + t.b_bytes : nullptr, t.inner, st);
+}
+
+int ttb_conv2d_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(d, "conv2d_fprop")) return rc;
+  cudaStream_t st = as_stream(stream);
+  TensorPlan t;
+  if (!plan_tensor(d, 0, &t)) return direct_fprop(d, x, w, bias, y, st);
+  return fprop_tensor(d, t, x, w, bias_epilogue(bias), y, workspace, workspace_bytes, st);
+}
+
+/* ---- fused epilogues (north star: "fused bias/BN-scale/ReLU epilogues"; tensor path only) ------------------------- */
+
+int ttb_conv2d_fused_epilogue_supported(const ttb_conv_desc* d) {
+  if (!d) return 0;
+  TensorPlan t;
+  return plan_tensor(d, 0, &t) ? 1 : 0;
+}
+
+int ttb_conv2d_fprop_stats_chunks(const ttb_conv_desc* d) {
+  if (!d) return 0;
+  TensorPlan t;
+  if (!plan_tensor(d, 0, &t)) return 0;
+  if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop_stats_chunks(&t.p);
+  return igemm_fprop_stats_chunks(&t.p);
+}
+
+int ttb_conv2d_fprop_fused(const ttb_conv_desc* d, const float* x, const float* w, const ttb_conv_epilogue* ep, float* y,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate(d, "conv2d_fprop_fused")) return rc;
+  TensorPlan t;
+  TTB_REQUIRE(plan_tensor(d, 0, &t), "conv2d_fprop_fused: problem is not on the tensor path (ttb_conv2d_fused_epilogue_supported)");
+  return fprop_tensor(d, t, x, w, to_epilogue(ep), y, workspace, workspace_bytes, as_stream(stream));
 }
 
 int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, void* workspace,
@@ -293,12 +330,13 @@ int ttb_conv2d_dgrad_pack_weights(int count, const ttb_conv_desc* const* descs, 
   return igemm_pack_dgrad_weights(count, descs, w, w_packed, as_stream(stream));
 }
 
-int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, void* stream) {
+int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const float* w_packed, const float* accum, float* dx,
+                               void* stream) {
   if (int rc = validate(d, "conv2d_dgrad_prepacked")) return rc;
   TensorPlan t;
   TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops, "conv2d_dgrad_prepacked: problem needs the staged path");
-  if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream));
-  return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed);
+  if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream), accum);
+  return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed, accum);
 }
 
 /* ttb_conv2d_wgrad without the split reduction: *splits_out partial buffers of K*R*S*C floats are left at
@@ -342,17 +380,18 @@ size_t ttb_conv2d_workspace_size_bf16(const ttb_conv_desc* d, int pass) {
   return pass == 2 ? align256(igemm_workspace_size(d, 2)) : 0;
 }
 
-int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const float* bias, float* y,
-                          void* stream) {
+int ttb_conv2d_fprop_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* w_bf16, const ttb_conv_epilogue* ep,
+                          float* y, void* stream) {
   if (int rc = validate(d, "conv2d_fprop_bf16")) return rc;
   TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 0), "conv2d_fprop_bf16: problem needs the staged path (ttb_conv2d_fprop)");
-  return igemm_fprop(d, x_bf16, w_bf16, bias, y, nullptr, 0, as_stream(stream));
+  return igemm_fprop(d, x_bf16, w_bf16, to_epilogue(ep), y, nullptr, 0, as_stream(stream));
 }
 
-int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, float* dx, void* stream) {
+int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const void* w_packed_bf16, const float* accum,
+                          float* dx, void* stream) {
   if (int rc = validate(d, "conv2d_dgrad_bf16")) return rc;
   TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 1), "conv2d_dgrad_bf16: problem needs the staged path (ttb_conv2d_dgrad)");
-  return igemm_dgrad(d, dy_bf16, nullptr, dx, nullptr, 0, as_stream(stream), w_packed_bf16);
+  return igemm_dgrad(d, dy_bf16, nullptr, dx, nullptr, 0, as_stream(stream), w_packed_bf16, accum);
 }
 
 int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,

@@ -1,0 +1,166 @@
+// Shared epilogue of the tcgen05 convolution kernels (conv_igemm.cu, conv_flat.cu): accumulator tile (128 TMEM lanes x BN
+// fp32 columns) -> per-channel scale / bias -> residual add -> ReLU -> global rows, and - optionally - the per-channel
+// sum / sum of squares of what was stored, so that the BatchNorm that follows the convolution does not have to read the
+// tensor again for its statistics (reference: BatchNorm.forward's xp.mean / xp.var passes, autograd/grad_nn.py:923-924).
+#pragma once
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace ttb {
+
+constexpr int kStagePitch = 36;      // floats per staged epilogue row (32 + 4 pad: conflict-free float4 access)
+constexpr int kEpilogueStagingBytes = 4 * 32 * kStagePitch * 4;  // four epilogue warps x 32 rows
+
+// Running per-lane column statistics of one epilogue warp, kept in registers across all tiles of a persistent CTA.
+// Lane (sub = lane / 8, c4 = lane % 8) stores - and therefore accumulates - columns 4*c4 .. 4*c4+3 of every 32-column block
+// for rows sub, sub + 4, ... of the warp's 32 rows.  Sums are SHIFTED by a lane-private K (the first value the lane saw
+// in that column): sum(v - K), sum((v - K)^2) in fp32 do not cancel when |mean| >> sd, and each lane converts its own
+// sums to plain double sums at the end (epilogue_stats_flush), so K never has to agree between lanes.
+template <int BN>
+struct EpiStats {
+  float k[BN / 32][4], s0[BN / 32][4], s1[BN / 32][4];
+  int cnt;  // rows accumulated so far (identical for every column block)
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int b = 0; b < BN / 32; ++b)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[b][j] = s0[b][j] = s1[b][j] = 0.f;
+    cnt = 0;
+  }
+};
+
+// One tile.  `my_off`: element offset of the output row this thread's accumulator row maps to (< 0: the row does not
+// exist / is dropped); `st`: this warp's 32 x kStagePitch staging floats; `lane_block` = TMEM lane block (warp_id % 4).
+template <int BN, bool STATS>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, float* __restrict__ out, int64_t my_off, int n0,
+                                              int n_total, const Epilogue& ep, int lane_block, EpiStats<BN>& es) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, c4 = lane & 7;
+  const bool fresh = STATS && es.cnt == 0;
+  int tile_rows = 0;
+  // output offsets (in float4 units; every row offset is a multiple of 4 elements) of the 8 rows this lane stores, fetched
+  // from their owner lanes once per tile instead of once per column block
+  const int my_off4 = my_off < 0 ? -1 : (int)(my_off >> 2);
+  int off4[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    off4[it] = __shfl_sync(0xffffffffu, my_off4, it * 4 + sub);
+    if (STATS && off4[it] >= 0) ++tile_rows;
+  }
+#ifdef TTB_TUNING
+  const int dbg = ep.relu >> 8;  // timing experiments (wrong results): 1 no global stores, 2 no staging, 4 no TMEM load
+#else
+  constexpr int dbg = 0;
+#endif
+  float4* const out4 = reinterpret_cast<float4*>(out);
+  const float4* const accum4 = reinterpret_cast<const float4*>(ep.accum);
+  const bool relu = (ep.relu & 1) != 0;
+  // (fully unrolled: the statistics live in registers indexed by cb)
+#pragma unroll
+  for (int cb = 0; cb < BN / 32; ++cb) {
+    const int col0 = n0 + cb * 32;
+    if (col0 >= n_total) break;  // warp-uniform
+    uint32_t r[32];
+    if (!(dbg & 4)) {
+      ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
+      ptx::tmem_ld_wait();
+    }
+    if (ep.scale) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < n_total) r[j] = __float_as_uint(__uint_as_float(r[j]) * __ldg(ep.scale + col0 + j));
+    }
+    if (ep.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < n_total) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(ep.bias + col0 + j));
+    }
+    // own row -> smem (8 x float4), then 4 rows x 128 B per store instruction
+    float4* srow = reinterpret_cast<float4*>(st + lane * kStagePitch);
+    if (!(dbg & 2)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+    }
+    __syncwarp();
+    const bool col_ok = col0 + c4 * 4 < n_total;
+    const int colq = (col0 >> 2) + c4;
+    bool seen = false;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + sub;
+      float4 v = (dbg & 2) ? make_float4(__uint_as_float(r[it]), 0.f, 0.f, 0.f)
+                           : *reinterpret_cast<const float4*>(st + rr * kStagePitch + c4 * 4);
+      if (off4[it] >= 0 && col_ok) {
+        const int64_t o4 = (int64_t)off4[it] + colq;
+        if (accum4) {
+          const float4 a = ld_f4_stream(reinterpret_cast<const float*>(accum4 + o4));
+          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        if (relu) {
+          v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+          v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+        }
+        if (!(dbg & 1)) out4[o4] = v;
+        if (STATS) {
+          if (fresh && !seen) { es.k[cb][0] = v.x; es.k[cb][1] = v.y; es.k[cb][2] = v.z; es.k[cb][3] = v.w; }
+          seen = true;
+          const float dx = v.x - es.k[cb][0], dy = v.y - es.k[cb][1], dz = v.z - es.k[cb][2], dw = v.w - es.k[cb][3];
+          es.s0[cb][0] += dx; es.s0[cb][1] += dy; es.s0[cb][2] += dz; es.s0[cb][3] += dw;
+          es.s1[cb][0] = fmaf(dx, dx, es.s1[cb][0]); es.s1[cb][1] = fmaf(dy, dy, es.s1[cb][1]);
+          es.s1[cb][2] = fmaf(dz, dz, es.s1[cb][2]); es.s1[cb][3] = fmaf(dw, dw, es.s1[cb][3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (STATS) es.cnt += tile_rows;
+}
+
+// End of a CTA's tile loop (all four epilogue warps call it): lane sums -> plain double sums -> warp -> CTA, then one row
+// segment of the partial buffer: row[c_total*0 + n0 + col] = sum(v), row[c_total + n0 + col] = sum(v*v) over every output
+// row this CTA stored.  `stage_smem`: the CTA's epilogue staging area (each warp reuses its own slice: BN*2 doubles
+// <= 32*kStagePitch floats); `bar_id`: a named barrier reserved for the 128 epilogue threads.
+template <int BN>
+__device__ __forceinline__ void epilogue_stats_flush(const EpiStats<BN>& es, float* stage_smem, int ep_warp, int bar_id,
+                                                     double* __restrict__ row, int n0, int n_total) {
+  static_assert(BN * 2 * sizeof(double) <= 32 * kStagePitch * sizeof(float), "per-warp statistics must fit its staging slice");
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, c4 = lane & 7;
+  double* mine = reinterpret_cast<double*>(stage_smem + ep_warp * (32 * kStagePitch));
+  const double n = (double)es.cnt;
+#pragma unroll
+  for (int cb = 0; cb < BN / 32; ++cb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double k = (double)es.k[cb][j], t0 = (double)es.s0[cb][j], t1 = (double)es.s1[cb][j];
+      double d0 = t0 + n * k;
+      double d1 = t1 + 2.0 * k * t0 + n * k * k;
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 8);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 8);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 16);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+      if (sub == 0) {
+        mine[(cb * 32 + c4 * 4 + j) * 2 + 0] = d0;
+        mine[(cb * 32 + c4 * 4 + j) * 2 + 1] = d1;
+      }
+    }
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  const int e = ep_warp * 32 + lane;
+  for (int col = e; col < BN; col += 128) {
+    if (n0 + col >= n_total) break;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {  // fixed order: deterministic
+      const double* p = reinterpret_cast<const double*>(stage_smem + w * (32 * kStagePitch));
+      t0 += p[col * 2 + 0];
+      t1 += p[col * 2 + 1];
+    }
+    row[n0 + col] = t0;
+    row[n_total + n0 + col] = t1;
+  }
+}
+
+}  // namespace ttb

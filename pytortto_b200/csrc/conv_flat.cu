@@ -1,6 +1,11 @@
-// "Flat-shift halo tile" fprop / dgrad.  Validated on B200 (parity vs the exact fp32 kernels on every case of
-// scripts/flat_check.py and tests/test_gpu_flat.py).  Two variants:
-//   * RESIDENT (default path of the 64 -> 64 channel 3x3 layers, TF32): the WHOLE weight matrix (K x R*S*C, 144 KB for
+// "Flat-shift halo tile" fprop / dgrad: an EXPERIMENT kept in the tuning build only (-DTTB_TUNING; the release library
+// does not contain it).  Validated on B200 (parity vs the exact fp32 kernels on every case of scripts/flat_check.py and
+// tests/test_gpu_flat.py), but not faster than the production im2col kernel where it matters: on the 64 -> 64 channel
+// 3x3 layer at batch 256 the resident variant measured 54.8 - 61.2 us against 56.5 - 56.8 us (graph replay, same box), and
+// with epilogue statistics 65.5 against 58.2 us (profiles/r2_conv_layer_probe.txt).  The layer is bound by the N = 64
+// tcgen05.mma itself (~62 tensor-pipe cycles per MMA, ncu: the 4 KB A operand is re-read from shared memory by every
+// MMA) and by the strip loads, not by the A re-reads from L2 this design removes.  Two variants:
+//   * RESIDENT (TTB_FLAT=-1: the 64 -> 64 channel 3x3 layers, TF32): the WHOLE weight matrix (K x R*S*C, 144 KB for
 //     64 x 576 fp32) is loaded into shared memory once per CTA and stays there for all of the CTA's tiles; the main
 //     loop then has no weight hand-shakes at all - per 32-channel slab one strip wait and 9 taps x 4 tcgen05.mma issued
 //     back to back.  The production im2col kernel is issue-bound on these layers (one mbarrier hand-shake per 4 small
@@ -31,15 +36,17 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 #include "sm100_ptx.cuh"
 
 namespace ttb {
 
+#ifdef TTB_TUNING
 namespace {
 
 constexpr int kFlatTileM = 128;
 constexpr int kFlatMaxTaps = 64;
-constexpr int kFlatStagePitch = 36;  // floats per staged epilogue row
+constexpr int kFlatStagePitch = kStagePitch;  // floats per staged epilogue row (conv_epilogue.cuh)
 constexpr int kFlatSlabsPerStrip = 2;  // 32-channel slabs brought in per strip stage (64 channels)
 constexpr int kFlatStripStages = 2;
 constexpr int kFlatBProducers = 2;
@@ -49,7 +56,7 @@ struct FlatParams {
   CUtensorMap tmX;   // 4-D tiled over NHWC x: dims (C, W, H, N), box (32, Wp, 1, 1)
   CUtensorMap tmB;   // 2-D tiled over the weight matrix [rows = output channels][cols = (tap, c)], box (32, BN)
   float* out;        // dense NHWC output [N][P][Q][K]
-  const float* bias; // [K] or null
+  Epilogue ep;       // per-channel scale / bias, residual, ReLU, statistics (common.cuh)
   int n_img, hp, wp, pad_h, pad_w;   // padded grid
   int p_out, q_out, k_out;           // valid outputs per image, output channels
   int taps_r, taps_s;                // filter size
@@ -59,54 +66,21 @@ struct FlatParams {
   int b_koff[kFlatMaxTaps];          // column of tap t's K-slice in the weight matrix (dgrad: flipped taps)
 };
 
-// accumulator (128 lanes x BN fp32 columns in TMEM) -> global rows; rows at padding positions are dropped
-template <int BN>
-__device__ __forceinline__ void flat_epilogue(uint32_t tmem_acc, float* stage_smem, const FlatParams& P, int64_t f0, int n0,
-                                              int ep_warp, int lane_block) {
-  const int lane = threadIdx.x & 31;
-  float* st = stage_smem + ep_warp * (32 * kFlatStagePitch);
-  const int64_t f = f0 + lane_block * 32 + lane;
-  int64_t my_off = -1;
-  if (f < P.m_flat) {
-    const int q = (int)(f % P.wp);
-    const int64_t t = f / P.wp;
-    const int p = (int)(t % P.hp);
-    const int64_t n = t / P.hp;
-    if (q < P.q_out && p < P.p_out) my_off = ((n * P.p_out + p) * P.q_out + q) * (int64_t)P.k_out;
-  }
-#pragma unroll 1
-  for (int cb = 0; cb < BN / 32; ++cb) {
-    const int col0 = n0 + cb * 32;
-    if (col0 >= P.k_out) break;  // warp-uniform
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
-    ptx::tmem_ld_wait();
-    if (P.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < P.k_out) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(P.bias + col0 + j));
-    }
-    float4* srow = reinterpret_cast<float4*>(st + lane * kFlatStagePitch);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                            __uint_as_float(r[4 * j + 3]));
-    __syncwarp();
-    const int sub = lane >> 3, c4 = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + sub;
-      const int64_t off = __shfl_sync(0xffffffffu, my_off, rr);
-      const float4 v = *reinterpret_cast<const float4*>(st + rr * kFlatStagePitch + c4 * 4);
-      if (off >= 0 && col0 + c4 * 4 < P.k_out) *reinterpret_cast<float4*>(P.out + off + col0 + c4 * 4) = v;
-    }
-    __syncwarp();
-  }
+// accumulator row f (padded-flat index) -> element offset of its output row; rows at padding positions are dropped (-1)
+__device__ __forceinline__ int64_t flat_row_offset(const FlatParams& P, int64_t f) {
+  if (f >= P.m_flat) return -1;
+  const int q = (int)(f % P.wp);
+  const int64_t t = f / P.wp;
+  const int p = (int)(t % P.hp);
+  const int64_t n = t / P.hp;
+  if (q >= P.q_out || p >= P.p_out) return -1;
+  return ((n * P.p_out + p) * P.q_out + q) * (int64_t)P.k_out;
 }
 
 // RES: resident weights - NB is ignored, `P.c_blocks * taps` weight tiles live in shared memory for the whole kernel and a
 // strip stage holds ONE 32-channel slab (kSlabsPerStrip = 1)
-template <int BN, int NB, bool RES>
+// STATS: per-channel sum / sum of squares of the stored outputs, one [2][K] double row per CTA (needs one N tile: nt == 1)
+template <int BN, int NB, bool RES, bool STATS>
 __global__ void __launch_bounds__(kFlatThreads, 1)
 igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
@@ -315,6 +289,9 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
   } else {
     // ===================== epilogue =====================
     const int ew = warp - (kMmaWarp + 1);
+    float* const my_stage = staging + ew * (32 * kFlatStagePitch);
+    EpiStats<BN> es;
+    if (STATS) es.reset();
     int it = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int64_t f0 = (t / nt) * kFlatTileM;
@@ -322,11 +299,14 @@ igemm_flat_kernel(const __grid_constant__ FlatParams P) {
       const int buf = it & 1;
       ptx::mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
       ptx::tc_fence_after();
-      flat_epilogue<BN>(tmem_base + (uint32_t)(buf * kAccCols), staging, P, f0, n0, ew, warp & 3);
+      epilogue_tile<BN, STATS>(tmem_base + (uint32_t)(buf * kAccCols), my_stage, P.out,
+                               flat_row_offset(P, f0 + (warp & 3) * 32 + lane), n0, P.k_out, P.ep, warp & 3, es);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
+    if (STATS && it > 0)
+      epilogue_stats_flush<BN>(es, staging, ew, 1, P.ep.stats + (int64_t)blockIdx.x * 2 * P.k_out, 0, P.k_out);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -352,7 +332,13 @@ int flat_load_driver() {
 
 constexpr size_t kFlatSmemLimit = 232448 - 512;  // 227 KB per CTA minus the kernel's static barriers
 
-template <int BN, int NB, bool RES>
+static unsigned flat_grid(int64_t m_flat, int k_out, int bn) {
+  const int64_t tiles = ceil_div(m_flat, kFlatTileM) * ceil_div(k_out, bn);
+  const int sms = sm_count();
+  return (unsigned)(tiles < sms ? tiles : sms);
+}
+
+template <int BN, int NB, bool RES, bool STATS = false>
 int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) {
   const size_t btiles = RES ? (size_t)P.c_blocks * P.taps_r * P.taps_s : (size_t)NB;
   const size_t smem = strip_bytes_total + btiles * BN * 128 + 4 * 32 * kFlatStagePitch * 4 + 1024;
@@ -362,26 +348,24 @@ int flat_launch(const FlatParams& P, size_t strip_bytes_total, cudaStream_t st) 
   }
   static size_t attr = 0;
   if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_flat_kernel<BN, NB, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_flat_kernel<BN, NB, RES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("conv flat path: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
       return 1;
     }
     attr = smem;
   }
-  const int64_t tiles = ceil_div(P.m_flat, kFlatTileM) * ceil_div(P.k_out, BN);
-  const int sms = sm_count();
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  launch_k(igemm_flat_kernel<BN, NB, RES>, grid, kFlatThreads, smem, st, P);
+  const unsigned grid = flat_grid(P.m_flat, P.k_out, BN);
+  launch_k(igemm_flat_kernel<BN, NB, RES, STATS>, grid, kFlatThreads, smem, st, P);
   return check_launch("igemm_flat_kernel");
 }
 
 }  // namespace
 
-// TTB_FLAT (tuning build): -1 = default (the resident-weight variant where it applies), 0 = never, 1 = every eligible
-// problem (also the streamed variant, which is slower than the production kernel)
+// TTB_FLAT: 0 = never (default), -1 = the resident-weight variant where it applies, 1 = every eligible problem (also the
+// streamed variant)
 static int flat_mode() {
-  static const int mode = tuning_knob("TTB_FLAT", -1);
+  static const int mode = tuning_knob("TTB_FLAT", 0);
   return mode;
 }
 
@@ -422,7 +406,7 @@ static bool flat_resident_ok(const FlatProblem& g) {
 
 // in: NHWC fp32 [n][h_in][w_in][c_in]; wmat: [k_out rows][r*s*c_in cols] fp32 with tap t's slice at column koff[t];
 // out: dense NHWC fp32 [n][p_out][q_out][k_out]
-static int flat_run(const FlatProblem& g, const float* in, const float* wmat, const int* koff, const float* bias, float* out,
+static int flat_run(const FlatProblem& g, const float* in, const float* wmat, const int* koff, const Epilogue& ep, float* out,
                     cudaStream_t st) {
   if (flat_load_driver()) return 1;
   static thread_local FlatParams P;
@@ -461,7 +445,8 @@ static int flat_run(const FlatProblem& g, const float* in, const float* wmat, co
     }
   }
   P.out = out;
-  P.bias = bias;
+  P.ep = ep;
+  P.ep.relu = (ep.relu ? 1 : 0) | (tuning_knob("TTB_EPI_DBG", 0) << 8);  // (experiment bits: tuning build only)
   P.n_img = g.n;
   P.hp = hp;
   P.wp = wp;
@@ -476,7 +461,13 @@ static int flat_run(const FlatProblem& g, const float* in, const float* wmat, co
   P.rows_max = flat_rows_max_of(g);
   P.m_flat = (int64_t)g.n * hp * wp;
   for (int t = 0; t < g.r * g.s; ++t) P.b_koff[t] = koff[t];
-  if (flat_resident_ok(g)) return flat_launch<64, 6, true>(P, flat_strip_bytes(g, 1), st);
+  if (flat_resident_ok(g))
+    return ep.stats ? flat_launch<64, 6, true, true>(P, flat_strip_bytes(g, 1), st)
+                    : flat_launch<64, 6, true, false>(P, flat_strip_bytes(g, 1), st);
+  if (ep.stats) {
+    set_error("conv flat path: epilogue statistics need the resident-weight variant");
+    return 1;
+  }
   const size_t strips = flat_strip_bytes(g, kFlatSlabsPerStrip);
   switch (bn) {
     case 128: return flat_launch<128, 4, false>(P, strips, st);
@@ -507,18 +498,34 @@ bool flat_fprop_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && 
 bool flat_dgrad_supported(const ttb_conv_desc* d) { return flat_common_ok(d) && flat_take(flat_dgrad_problem(d)); }
 
 // x: NHWC fp32, w: [K][R][S][C] fp32, y: dense NHWC fp32
-int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+int flat_fprop(const ttb_conv_desc* d, const float* x, const float* w, const Epilogue& ep, float* y, cudaStream_t st) {
   int koff[kFlatMaxTaps];
   for (int t = 0; t < d->r * d->s; ++t) koff[t] = t * d->c;
-  return flat_run(flat_fprop_problem(d), x, w, koff, bias, y, st);
+  return flat_run(flat_fprop_problem(d), x, w, koff, ep, y, st);
+}
+
+// rows of the [chunks][2][K] statistics partial buffer flat_fprop writes for this problem (Epilogue::stats); 0: the
+// resident-weight variant (the only one that emits statistics) does not take the problem
+int flat_fprop_stats_chunks(const ttb_conv_desc* d) {
+  const FlatProblem g = flat_fprop_problem(d);
+  if (!flat_common_ok(d) || !flat_resident_ok(g)) return 0;
+  return (int)flat_grid((int64_t)g.n * (g.h_in + 2 * g.pad_h) * (g.w_in + 2 * g.pad_w), g.k_out, 64);
 }
 
 // dy: NHWC fp32 [N][P][Q][K], w_packed: [C][R][S][K] fp32 (the dgrad re-ordering), dx: dense NHWC fp32 [N][H][W][C]
-int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st) {
+int flat_dgrad(const ttb_conv_desc* d, const float* dy, const float* w_packed, float* dx, cudaStream_t st, const float* accum) {
   int koff[kFlatMaxTaps];
   for (int r = 0; r < d->r; ++r)
     for (int s = 0; s < d->s; ++s) koff[r * d->s + s] = ((d->r - 1 - r) * d->s + (d->s - 1 - s)) * d->k;  // flipped taps
-  return flat_run(flat_dgrad_problem(d), dy, w_packed, koff, nullptr, dx, st);
+  return flat_run(flat_dgrad_problem(d), dy, w_packed, koff, Epilogue{nullptr, nullptr, accum, 0, nullptr}, dx, st);
 }
+
+#else  // release build: the production im2col kernels take every problem
+bool flat_fprop_supported(const ttb_conv_desc*) { return false; }
+bool flat_dgrad_supported(const ttb_conv_desc*) { return false; }
+int flat_fprop(const ttb_conv_desc*, const float*, const float*, const Epilogue&, float*, cudaStream_t) { return 1; }
+int flat_fprop_stats_chunks(const ttb_conv_desc*) { return 0; }
+int flat_dgrad(const ttb_conv_desc*, const float*, const float*, float*, cudaStream_t, const float*) { return 1; }
+#endif
 
 }  // namespace ttb

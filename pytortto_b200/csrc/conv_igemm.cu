@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 #include "sm100_ptx.cuh"
 
 namespace ttb {
@@ -42,7 +43,6 @@ static inline Elem elem_of(bool bf16) {
   return bf16 ? Elem{true, 2, 64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16} : Elem{false, 4, 32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32};
 }
 constexpr int kThreadsIgemm = 192;
-constexpr int kStagePitch = 36;      // floats per staged epilogue row (32 + 4 pad: conflict-free float4 access)
 
 // ------------------------------------------------------------------------------------------------------------
 // driver entry points (resolved through the runtime so the library has no link-time libcuda dependency)
@@ -146,7 +146,7 @@ struct OutMap {            // accumulator row m -> element offset of the output 
 struct FwdParams {         // fprop / dgrad (K-major A via im2col TMA, K-major B via tiled TMA)
   CUtensorMap tmA, tmB;
   OutMap o;
-  const float* bias;       // [n_total] or null
+  Epilogue ep;             // per-output-channel scale / bias, accumulate-into, ReLU (common.cuh)
   int c_blocks;            // reduction channels / 32
   int num_taps;
   int base_w, base_h;      // coordinates of base pixel (i=0, j=0)
@@ -177,53 +177,15 @@ struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B =
 };
 
 // ------------------------------------------------------------------------------------------------------------
-// shared epilogue: accumulator (128 lanes x BN fp32 columns in TMEM) -> global rows
+// accumulator row m of a tile -> element offset of its output row (conv_epilogue.cuh does the rest)
 // ------------------------------------------------------------------------------------------------------------
-template <int BN>
-__device__ __forceinline__ void epilogue_store(uint32_t tmem_base, float* stage_smem, const OutMap& o, int m0, int n0,
-                                               const float* bias, int ep_warp /*0..3 position among epilogue warps*/,
-                                               int lane_block /*TMEM lane block = warp_id % 4*/) {
-  const int lane = threadIdx.x & 31;
-  float* st = stage_smem + ep_warp * (32 * kStagePitch);
-  const int row = lane_block * 32 + lane;  // accumulator row owned by this thread
-  const int m = m0 + row;
-  int64_t my_off = -1;
-  if (m < o.m_total) {
-    int j = m % o.q_dim;
-    int t = m / o.q_dim;
-    int i = t % o.p_dim;
-    int n = t / o.p_dim;
-    my_off = o.base + (int64_t)n * o.n_stride + (int64_t)i * o.h_stride + (int64_t)j * o.w_stride;
-  }
-#pragma unroll 1
-  for (int cb = 0; cb < BN / 32; ++cb) {
-    const int col0 = n0 + cb * 32;
-    if (col0 >= o.n_total) break;  // warp-uniform
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
-    ptx::tmem_ld_wait();
-    if (bias) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < o.n_total) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(bias + col0 + j));
-    }
-    // own row -> smem (8 x float4), then 4 rows x 128 B per store instruction
-    float4* srow = reinterpret_cast<float4*>(st + lane * kStagePitch);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                            __uint_as_float(r[4 * j + 3]));
-    __syncwarp();
-    const int sub = lane >> 3, c4 = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + sub;
-      int64_t off = __shfl_sync(0xffffffffu, my_off, rr);
-      float4 v = *reinterpret_cast<const float4*>(st + rr * kStagePitch + c4 * 4);
-      if (off >= 0 && col0 + c4 * 4 < o.n_total) *reinterpret_cast<float4*>(o.out + off + col0 + c4 * 4) = v;
-    }
-    __syncwarp();
-  }
+__device__ __forceinline__ int64_t out_row_offset(const OutMap& o, int m) {
+  if (m >= o.m_total) return -1;
+  const int j = m % o.q_dim;
+  const int t = m / o.q_dim;
+  const int i = t % o.p_dim;
+  const int n = t / o.p_dim;
+  return o.base + (int64_t)n * o.n_stride + (int64_t)i * o.h_stride + (int64_t)j * o.w_stride;
 }
 
 // Up to kMaxMulti independent problems of the same shape class in one launch: the stride-parity classes of a strided
@@ -244,10 +206,11 @@ struct FwdParamsMulti {
 //   * two accumulator buffers in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.
 // Warp roles: [0, NPROD) producers, NPROD = MMA issuer + TMEM owner, NPROD+1 .. NPROD+4 epilogue.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kEpilogueStagingBytes = 4 * 32 * kStagePitch * 4;
-
-template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
-__global__ void __launch_bounds__((NPROD + 5) * 32, 1)
+// STATS: the epilogue also accumulates the per-channel sum / sum of squares of everything this CTA stores and writes
+// them as one segment of a [gridDim.x / nt][2][n_total] double partial buffer (P.ep.stats); the host then sizes the grid
+// as a multiple of nt, so that every CTA keeps the same N tile for all of its tiles (conv_epilogue.cuh).
+template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16, bool STATS>
+__global__ void __launch_bounds__((NPROD + 5) * 32, BN <= 64 ? 2 : 1)  // narrow tiles: two CTAs per SM (<= 128 registers)
 igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   static_assert(NSTAGES % NPROD == 0, "a stage must always be filled by the same producer thread");
@@ -404,7 +367,10 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
   } else {
     // ===================== epilogue =====================
     const int ew = warp - (NPROD + 1);
-    int it = 0;
+    float* const my_stage = staging + ew * (32 * kStagePitch);
+    EpiStats<BN> es;
+    if (STATS) es.reset();
+    int it = 0, n0_last = 0;
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++it) {
       int cls, m0, n0;
       decode(t, cls, m0, n0);
@@ -413,11 +379,18 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
       ptx::mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
       ptx::tc_fence_after();
       if (tr && ew == 0 && lane == 0 && it < 250) tr[528 + 2 * it] = clock64();
-      epilogue_store<BN>(tmem_base + (uint32_t)(buf * kAccCols), staging, P.o, m0, n0, P.bias, ew, warp & 3);
+      epilogue_tile<BN, STATS>(tmem_base + (uint32_t)(buf * kAccCols), my_stage, P.o.out,
+                               out_row_offset(P.o, m0 + (warp & 3) * 32 + lane), n0, P.o.n_total, P.ep, warp & 3, es);
+      n0_last = n0;
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
       if (tr && ew == 0 && lane == 0 && it < 250) tr[529 + 2 * it] = clock64();
+    }
+    if (STATS && it > 0) {
+      const FwdParams& P = PM.p[0];
+      epilogue_stats_flush<BN>(es, staging, ew, 1, P.ep.stats + (int64_t)(blockIdx.x / nt) * 2 * P.o.n_total, n0_last,
+                               P.o.n_total);
     }
   }
   ptx::tc_fence_before();
@@ -430,7 +403,7 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
 // wgrad kernel: D[k (128 lanes), (tap,c) (BN columns)] += dY[pixels, k]^T * A[pixels, (tap,c)]
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, int KP, int NSTAGES, bool BF16>
-__global__ void __launch_bounds__(kThreadsIgemm)
+__global__ void __launch_bounds__(kThreadsIgemm, 1)
 igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   constexpr int kSlabCh = BF16 ? 64 : 32;            // channels per 128-byte-wide MN slab
@@ -567,7 +540,9 @@ igemm_wgrad_kernel(const __grid_constant__ WgradParams P) {
     ptx::tc_fence_after();
     OutMap o = P.o;
     o.out = P.o.out + (int64_t)split * P.split_stride;
-    epilogue_store<BN>(tmem_base, reinterpret_cast<float*>(smem), o, k0, n0, nullptr, warp - 2, warp & 3);
+    EpiStats<BN> none;
+    epilogue_tile<BN, false>(tmem_base, reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch), o.out,
+                             out_row_offset(o, k0 + (warp & 3) * 32 + lane), n0, o.n_total, Epilogue{}, warp & 3, none);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -739,6 +714,8 @@ static bool common_ok(const ttb_conv_desc* d) {
   if (d->r * d->s > kMaxTaps) return false;
   if (d->n <= 0 || d->p <= 0 || d->q <= 0) return false;
   if ((int64_t)d->n * d->p * d->q >= (1ll << 31) || (int64_t)d->n * d->h * d->w >= (1ll << 31)) return false;
+  // (the epilogue addresses output rows by 32-bit offsets in float4 units)
+  if ((int64_t)d->n * d->p * d->q * d->k >= (1ll << 33) || (int64_t)d->n * d->h * d->w * d->c >= (1ll << 33)) return false;
   if (d->stride_h > 8 || d->stride_w > 8) return false;
   if ((d->r - 1) * d->dil_h > 255 || (d->s - 1) * d->dil_w > 255) return false;
   return true;
@@ -786,13 +763,27 @@ static int pick_bn(int64_t m_total, int n_total) {
   return 32;
 }
 
-template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16>
+constexpr size_t persist_smem_bytes(int bn, int nstages, int kps) {
+  return (size_t)nstages * kps * (kTileM * 128 + bn * 128) + kEpilogueStagingBytes + 1024;
+}
+
+// CTAs of a persistent launch: one per SM (two for the narrow tiles whose ring is sized for it), never more than tiles;
+// with epilogue statistics a multiple of the N-tile count, so that a CTA keeps one N tile (see the kernel)
+static unsigned persist_grid(int64_t tiles, int nt, size_t smem, bool stats) {
+  int sms = sm_count() * (smem <= 113 * 1024 ? 2 : 1);
+  sms = tuning_knob("TTB_PERSIST_GRID", sms);  // experiment switch (tuning build only): cap the number of CTAs
+  int64_t grid = tiles < sms ? tiles : sms;
+  if (stats && nt > 1) grid = grid >= nt ? grid / nt * nt : nt;  // (tiles is a multiple of nt)
+  return (unsigned)grid;
+}
+
+template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16, bool STATS>
 static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NSTAGES * KPS * (kTileM * 128 + BN * 128) + kEpilogueStagingBytes + 1024;
+  constexpr size_t smem = persist_smem_bytes(BN, NSTAGES, KPS);
   static_assert(smem <= 232448, "shared memory budget of one SM");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16, STATS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -800,39 +791,55 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
     }
     attr_set = true;
   }
+  const int nt = (int)ceil_div(PM.p[0].o.n_total, BN);
   int64_t tiles = 0;
-  for (int i = 0; i < count; ++i) tiles += (int64_t)ceil_div(PM.p[i].o.m_total, kTileM) * ceil_div(PM.p[0].o.n_total, BN);
+  for (int i = 0; i < count; ++i) tiles += (int64_t)ceil_div(PM.p[i].o.m_total, kTileM) * nt;
   // narrow tiles leave room for two CTAs per SM (two independent MMA-issue streams: a 64-column K-block is 128
   // tensor-core cycles but ~300 cycles of issue-side latency per CTA)
-  int sms = sm_count() * (smem <= 113 * 1024 ? 2 : 1);
-  sms = tuning_knob("TTB_PERSIST_GRID", sms);  // experiment switch (tuning build only): cap the number of CTAs
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16>, grid, (NPROD + 5) * 32, smem, st, PM, count);
+  const unsigned grid = persist_grid(tiles, nt, smem, STATS);
+  launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16, STATS>, grid, (NPROD + 5) * 32, smem, st, PM, count);
   return check_launch("igemm_fwd_persist_kernel");
 }
 
-static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
-  // <BN, stages, producer warps, K-blocks per stage>.  Measured on B200 (TF32): the MMA warp pays ~170 cycles per
-  // stage hand-shake + ~30 cycles per MMA issue against 32 / 64 / 128 tensor-core cycles per MMA at N = 64 / 128 / 256,
-  // so N = 256 is tensor-bound (512 cycles per K-block), N = 128 nearly (300 vs 256) and N <= 64 issue-bound: narrow
-  // tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
-  // Two K-blocks per stage (KPS = 2) halve the hand-shakes but the 3-stage ring that fits then hides less latency:
-  // measured slower (layer 2: 40.8 vs 38.2 us), kept instantiable for experiments (TTB_KPS2=1).
-  static const int kps2 = tuning_knob("TTB_KPS2", 0);
-  if (bf16) {
-    switch (bn) {
-      case 256: return launch_persist<256, 4, 2, 1, true>(PM, count, st);
-      case 128: return launch_persist<128, 6, 3, 1, true>(PM, count, st);
-      case 64: return launch_persist<64, 3, 3, 1, true>(PM, count, st);
-      default: return launch_persist<32, 3, 3, 1, true>(PM, count, st);
-    }
-  }
+// <BN, stages, producer warps, K-blocks per stage>.  Measured on B200 (TF32): the MMA warp pays ~170 cycles per
+// stage hand-shake + ~30 cycles per MMA issue against 32 / 64 / 128 tensor-core cycles per MMA at N = 64 / 128 / 256,
+// so N = 256 is tensor-bound (512 cycles per K-block), N = 128 nearly (300 vs 256) and N <= 64 issue-bound: narrow
+// tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
+// Two K-blocks per stage (KPS = 2) halve the hand-shakes but the 3-stage ring that fits then hides less latency:
+// measured slower (layer 2: 40.8 vs 38.2 us) and dropped.
+struct PersistCfg { int nstages, nprod, kps; };
+static PersistCfg persist_cfg(int bn) {
   switch (bn) {
-    case 256: return launch_persist<256, 4, 2, 1, false>(PM, count, st);
-    case 128: return kps2 ? launch_persist<128, 3, 3, 2, false>(PM, count, st) : launch_persist<128, 6, 3, 1, false>(PM, count, st);
-    case 64: return kps2 ? launch_persist<64, 4, 2, 2, false>(PM, count, st) : launch_persist<64, 3, 3, 1, false>(PM, count, st);
-    default: return launch_persist<32, 3, 3, 1, false>(PM, count, st);
+    case 256: return {4, 2, 1};
+    case 128: return {6, 3, 1};
+    default: return {3, 3, 1};
   }
+}
+
+template <bool BF16, bool STATS>
+static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_persist<256, 4, 2, 1, BF16, STATS>(PM, count, st);
+    case 128: return launch_persist<128, 6, 3, 1, BF16, STATS>(PM, count, st);
+    case 64: return launch_persist<64, 3, 3, 1, BF16, STATS>(PM, count, st);
+    default: return launch_persist<32, 3, 3, 1, BF16, STATS>(PM, count, st);
+  }
+}
+
+static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
+  const bool stats = count == 1 && PM.p[0].ep.stats != nullptr;
+  if (bf16) return stats ? launch_persist_sel<true, true>(PM, count, bn, st) : launch_persist_sel<true, false>(PM, count, bn, st);
+  return stats ? launch_persist_sel<false, true>(PM, count, bn, st) : launch_persist_sel<false, false>(PM, count, bn, st);
+}
+
+// rows of the [chunks][2][K] statistics partial buffer an fprop launch of this problem writes (Epilogue::stats)
+int igemm_fprop_stats_chunks(const ttb_conv_desc* d) {
+  const int64_t m_total = (int64_t)d->n * d->p * d->q;
+  const int bn = pick_bn(m_total, d->k);
+  const PersistCfg c = persist_cfg(bn);
+  const int nt = (int)ceil_div(d->k, bn);
+  const int64_t tiles = ceil_div(m_total, kTileM) * nt;
+  return (int)(persist_grid(tiles, nt, persist_smem_bytes(bn, c.nstages, c.kps), true) / nt);
 }
 
 static int wgrad_variant() {  // bring-up / tuning knob (tuning build only): 0 = default
@@ -892,7 +899,7 @@ static int igemm_dbg() {  // timing experiments that produce WRONG results: tuni
 }
 
 // x, w: operands in the element type of d->math_mode (fp32 for TF32, bf16 for BF16); y, bias: fp32
-int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const float* bias, float* y, void* /*ws*/,
+int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, void* /*ws*/,
                 size_t /*ws_bytes*/, cudaStream_t st) {
   if (load_driver_fns()) return 1;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
@@ -910,7 +917,8 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
   P.o.q_dim = d->q;
   P.o.m_total = d->n * d->p * d->q;
   P.o.n_total = d->k;
-  P.bias = bias;
+  P.ep = ep;
+  P.ep.relu = (ep.relu ? 1 : 0) | (tuning_knob("TTB_EPI_DBG", 0) << 8);  // (experiment bits: tuning build only)
   P.c_blocks = d->c / el.per_row;
   P.num_taps = d->r * d->s;
   P.base_w = -d->pad_w;
@@ -936,7 +944,8 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const floa
 
 // `prepacked` != null: the weights are already in the [C][R][S][K] order (igemm_pack_dgrad_weights), w / ws unused
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st, const void* prepacked) {
+                cudaStream_t st, const void* prepacked, const float* accum) {
+  // (`accum`, may be null: added to dx in the epilogue - the gradient already pending for the same tensor)
   if (load_driver_fns()) return 1;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * el.size;
@@ -1005,7 +1014,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         P.o.q_dim = wb;
         P.o.m_total = d->n * ha * wb;
         P.o.n_total = d->c;
-        P.bias = nullptr;
+        P.ep = Epilogue{nullptr, nullptr, accum, tuning_knob("TTB_EPI_DBG", 0) << 8, nullptr};
         P.c_blocks = d->k / el.per_row;
         P.num_taps = cls.nr * cls.ns;
         P.base_w = lo_w;
@@ -1035,8 +1044,9 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
       if (launch_persist_bn(PM, n_multi, bn, el.bf16, st)) return 1;
     }
-    if (pass == 0 && need_zero) {
-      cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st);
+    if (pass == 0 && need_zero) {  // input pixels no filter tap reaches: zero (or just the pending gradient)
+      const size_t bytes = (size_t)d->n * d->h * d->w * d->c * sizeof(float);
+      cudaError_t e = accum ? cudaMemcpyAsync(dx, accum, bytes, cudaMemcpyDeviceToDevice, st) : cudaMemsetAsync(dx, 0, bytes, st);
       if (e != cudaSuccess) {
         set_error("conv2d_dgrad: memset failed: %s", cudaGetErrorString(e));
         return 1;

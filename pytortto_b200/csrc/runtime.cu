@@ -41,7 +41,7 @@ extern "C" {
 
 const char* ttb_last_error(void) { return ttb::g_err; }
 
-int ttb_version(void) { return 3; }
+int ttb_version(void) { return 4; }
 
 int ttb_device_sm_count(int* out) {
   if (!out) return 2;

@@ -45,6 +45,36 @@ def max_pool2d(input, kernel_size, stride=(1, 1), padding=(0, 0), dilation=(1, 1
                                       dilation=dilation, ceil_mode=ceil_mode, return_indices=return_indices)
 
 
+def _conv_desc_of(input, conv):
+    from .. import ops
+    return ops.conv_desc(tuple(input.shape), tuple(conv.weight.shape), tuple(conv.stride), tuple(conv.padding),
+                         tuple(conv.dilation), conv.groups)
+
+
+def conv2d_epilogue_available(input, conv):
+    """the convolution runs on the tensor path, whose epilogue can apply a folded BatchNorm / ReLU"""
+    from .. import ops
+    from ..xparray import cparray
+    if input.data.__class__ is not cparray or conv.weight.data.__class__ is not cparray:
+        return False
+    if conv.groups * conv.weight.shape[1] != input.shape[1]:
+        return False  # (let the plain path raise the reference's error)
+    return ops.conv_fused_info(_conv_desc_of(input, conv))[0]
+
+
+def conv2d_bn_eval(input, conv, bn, relu):
+    """Inference form of Conv2d -> BatchNorm2d(eval) [-> ReLU]: one convolution kernel; the BatchNorm (running statistics,
+    reference grad_nn.py:932-959) is folded to per-channel scale / shift applied, with the ReLU (:58), in its epilogue.
+    Called by nn.Sequential under no_grad; no graph is recorded."""
+    from .. import ops
+    from ..tensor import Tensor
+    d = _conv_desc_of(input, conv)
+    y = ops.conv2d_bn_eval(input.data, conv.weight.data, None if conv.bias is None else conv.bias.data, d,
+                           bn.running_mean.data, bn.running_var.data, bn.eps,
+                           None if bn.weight is None else bn.weight.data, None if bn.bias is None else bn.bias.data, relu)
+    return Tensor(y, copy=False, dtype=y.dtype)
+
+
 def batch_norm(input, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
     return BatchNorm.apply(input, weight, bias, running_mean=running_mean, running_var=running_var,
                            training=training, momentum=momentum, eps=eps)

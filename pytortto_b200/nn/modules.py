@@ -13,7 +13,7 @@ from itertools import repeat
 import numpy as np
 
 from .. import VariableFunctions as V
-from ..autograd.grad_mode import no_grad
+from ..autograd.grad_mode import is_grad_enabled, no_grad
 from ..tensor import Tensor
 from ..xparray import cparray
 from . import functional as F
@@ -308,6 +308,12 @@ class Sequential(Module):
             if i + 1 < n and isinstance(m, _BatchNorm) and type(mods[i + 1]) is ReLU and _FUSE_BN_RELU[0]:
                 x = m(x, fuse_relu=True)
                 i += 2
+            elif i + 1 < n and type(m) is Conv2d and _conv_bn_eval_fusable(m, mods[i + 1], x):
+                # inference peephole: Conv2d -> BatchNorm2d(eval) [-> ReLU] is one convolution whose epilogue applies the
+                # folded per-channel scale / shift and the ReLU (no intermediate tensor)
+                relu = i + 2 < n and type(mods[i + 2]) is ReLU
+                x = F.conv2d_bn_eval(x, m, mods[i + 1], relu)
+                i += 3 if relu else 2
             else:
                 x = m(x)
                 i += 1
@@ -315,6 +321,12 @@ class Sequential(Module):
 
 
 _FUSE_BN_RELU = [True]
+
+
+def _conv_bn_eval_fusable(conv, bn, x):
+    return (_FUSE_BN_RELU[0] and type(bn) is BatchNorm2d and not bn.training and bn.running_mean is not None
+            and bn.running_var is not None and not is_grad_enabled() and conv.padding_mode == 'zeros' and x.ndim == 4
+            and F.conv2d_epilogue_available(x, conv))
 
 
 def set_bn_relu_fusion(flag):

@@ -174,20 +174,78 @@ def conv_desc(x_shape, w_shape, stride, padding, dilation, groups, out_hw=None):
     return d
 
 
-def conv2d_fprop(x, w, bias, d):
+# Fused conv epilogues (tensor path): per-channel scale / bias, a residual add, ReLU, and the per-channel sum / sum of
+# squares of the stored output for the BatchNorm that reads it next (`cparray._bnstats`).  TORTTO_B200_EPILOGUE_STATS=0
+# switches the statistics off (every BatchNorm then runs its own statistics pass).
+_EPILOGUE_STATS = os.environ.get("TORTTO_B200_EPILOGUE_STATS", "1") != "0"
+_fused_info = {}
+
+
+def conv_fused_info(d):
+    """(fused epilogue available, statistics chunks) of fprop of this problem"""
+    ent = _fused_info.get(id(d))
+    if ent is None:
+        lib = _cabi.load()
+        ok = bool(lib.ttb_conv2d_fused_epilogue_supported(ctypes.byref(d)))
+        ent = _fused_info[id(d)] = (d, ok, int(lib.ttb_conv2d_fprop_stats_chunks(ctypes.byref(d))) if ok else 0)  # keeps d alive
+    return ent[1], ent[2]
+
+
+def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=False):
+    """y = conv(x, w) [* scale[k]] [+ bias[k]] [+ residual] [max(., 0)]; `stats`: also emit the BatchNorm statistics
+    partials of y (y._bnstats).  scale / residual / relu / stats need conv_fused_info(d)[0]."""
     y = new_f32((d.n, d.k, d.p, d.q))
     if y.size == 0:
         return y
-    if d.math_mode == _cabi.TTB_MATH_BF16:
-        if conv_bf16_supported(d, 0) and w.ndim == 4:
-            _cabi.call("ttb_conv2d_fprop_bf16", ctypes.byref(d), bf16_of(x).data_ptr(), _weight_bf16(w, False).data_ptr(),
-                       _ptr(bias), _ptr(y), current_stream_ptr())
-            return y
+    bf16_direct = d.math_mode == _cabi.TTB_MATH_BF16 and conv_bf16_supported(d, 0) and w.ndim == 4
+    if d.math_mode == _cabi.TTB_MATH_BF16 and not bf16_direct:
         d = _tf32_twin(d)
+    fused = scale is not None or residual is not None or relu or stats
+    ep = None
+    if fused:
+        ok, chunks = conv_fused_info(d)
+        if not ok:
+            raise RuntimeError("conv2d_fprop: this problem has no fused epilogue (exact fp32 / grouped path)")
+        partials = None
+        if stats and chunks > 0 and _EPILOGUE_STATS:
+            partials = torch.empty((chunks, 2, d.k), dtype=torch.float64, device=y.t.device)
+            y._bnstats = (partials, chunks, y._version[0])
+        ep = _cabi.ConvEpilogue(_ptr(scale), _ptr(bias), _ptr(residual), int(bool(relu)),
+                                None if partials is None else partials.data_ptr())
+    if bf16_direct:
+        if ep is None:
+            ep = _cabi.ConvEpilogue(None, _ptr(bias), None, 0, None)
+        _cabi.call("ttb_conv2d_fprop_bf16", ctypes.byref(d), bf16_of(x).data_ptr(), _weight_bf16(w, False).data_ptr(),
+                   ctypes.byref(ep), _ptr(y), current_stream_ptr())
+        return y
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 0))
-    _cabi.call("ttb_conv2d_fprop", ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y),
-               None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
+    if ep is not None:
+        _cabi.call("ttb_conv2d_fprop_fused", ctypes.byref(d), _ptr(x), _ptr(w), ctypes.byref(ep), _ptr(y),
+                   None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
+    else:
+        _cabi.call("ttb_conv2d_fprop", ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y),
+                   None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
     return y
+
+
+def conv2d_bn_eval(x, w, conv_bias, d, mean, var, eps, gamma, beta, relu):
+    """relu?(batch_norm_eval(conv(x, w) + conv_bias)) as ONE kernel: the BatchNorm is folded to the epilogue's per-channel
+    scale / bias (inference; needs conv_fused_info(d)[0])"""
+    c = d.k
+    sb = new_f32((2, c))
+    base = sb.t.data_ptr()
+    _cabi.call("ttb_bn_fold_eval", _ptr(mean), _ptr(var), c, float(eps), _ptr(gamma), _ptr(beta), _ptr(conv_bias), base,
+               base + 4 * c, current_stream_ptr())
+    scale, bias = cparray(sb.t[0]), cparray(sb.t[1])
+    return conv2d_fprop(x, w, bias, d, scale=scale, relu=relu)
+
+
+def bn_stats_of(x):
+    """(partials tensor, chunks) a producer attached to x, if still valid for its current contents"""
+    bs = x._bnstats
+    if bs is not None and bs[2] == x._version[0]:
+        return bs[0], bs[1]
+    return None
 
 
 # dgrad needs the filters as [C][R][S][K]; the [K][R][S][C] -> [C][R][S][K] re-ordering of ALL conv layers of a step is
@@ -243,26 +301,31 @@ def _flush_dgrad_pack():
     _cabi.call("ttb_conv2d_dgrad_pack_weights", n, descs, src, dst, current_stream_ptr())
 
 
-def conv2d_dgrad(dy, w, d):
+def conv2d_dgrad(dy, w, d, accum=None):
+    """`accum`: a gradient already pending for the same tensor (the engine's `grad += new`): added in the dgrad epilogue
+    where the kernel can (pre-packed TF32 / bf16 tensor path), by a separate add otherwise."""
     dx = new_f32((d.n, d.c, d.h, d.w))
     if dx.size == 0:
-        return dx
+        return dx if accum is None else accum
+    if accum is not None and (accum.shape != dx.shape or accum.t.dtype != torch.float32):
+        return add_arrays(conv2d_dgrad(dy, w, d), accum)
     if d.math_mode == _cabi.TTB_MATH_BF16:
         if conv_bf16_supported(d, 1) and w.ndim == 4:
             _cabi.call("ttb_conv2d_dgrad_bf16", ctypes.byref(d), bf16_of(dy).data_ptr(), _weight_bf16(w, True).data_ptr(),
-                       _ptr(dx), current_stream_ptr())
+                       _ptr(accum), _ptr(dx), current_stream_ptr())
             return dx
         d = _tf32_twin(d)
     if _dgrad_pack["enabled"] and _dgrad_pack["in_sweep"]:  # (a dgrad outside backward = ConvTranspose2d forward)
         _flush_dgrad_pack()
         ent = _dgrad_pack["packed"].get(w.t.data_ptr())
         if ent is not None and ent[1] == _dgrad_pack["sweep"] and _prepack_ok.get(id(d)):
-            _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), _ptr(dy), ent[0].data_ptr(), _ptr(dx), current_stream_ptr())
+            _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), _ptr(dy), ent[0].data_ptr(), _ptr(accum), _ptr(dx),
+                       current_stream_ptr())
             return dx
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 1))
     _cabi.call("ttb_conv2d_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w), _ptr(dx),
                None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
-    return dx
+    return dx if accum is None else add_arrays(dx, accum)
 
 
 # Weight gradients are leaves of the backward pass: nothing downstream of a conv's backward needs dW before the
@@ -498,15 +561,24 @@ def _rows_channels(x):
     raise RuntimeError(f"batch_norm on the B200 path supports (N,C,H,W) and (N,C) inputs, got shape {shp}")
 
 
+def _bn_partials(x, m, c):
+    """statistics partials [chunks][2][C] of x: the producer's (conv epilogue / fused add) when still valid, else a
+    statistics pass over x"""
+    got = bn_stats_of(x)
+    if got is not None:
+        return got
+    chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+    partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
+    _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, current_stream_ptr())
+    return partials, chunks
+
+
 def bn_sums(x, reduce_hook=None):
     """per-channel sum(x), sum(x^2) as double partials [chunks][2][C] -> (buffer, chunks, count).  Without a hook
     the per-chunk partials go straight to the finalize kernel (which sums them in fixed order); with a hook
     (SyncBN) `reduce_hook(partials, chunks, 2C, count)` returns the cross-rank [2][C] sums and the global count."""
     m, c = _rows_channels(x)
-    chunks = _cabi.load().ttb_bn_num_chunks(m, c)
-    partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
-    st = current_stream_ptr()
-    _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
+    partials, chunks = _bn_partials(x, m, c)
     if reduce_hook is None:
         return partials, chunks, m
     sums, m = reduce_hook(partials, chunks, 2 * c, m)
@@ -521,9 +593,7 @@ def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, r
     st = current_stream_ptr()
     fused = getattr(reduce_hook, "fused", None)  # SyncBN over NVLink peer memory: exchange + finalize are one kernel
     if fused is not None and x.t.is_cuda and fused.fits(2 * c, reduce_hook.key):
-        chunks = _cabi.load().ttb_bn_num_chunks(m, c)
-        partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
-        _cabi.call("ttb_bn_stats", _ptr(x), m, c, partials.data_ptr(), chunks, st)
+        partials, chunks = _bn_partials(x, m, c)
         count = m * fused.world  # equal shards by construction (distributed.shard_batch)
         fused.call("ttb_comm_bn_finalize", reduce_hook.key, partials, chunks, count, c, eps,
                    0.0 if momentum is None else momentum, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
@@ -612,11 +682,20 @@ def relu_bwd(dy, y):
     return dx
 
 
-def add_arrays(a, b):
-    """a + b into a fresh array (same shape, float32, same canonical layout)."""
+def add_arrays(a, b, stats=False):
+    """a + b into a fresh array (same shape, float32, same canonical layout).  `stats`: for 4-D operands the same pass also
+    emits the BatchNorm statistics partials of the sum (out._bnstats) - the residual add of a pre-activation block feeds
+    the next block's BatchNorm."""
     if a.shape != b.shape or a.t.dtype != torch.float32 or b.t.dtype != torch.float32:
         return cparray(a.t + b.t)
     out = cparray(empty_device(a.shape))
+    if stats and _EPILOGUE_STATS and a.ndim == 4 and a.size > 0:
+        m, c = _rows_channels(a)
+        chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+        partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=a.t.device)
+        _cabi.call("ttb_add_bn_stats", _ptr(a), _ptr(b), _ptr(out), m, c, partials.data_ptr(), chunks, current_stream_ptr())
+        out._bnstats = (partials, chunks, out._version[0])
+        return out
     _cabi.call("ttb_add", _ptr(a), _ptr(b), _ptr(out), a.size, current_stream_ptr())
     return out
 

@@ -57,7 +57,7 @@ class cparray:
     """Device array.  `t` is the owning torch tensor (logical shape, canonical physical layout).
     `_h` / `_hver`: optional bf16 shadow of the same values (same physical layout) and the `_version` it was written
     at - co-written by the producing kernel in bf16 math mode so the next convolution reads 2-byte operands."""
-    __slots__ = ("t", "_version", "base", "_h", "_hver", "__weakref__")
+    __slots__ = ("t", "_version", "base", "_h", "_hver", "_bnstats", "__weakref__")
 
     def __init__(self, t, version=None, base=None):
         if t.__class__ is not torch.Tensor:
@@ -71,10 +71,14 @@ class cparray:
         self.base = base
         self._h = None
         self._hver = 0
+        # (partials, chunks, version): per-channel sum / sum-of-squares partials of this array, emitted by the kernel that
+        # produced it (a conv epilogue, the fused add) for the BatchNorm that reads it next; valid while _version matches
+        self._bnstats = None
 
     def _touched(self):
         """an in-place write happened outside the shadow-maintaining kernels"""
         self._h = None
+        self._bnstats = None
         if self.t.dim() == 4:
             mutation_epoch[0] += 1
 

@@ -1,7 +1,7 @@
 """Parity + timing of the flat-shift halo-tile kernels (csrc/conv_flat.cu) on a B200:
 
-    python scripts/flat_check.py                                        # release library: resident variant where it applies
-    TORTTO_B200_LIB=tuning TTB_FLAT=0 python scripts/flat_check.py      # im2col kernel everywhere (the A/B baseline)
+    python scripts/flat_check.py                                        # release library: im2col kernels (the A/B baseline)
+    TORTTO_B200_LIB=tuning TTB_FLAT=-1 python scripts/flat_check.py     # resident-weight flat-shift variant where it applies
     TORTTO_B200_LIB=tuning TTB_FLAT=1 python scripts/flat_check.py      # flat-shift everywhere eligible (streamed variant too)
 
 Every case is compared with the exact fp32 direct kernels on the same inputs (tolerance 2e-3 of the tensor max) and
@@ -63,7 +63,7 @@ def main():
             dx = cparray(torch.empty_like(x.t))
 
             def run_dgrad():
-                _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), packed.data_ptr(), dx.t.data_ptr(),
+                _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), packed.data_ptr(), None, dx.t.data_ptr(),
                            current_stream_ptr())
             run_dgrad()
             derr = float(np.abs(dx.get() - dref).max() / np.abs(dref).max())

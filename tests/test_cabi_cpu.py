@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     from pytortto_b200 import _cabi
     assert sorted(_cabi.EXPORTED_SYMBOLS) == declared  # the ctypes layer binds exactly the header's surface
-    assert _cabi.load().ttb_version() == 3
+    assert _cabi.load().ttb_version() == 4
     assert ctypes.sizeof(_cabi.ConvDesc) == 17 * 4 and ctypes.sizeof(_cabi.PoolDesc) == 14 * 4
 
 

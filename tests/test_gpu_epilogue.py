@@ -1,0 +1,239 @@
+"""GPU parity of the fused convolution epilogues (per-channel scale / bias, residual add, ReLU, BatchNorm statistics),
+the dgrad accumulate-into epilogue, the fused add + statistics pass and the inference peephole
+Sequential(Conv2d, BatchNorm2d(eval)[, ReLU]) against the numpy oracle.
+
+What each replaces in the reference (/root/reference/src/tortto/): the bias add autograd/grad_nn.py:714-715, eval-mode
+BatchNorm :932-959, `Add` tensor.py:597-599, `Relu` :58, and BatchNorm.forward's xp.mean / xp.var passes :923-924.
+Tolerances: TF32 2e-3, bf16 1e-2 of the tensor max for conv outputs (north star); statistics are held to 1e-6 of the
+double sums of the SAME stored tensor (they are sums of stored values, not a second contraction)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from gpu_util import assert_close, require_gpu
+from oracle import tortto_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"tf32": 2e-3, "bf16": 1e-2}
+
+# (N, Cin, H, W, Cout, k, stride, pad): the stem (padded channels), flat-shift kernel (64 -> 64, >= 4 tiles per SM), the
+# 64 / 128 / 256-wide im2col tiles with one and several N tiles per CTA row, ragged M
+CASES = [
+    (8, 3, 32, 32, 64, 3, 1, 1),
+    (96, 64, 32, 32, 64, 3, 1, 1),
+    (4, 64, 16, 16, 64, 3, 1, 1),
+    (16, 64, 16, 16, 128, 3, 2, 1),
+    (3, 64, 15, 17, 96, 3, 1, 1),
+    (32, 128, 16, 16, 128, 3, 1, 1),
+    (64, 256, 8, 8, 512, 1, 1, 0),
+    (64, 128, 8, 8, 384, 3, 1, 1),
+    (2, 64, 7, 7, 40, 1, 1, 0),
+]
+IDS = [f"n{c[0]}_c{c[1]}_{c[2]}x{c[3]}_k{c[4]}_f{c[5]}s{c[6]}" for c in CASES]
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    require_gpu()
+
+
+def _tt(mode):
+    import pytortto_b200 as tt
+    tt.set_math_mode(mode)
+    return tt
+
+
+def _dev(a):
+    from pytortto_b200.xparray import cparray
+    return cparray.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+
+
+def _problem(case, seed=0):
+    n, ci, h, w, co, k, s, p = case
+    rng = np.random.default_rng(seed + n * 131 + ci)
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32)
+    return rng, x, wt
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_fused_epilogue_and_statistics(case, mode):
+    _tt(mode)
+    from pytortto_b200 import ops
+    n, ci, h, w, co, k, s, p = case
+    rng, x, wt = _problem(case)
+    yo = O.conv2d_forward(x, wt, None, s, p, 1)
+    scale = rng.uniform(0.5, 1.5, co).astype(np.float32)
+    bias = rng.standard_normal(co).astype(np.float32)
+    res = rng.standard_normal(yo.shape).astype(np.float32)
+    ref = np.maximum(yo * scale[None, :, None, None] + bias[None, :, None, None] + res, 0)
+    d = ops.conv_desc(x.shape, wt.shape, (s, s), (p, p), (1, 1), 1)
+    ok, chunks = ops.conv_fused_info(d)
+    assert ok and chunks > 0
+    xd, wd = _dev(x), _dev(wt)
+    y = ops.conv2d_fprop(xd, wd, _dev(bias), d, scale=_dev(scale), residual=_dev(res), relu=True, stats=True)
+    got = y.get()
+    assert_close(f"{mode} relu(conv*scale+bias+res)", got, ref, TOL[mode])
+    # the statistics describe exactly what was stored
+    part, nch = ops.bn_stats_of(y)
+    assert nch == chunks and tuple(part.shape) == (chunks, 2, co)
+    sums = part.sum(dim=0).cpu().numpy()
+    g64 = got.astype(np.float64)
+    s0, s1 = g64.sum(axis=(0, 2, 3)), (g64 * g64).sum(axis=(0, 2, 3))
+    assert_close("sum(y)", sums[0], s0, 1e-6)
+    assert_close("sum(y^2)", sums[1], s1, 1e-6)
+    # plain call (bias only) and statistics without any other epilogue stage
+    y2 = ops.conv2d_fprop(xd, wd, None, d, stats=True)
+    assert_close(f"{mode} conv", y2.get(), yo, TOL[mode])
+    sums2 = ops.bn_stats_of(y2)[0].sum(dim=0).cpu().numpy()
+    g2 = y2.get().astype(np.float64)
+    assert_close("sum(y) plain", sums2[0], g2.sum(axis=(0, 2, 3)), 1e-6)
+    assert_close("sum(y^2) plain", sums2[1], (g2 * g2).sum(axis=(0, 2, 3)), 1e-6)
+
+
+def test_epilogue_statistics_large_mean():
+    """|mean| / sd ~ 1e3 per channel (a big conv bias): the shifted sums must keep the variance (reference: two-pass
+    xp.var, grad_nn.py:923-924); checked through the BatchNorm that consumes them."""
+    _tt("tf32")
+    from pytortto_b200 import ops
+    case = (96, 64, 32, 32, 64, 3, 1, 1)
+    n, ci, h, w, co, k, s, p = case
+    rng, x, wt = _problem(case, 7)
+    bias = (1000.0 * rng.choice([-1.0, 1.0], co)).astype(np.float32)
+    d = ops.conv_desc(x.shape, wt.shape, (s, s), (p, p), (1, 1), 1)
+    y = ops.conv2d_fprop(_dev(x), _dev(wt), _dev(bias), d, stats=True)
+    assert ops.bn_stats_of(y) is not None
+    g = y.get().astype(np.float64)
+    out, stats, _ = ops.bn_forward_train(y, None, None, None, None, 0.1, 1e-5)
+    st = stats.get()
+    assert_close("mean", st[0], g.mean(axis=(0, 2, 3)), 1e-6)
+    assert_close("var+eps", st[1], g.var(axis=(0, 2, 3)) + 1e-5, 2e-5)
+    y._bnstats = None  # the BatchNorm's own statistics pass on the same tensor
+    out2, stats2, _ = ops.bn_forward_train(y, None, None, None, None, 0.1, 1e-5)
+    assert_close("var: epilogue vs statistics pass", st[1], stats2.get()[1], 2e-5)
+    assert_close("y: epilogue vs statistics pass", out.get(), out2.get(), 2e-5)
+
+
+def test_statistics_dropped_after_inplace_write():
+    tt = _tt("tf32")
+    from pytortto_b200 import ops
+    case = (4, 64, 16, 16, 64, 3, 1, 1)
+    rng, x, wt = _problem(case)
+    d = ops.conv_desc(x.shape, wt.shape, (1, 1), (1, 1), (1, 1), 1)
+    y = ops.conv2d_fprop(_dev(x), _dev(wt), None, d, stats=True)
+    assert ops.bn_stats_of(y) is not None
+    t = tt.Tensor(y, copy=False, dtype=y.dtype)
+    tt.nn.functional.relu(t, inplace=True)  # bumps the version: the statistics no longer describe the contents
+    assert ops.bn_stats_of(y) is None
+    out, stats, _ = ops.bn_forward_train(y, None, None, None, None, 0.1, 1e-5)
+    g = y.get().astype(np.float64)
+    assert_close("mean after in-place relu", stats.get()[0], g.mean(axis=(0, 2, 3)), 1e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", [(96, 64, 32, 32, 64, 3, 1, 1), (16, 64, 16, 16, 128, 3, 2, 1), (32, 128, 16, 16, 128, 3, 1, 1),
+                                  (8, 256, 8, 8, 64, 1, 1, 0)],
+                         ids=["flat64", "s2_64_128", "c128", "1x1_256_64"])
+def test_dgrad_accumulates_pending_gradient(case, mode):
+    """the engine's `grad += new` (tensor.py:597-599) folded into the dgrad epilogue: x feeds two convolutions"""
+    tt = _tt(mode)
+    n, ci, h, w, co, k, s, p = case
+    rng, x, wt = _problem(case, 3)
+    wt2 = (rng.standard_normal((co, ci, k, k)) / np.sqrt(ci * k * k)).astype(np.float32)
+    yo = O.conv2d_forward(x, wt, None, s, p, 1)
+    dy = rng.standard_normal(yo.shape).astype(np.float32)
+    dx1, _, _ = O.conv2d_backward(x, wt, dy, s, p, 1)
+    dx2, _, _ = O.conv2d_backward(x, wt2, 2 * dy, s, p, 1)
+    xin = tt.nn.Parameter(tt.tensor(x).cuda())
+    w1 = tt.nn.Parameter(tt.tensor(wt).cuda())
+    w2 = tt.nn.Parameter(tt.tensor(wt2).cuda())
+    F = tt.nn.functional
+    out = F.conv2d(xin, w1, None, (s, s), (p, p)) + F.conv2d(xin, w2, None, (s, s), (p, p)) * 2.0
+    out.backward(tt.tensor(dy).cuda())
+    assert_close(f"{mode} dx (two branches)", xin.grad.get(), dx1 + dx2, TOL[mode])
+
+
+def test_add_with_statistics():
+    _tt("tf32")
+    from pytortto_b200 import ops
+    rng = np.random.default_rng(5)
+    for shape in [(8, 64, 32, 32), (3, 40, 7, 9), (2, 6, 5, 5)]:
+        a = (rng.standard_normal(shape) + 50.0).astype(np.float32)
+        b = rng.standard_normal(shape).astype(np.float32)
+        out = ops.add_arrays(_dev(a), _dev(b), stats=True)
+        got = out.get()
+        np.testing.assert_array_equal(got, a + b)
+        part, chunks = ops.bn_stats_of(out)
+        sums = part.sum(dim=0).cpu().numpy()
+        g = got.astype(np.float64)
+        assert_close("sum(a+b)", sums[0], g.sum(axis=(0, 2, 3)), 1e-6)
+        assert_close("sum((a+b)^2)", sums[1], (g * g).sum(axis=(0, 2, 3)), 1e-6)
+        _, stats, _ = ops.bn_forward_train(out, None, None, None, None, 0.1, 1e-5)
+        assert_close("var+eps", stats.get()[1], g.var(axis=(0, 2, 3)) + 1e-5, 2e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("relu", [False, True])
+def test_inference_conv_bn_relu_is_one_kernel(mode, relu):
+    """Sequential(Conv2d, BatchNorm2d.eval()[, ReLU]) under no_grad = one convolution with the BatchNorm folded into its
+    epilogue; compared with the oracle's conv -> eval batch norm -> relu"""
+    tt = _tt(mode)
+    from pytortto_b200 import _cabi
+    rng = np.random.default_rng(11)
+    n, ci, h, w, co = 8, 64, 16, 16, 128
+    conv = tt.nn.Conv2d(ci, co, 3, 1, 1, bias=True)
+    bn = tt.nn.BatchNorm2d(co)
+    mods = [conv, bn] + ([tt.nn.ReLU()] if relu else [])
+    net = tt.nn.Sequential(*mods).cuda()
+    rm, rv = rng.standard_normal(co).astype(np.float32), rng.uniform(0.5, 2.0, co).astype(np.float32)
+    gam, bet = rng.uniform(0.5, 1.5, co).astype(np.float32), rng.standard_normal(co).astype(np.float32)
+    bn.running_mean.data = _dev(rm)
+    bn.running_var.data = _dev(rv)
+    bn.weight.data = _dev(gam)
+    bn.bias.data = _dev(bet)
+    net.eval()
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt, cb = conv.weight.data.get(), conv.bias.data.get()
+    yo = O.conv2d_forward(x, wt, cb, 1, 1, 1)
+    ref = (yo - rm[None, :, None, None]) / np.sqrt(rv + bn.eps)[None, :, None, None] * gam[None, :, None, None] \
+        + bet[None, :, None, None]
+    if relu:
+        ref = np.maximum(ref, 0)
+    xt = tt.tensor(x).cuda()
+    with tt.no_grad():
+        before = _cabi.launch_count
+        y = net(xt)
+        calls = _cabi.launch_count - before
+    assert_close(f"{mode} fused inference", y.data.get(), ref, TOL[mode])
+    assert calls <= (4 if mode == "bf16" else 2), f"{calls} C-ABI calls: the BatchNorm / ReLU were not folded"
+    # with a graph being recorded the modules run unfused and must agree
+    y2 = net(xt)
+    assert_close(f"{mode} unfused", y2.data.get(), ref, TOL[mode])
+
+
+def test_training_step_uses_epilogue_statistics():
+    """conv -> BatchNorm(train) consumes the epilogue statistics: no ttb_bn_stats call, same result as with them off"""
+    tt = _tt("tf32")
+    from pytortto_b200 import ops
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((32, 64, 16, 16)).astype(np.float32)
+
+    def run(flag):
+        ops._EPILOGUE_STATS = flag
+        try:
+            np.random.seed(0)
+            net = tt.nn.Sequential(tt.nn.Conv2d(64, 128, 3, 1, 1, bias=False), tt.nn.BatchNorm2d(128), tt.nn.ReLU()).cuda()
+            xin = tt.nn.Parameter(tt.tensor(x).cuda())
+            y = net(xin)
+            y.sum().backward()
+            return y.data.get(), xin.grad.get(), net[1].running_var.data.get()
+        finally:
+            ops._EPILOGUE_STATS = True
+
+    a, b = run(True), run(False)
+    assert_close("y", a[0], b[0], 2e-5)
+    assert_close("dx", a[1], b[1], 1e-4)
+    assert_close("running_var", a[2], b[2], 2e-5)

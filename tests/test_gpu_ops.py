@@ -342,7 +342,7 @@ def test_multi_tensor_backward_helpers_match_per_layer_calls():
     for (x, w, d, dy), pk in zip(layers, packed):
         dx_ref = ops.conv2d_dgrad(dy, w, d).get()
         dx = cparray(torch.empty_like(x.t))
-        _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), pk.data_ptr(), dx.t.data_ptr(), st)
+        _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), dy.t.data_ptr(), pk.data_ptr(), None, dx.t.data_ptr(), st)
         np.testing.assert_array_equal(dx.get(), dx_ref)
         dw_ref = ops.conv2d_wgrad(x, dy, d).get()
         dw = cparray(torch.zeros_like(w.t))
