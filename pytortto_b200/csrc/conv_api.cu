@@ -3,6 +3,10 @@
 //
 // The ABI always takes fp32 NHWC activations and fp32 [K][R][S][C] weights.  Operand staging for the tensor path:
 //   TF32, channels % 32 == 0 : none - TMA reads the caller's buffers directly.
+//   <= 4 input channels       : TAP-PACKED (fprop / wgrad): the network stems (3 x 3 x 3, 7 x 7 x 3) would spend 9 / 49 K-blocks
+//                               of zero-padded channels per tile; instead the R*S*C taps of a pixel are packed into one row
+//                               of round_up(R*S*C, 32) columns (27 -> 32: ONE K-block) and the layer runs as a 1 x 1
+//                               convolution over that staged tensor - the same bytes as the channel-padded copy.
 //   TF32, other channel count : fprop / wgrad run over a zero-padded fp32 copy (C -> round_up(C, 32)); this is how
 //                               the 3-channel network stems reach the tensor cores.
 //   BF16                      : operands are converted (and padded to a multiple of 64 channels) to bf16 copies in
@@ -26,10 +30,13 @@ size_t igemm_workspace_size(const ttb_conv_desc* d, int pass);
 int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, void* ws,
                 size_t ws_bytes, cudaStream_t st);
 int igemm_fprop_stats_chunks(const ttb_conv_desc* d);
+int igemm_fprop_grouped(const ttb_conv_desc* dg, int groups, const void* x, size_t x_goff_bytes, int x_ctot, const void* w,
+                        size_t w_goff_bytes, const Epilogue& ep, float* y, int y_ctot, cudaStream_t st);
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st, const void* prepacked = nullptr, const float* accum = nullptr);
+                cudaStream_t st, const void* prepacked = nullptr, const float* accum = nullptr, int dy_ctot = 0, int dx_ctot = 0,
+                bool zero_done = false);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-                cudaStream_t st, int* splits_out = nullptr);
+                cudaStream_t st, int* splits_out = nullptr, int x_ctot = 0, int dy_ctot = 0);
 // conv_flat.cu: "flat-shift halo tile" fprop / dgrad with shared-memory-resident weights (the 64-channel 3x3 layers)
 bool flat_fprop_supported(const ttb_conv_desc* d);
 bool flat_dgrad_supported(const ttb_conv_desc* d);
@@ -90,6 +97,69 @@ unpad_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, in
   }
 }
 
+// x [N][H][W][C] -> xcol [groups][N*P*Q][kp]: xcol[g][m][(r*S + s)*Cg + c] = x zero-padded at (p*sh + r*dh - ph,
+// q*sw + s*dw - pw) of channel g*Cg + c (Cg = C / groups), columns R*S*Cg .. kp-1 zero.  One thread = 4 consecutive columns
+// of one output pixel, so a warp writes whole 128-byte lines; the (row, column, channel) offsets of the kp columns are
+// decoded once per block into shared memory (the gathers hit L1 / L2: the input is tiny).
+constexpr int kPackMaxCols = 1024;
+template <class OutT>
+__global__ void __launch_bounds__(256)
+pack_taps_kernel(const float* __restrict__ x, OutT* __restrict__ xcol, ttb_conv_desc d, int kp) {
+  pdl_entry();
+  __shared__ int tab_dh[kPackMaxCols], tab_dw[kPackMaxCols], tab_off[kPackMaxCols];  // dh < 0 marks a zero column
+  const int cg = d.c / d.groups;
+  const int rsc = d.r * d.s * cg;
+  for (int j = threadIdx.x; j < kp; j += blockDim.x) {
+    if (j < rsc) {
+      const int tap = j / cg, c = j - tap * cg;
+      const int r = tap / d.s, s = tap - r * d.s;
+      tab_dh[j] = r * d.dil_h;
+      tab_dw[j] = s * d.dil_w;
+      tab_off[j] = (r * d.dil_h * d.w + s * d.dil_w) * d.c + c;
+    } else {
+      tab_dh[j] = -1;
+      tab_dw[j] = 0;
+      tab_off[j] = 0;
+    }
+  }
+  __syncthreads();
+  const int q4 = kp / 4;
+  const int64_t per_group = (int64_t)d.n * d.p * d.q * q4;
+  const int64_t total = per_group * d.groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int g = (int)(t / per_group);
+    int64_t m = t - g * per_group;
+    const int j0 = (int)(m % q4) * 4;
+    m /= q4;
+    const int qq = (int)(m % d.q);
+    m /= d.q;
+    const int pp = (int)(m % d.p);
+    const int n = (int)(m / d.p);
+    const int h0 = pp * d.stride_h - d.pad_h, w0 = qq * d.stride_w - d.pad_w;
+    const float* base = x + (((int64_t)n * d.h + h0) * d.w + w0) * d.c + g * cg;  // (may point before the tensor: only offset)
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int dh = tab_dh[j0 + u], dw = tab_dw[j0 + u];
+      const int h = h0 + dh, w = w0 + dw;
+      v[u] = (dh >= 0 && h >= 0 && h < d.h && w >= 0 && w < d.w) ? __ldg(base + tab_off[j0 + u]) : 0.f;
+    }
+    const float4 f = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (sizeof(OutT) == 4) st_f4(reinterpret_cast<float*>(xcol) + t * 4, f);
+    else st_bf16x4(reinterpret_cast<__nv_bfloat16*>(xcol) + t * 4, f);
+  }
+}
+
+static int pack_taps(const ttb_conv_desc* d, const float* x, void* xcol, int kp, bool bf16, cudaStream_t st) {
+  const int64_t work = (int64_t)d->n * d->p * d->q * (kp / 4) * d->groups;
+  if (work <= 0) return 0;
+  const int grid = elementwise_grid(work, 256);
+  if (bf16) launch_k(pack_taps_kernel<__nv_bfloat16>, grid, 256, 0, st, x, reinterpret_cast<__nv_bfloat16*>(xcol), *d, kp);
+  else launch_k(pack_taps_kernel<float>, grid, 256, 0, st, x, reinterpret_cast<float*>(xcol), *d, kp);
+  return check_launch("pack_taps");
+}
+
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static int stage(const float* src, void* dst, int64_t rows, int c, int cp, bool bf16, cudaStream_t st) {
@@ -105,17 +175,76 @@ struct TensorPlan {
   ttb_conv_desc p;
   bool bf16;        // operands are staged as bf16
   bool stage_ops;   // operands need a staged copy (conversion and / or channel padding)
+  bool packed;      // tap-packed staging: `p` is the 1 x 1 convolution over [N][P][Q][round_up(R*S*C)] (fprop / wgrad)
+  int groups;       // > 1: `p` is ONE GROUP (c = C/groups, k = K/groups) of a grouped convolution; the groups run either in
+                    // place on channel slices of the caller's tensors (aligned channel counts) or tap-packed (<= 4 channels
+                    // per group)
   size_t a_bytes;   // staged activation-like operand #1 (x for fprop/wgrad, dy for dgrad)
   size_t b_bytes;   // staged operand #2 (w for fprop/dgrad, dy for wgrad in bf16 mode)
   size_t c_bytes;   // wgrad only: padded fp32 dw when the channel count was padded
   size_t inner;     // workspace of the igemm pass itself
 };
 
+// Grouped convolution on the tensor path (TF32; the reference vectorises its einsum over groups, grad_nn.py:628-642, and its
+// only known-answer test is a groups = 2 layer, examples/conv2d_result_speed_comparison.ipynb:21-24).
+static bool plan_grouped(const ttb_conv_desc* d, int pass, TensorPlan* t) {
+  if (d->math_mode != TTB_MATH_TF32) return false;
+  const int G = d->groups, cg = d->c / G, kg = d->k / G;
+  ttb_conv_desc q = *d;
+  q.groups = 1; q.c = cg; q.k = kg;
+  t->bf16 = false; t->groups = G; t->packed = false; t->stage_ops = false;
+  t->a_bytes = t->b_bytes = t->c_bytes = 0;
+  const size_t yrows = (size_t)d->n * d->p * d->q;
+  if (pass != 1 && cg <= 4 && kg % 8 == 0 && d->r * d->s * cg <= kPackMaxCols - 64 && tuning_knob("TTB_TAP_PACK", 1)) {
+    const int kp = (d->r * d->s * cg + 31) / 32 * 32;
+    q.c = kp; q.h = d->p; q.w = d->q; q.r = q.s = 1;
+    q.stride_h = q.stride_w = q.dil_h = q.dil_w = 1;
+    q.pad_h = q.pad_w = 0;
+    if (!igemm_supported(&q, pass)) return false;
+    t->p = q;
+    t->packed = t->stage_ops = true;
+    t->a_bytes = align256((size_t)G * yrows * kp * 4);
+    t->b_bytes = pass == 0 ? align256((size_t)d->k * kp * 4) : 0;
+    t->c_bytes = pass == 2 ? align256((size_t)d->k * kp * 4) : 0;
+    t->inner = align256(igemm_workspace_size(&q, pass));
+    return true;
+  }
+  // aligned channel counts: the TMA maps read / the epilogue writes each group's channel slice of the caller's tensors
+  if (!igemm_supported(&q, pass)) return false;
+  if (pass == 1 && kg % 32 != 0) return false;
+  t->p = q;
+  t->inner = align256(igemm_workspace_size(&q, pass)) * (pass == 1 ? (size_t)G : 1);
+  return true;
+}
+
 static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
-  if (d->math_mode == TTB_MATH_FP32 || d->groups != 1) return false;
+  if (d->math_mode == TTB_MATH_FP32) return false;
+  if (d->groups != 1) return plan_grouped(d, pass, t);
   t->p = *d;
+  t->groups = 1;
   t->bf16 = d->math_mode == TTB_MATH_BF16;
+  t->packed = false;
   const int blk = igemm_channel_block(d);
+  if (pass != 1 && d->c <= 4 && d->r * d->s > 1 && d->r * d->s * d->c <= kPackMaxCols - 64 && tuning_knob("TTB_TAP_PACK", 1)) {
+    // tap-packed: the layer as a 1 x 1 convolution over the staged [N][P][Q][kp] tensor
+    const int kp = (d->r * d->s * d->c + blk - 1) / blk * blk;
+    ttb_conv_desc q = *d;
+    q.c = kp; q.h = d->p; q.w = d->q; q.r = q.s = 1;
+    q.stride_h = q.stride_w = q.dil_h = q.dil_w = 1;
+    q.pad_h = q.pad_w = 0;
+    if (igemm_supported(&q, pass)) {
+      t->p = q;
+      t->packed = true;
+      t->stage_ops = true;
+      const size_t es = t->bf16 ? 2 : 4;
+      const size_t yrows = (size_t)d->n * d->p * d->q;
+      t->a_bytes = align256(yrows * kp * es);
+      t->b_bytes = pass == 0 ? align256((size_t)d->k * kp * es) : (t->bf16 ? align256(yrows * d->k * es) : 0);
+      t->c_bytes = pass == 2 ? align256((size_t)d->k * kp * sizeof(float)) : 0;
+      t->inner = align256(igemm_workspace_size(&t->p, pass));
+      return true;
+    }
+  }
   if (pass != 1) {
     t->p.c = (d->c + blk - 1) / blk * blk;
   } else {
@@ -201,8 +330,22 @@ static int fprop_tensor(const ttb_conv_desc* d, const TensorPlan& t, const float
               "conv2d_fprop: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
   char* ws = reinterpret_cast<char*>(workspace);
   const void *xa = x, *wa = w;
+  if (t.groups > 1) {
+    TTB_REQUIRE(ep.stats == nullptr, "conv2d_fprop: epilogue statistics are not available for grouped convolutions");
+    const size_t wg = (size_t)t.p.k * d->r * d->s * (d->c / d->groups) * 4;  // one group's filters
+    if (!t.packed) return igemm_fprop_grouped(&t.p, t.groups, x, (size_t)t.p.c * 4, d->c, w, wg, ep, y, d->k, st);
+    if (pack_taps(d, x, ws, t.p.c, false, st)) return 1;
+    if (stage(w, ws + t.a_bytes, d->k, d->r * d->s * (d->c / d->groups), t.p.c, false, st)) return 1;
+    return igemm_fprop_grouped(&t.p, t.groups, ws, (size_t)d->n * d->p * d->q * t.p.c * 4, 0, ws + t.a_bytes,
+                               (size_t)t.p.k * t.p.c * 4, ep, y, d->k, st);
+  }
   if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, ep, y, st);
-  if (t.stage_ops) {
+  if (t.packed) {  // w [K][R*S*C] -> [K][kp] (zero tail), x -> xcol
+    if (pack_taps(d, x, ws, t.p.c, t.bf16, st)) return 1;
+    if (stage(w, ws + t.a_bytes, d->k, d->r * d->s * d->c, t.p.c, t.bf16, st)) return 1;
+    xa = ws;
+    wa = ws + t.a_bytes;
+  } else if (t.stage_ops) {
     if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
     if (stage(w, ws + t.a_bytes, (int64_t)d->k * d->r * d->s, d->c, t.p.c, t.bf16, st)) return 1;
     xa = ws;
@@ -232,6 +375,7 @@ int ttb_conv2d_fprop_stats_chunks(const ttb_conv_desc* d) {
   if (!d) return 0;
   TensorPlan t;
   if (!plan_tensor(d, 0, &t)) return 0;
+  if (t.groups > 1) return 0;  // (grouped: the BatchNorm runs its own statistics pass)
   if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop_stats_chunks(&t.p);
   return igemm_fprop_stats_chunks(&t.p);
 }
@@ -256,6 +400,19 @@ int ttb_conv2d_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, fl
   char* ws = reinterpret_cast<char*>(workspace);
   const void *dya = dy, *wa = w;
   float* dxa = dx;
+  if (t.groups > 1) {  // aligned groups, in place on the channel slices; every stride-parity class without a tap stays zero
+    const bool strided = d->stride_h * d->stride_w > 1;
+    if (strided && cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->c * sizeof(float), st) != cudaSuccess) {
+      set_error("conv2d_dgrad: memset failed");
+      return 1;
+    }
+    const size_t wg = (size_t)t.p.k * d->r * d->s * t.p.c, per = t.inner / t.groups;
+    for (int g = 0; g < t.groups; ++g)
+      if (int rc = igemm_dgrad(&t.p, dy + (size_t)g * t.p.k, w + g * wg, dx + (size_t)g * t.p.c, ws + g * per, per, st, nullptr,
+                               nullptr, d->k, d->c, strided))
+        return rc;
+    return 0;
+  }
   if (t.stage_ops) {  // bf16 conversion and / or channel padding (K to whole K-blocks, C to a multiple of 8)
     if (stage(dy, ws, (int64_t)d->n * d->p * d->q, d->k, t.p.k, t.bf16, st)) return 1;
     const int64_t wrows = (int64_t)d->k * d->r * d->s;
@@ -293,8 +450,29 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
   char* ws = reinterpret_cast<char*>(workspace);
   const void *xa = x, *dya = dy;
   float* dwa = dw;
+  if (t.groups > 1) {
+    const int cg = d->c / d->groups, rsc = d->r * d->s * cg;
+    char* inner = ws ? ws + t.a_bytes + t.b_bytes + t.c_bytes : nullptr;
+    if (!t.packed) {
+      for (int g = 0; g < t.groups; ++g)
+        if (int rc = igemm_wgrad(&t.p, x + (size_t)g * cg, dy + (size_t)g * t.p.k, dw + (size_t)g * t.p.k * rsc, inner, t.inner,
+                                 st, nullptr, d->c, d->k))
+          return rc;
+      return 0;
+    }
+    if (pack_taps(d, x, ws, t.p.c, false, st)) return 1;
+    float* dwp = reinterpret_cast<float*>(ws + t.a_bytes + t.b_bytes);  // [K][kp]
+    const size_t xg = (size_t)d->n * d->p * d->q * t.p.c;
+    for (int g = 0; g < t.groups; ++g)
+      if (int rc = igemm_wgrad(&t.p, reinterpret_cast<float*>(ws) + g * xg, dy + (size_t)g * t.p.k,
+                               dwp + (size_t)g * t.p.k * t.p.c, inner, t.inner, st, nullptr, 0, d->k))
+        return rc;
+    launch_k(unpad_channels_kernel, elementwise_grid((int64_t)d->k * rsc, 256), 256, 0, st, dwp, dw, (int64_t)d->k, rsc, t.p.c);
+    return check_launch("unpad_channels");
+  }
   if (t.stage_ops) {
-    if (stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st)) return 1;
+    if (t.packed ? pack_taps(d, x, ws, t.p.c, t.bf16, st) : stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st))
+      return 1;
     xa = ws;
     if (t.bf16) {
       if (stage(dy, ws + t.a_bytes, (int64_t)d->n * d->p * d->q, d->k, d->k, true, st)) return 1;
@@ -303,9 +481,10 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
     if (t.c_bytes) dwa = reinterpret_cast<float*>(ws + t.a_bytes + t.b_bytes);
   }
   if (int rc = igemm_wgrad(&t.p, xa, dya, dwa, ws ? ws + t.a_bytes + t.b_bytes + t.c_bytes : nullptr, t.inner, st)) return rc;
-  if (t.c_bytes) {
-    const int64_t wrows = (int64_t)d->k * d->r * d->s;
-    launch_k(unpad_channels_kernel, elementwise_grid(wrows * d->c, 256), 256, 0, st, dwa, dw, wrows, d->c, t.p.c);
+  if (t.c_bytes) {  // crop the padded reduction columns: [K][kp] -> [K][R*S*C] (tap-packed) / [K*R*S][cp] -> [K*R*S][C]
+    const int64_t wrows = t.packed ? d->k : (int64_t)d->k * d->r * d->s;
+    const int wc = t.packed ? d->r * d->s * d->c : d->c;
+    launch_k(unpad_channels_kernel, elementwise_grid(wrows * wc, 256), 256, 0, st, dwa, dw, wrows, wc, t.p.c);
     return check_launch("unpad_channels");
   }
   return 0;
@@ -318,7 +497,7 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
 int ttb_conv2d_dgrad_prepacked_supported(const ttb_conv_desc* d) {
   if (!d) return 0;
   TensorPlan t;
-  return (plan_tensor(d, 1, &t) && !t.stage_ops) ? 1 : 0;
+  return (plan_tensor(d, 1, &t) && !t.stage_ops && t.groups == 1) ? 1 : 0;
 }
 
 /* w[i] (Cout, Cin, kh, kw channels-last = [K][R][S][C]) -> w_packed[i] [C][R][S][K], same byte size, for `count` layers */
@@ -334,7 +513,7 @@ int ttb_conv2d_dgrad_prepacked(const ttb_conv_desc* d, const float* dy, const fl
                                void* stream) {
   if (int rc = validate(d, "conv2d_dgrad_prepacked")) return rc;
   TensorPlan t;
-  TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops, "conv2d_dgrad_prepacked: problem needs the staged path");
+  TTB_REQUIRE(plan_tensor(d, 1, &t) && !t.stage_ops && t.groups == 1, "conv2d_dgrad_prepacked: problem needs the staged path");
   if (flat_dgrad_supported(&t.p)) return flat_dgrad(&t.p, dy, w_packed, dx, as_stream(stream), accum);
   return igemm_dgrad(&t.p, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed, accum);
 }
@@ -349,7 +528,7 @@ int ttb_conv2d_wgrad_partial(const ttb_conv_desc* d, const float* x, const float
   *partials_out = nullptr;
   if (int rc = validate(d, "conv2d_wgrad_partial")) return rc;
   TensorPlan t;
-  if (!plan_tensor(d, 2, &t) || t.stage_ops) return ttb_conv2d_wgrad(d, x, dy, dw, workspace, workspace_bytes, stream);
+  if (!plan_tensor(d, 2, &t) || t.stage_ops || t.groups > 1) return ttb_conv2d_wgrad(d, x, dy, dw, workspace, workspace_bytes, stream);
   TTB_REQUIRE(t.inner == 0 || (workspace != nullptr && workspace_bytes >= t.inner),
               "conv2d_wgrad_partial: workspace of %zu bytes needed, %zu given", t.inner, workspace_bytes);
   if (int rc = igemm_wgrad(&t.p, x, dy, dw, workspace, t.inner, as_stream(stream), splits_out)) return rc;

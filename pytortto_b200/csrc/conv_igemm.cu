@@ -76,10 +76,11 @@ static int load_driver_fns() {
 }
 
 // 2-D row-major matrix [rows][cols] -> tiled map with box [box_rows][128 bytes], 128B swizzle, zero OOB fill
+// (`row_stride`: elements between rows, 0 = dense; a channel group of a wider tensor has cols < row_stride)
 static int make_tiled_2d(CUtensorMap* tm, const void* base, Elem el, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                         CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t row_stride = 0) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * (uint64_t)el.size};
+  cuuint64_t strides[1] = {(row_stride ? row_stride : cols) * (uint64_t)el.size};
   cuuint32_t box[2] = {(cuuint32_t)el.per_row, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encodeTiled(tm, el.dt, 2, (void*)base, dims, strides, box, estr,
@@ -107,12 +108,14 @@ static int make_tiled_nd(CUtensorMap* tm, const void* base, Elem el, int rank, c
 
 // NHWC activation [n][h][w][c] -> im2col map: `pixels` base pixels x 128 bytes of channels per load, traversal strides
 // (tw, th), bounding-box corners in W/H order, 128B swizzle, zero fill outside the image.
+// (`cs`: elements between pixels, 0 = c; a channel group of a wider tensor has c < cs)
 static int make_im2col_4d(CUtensorMap* tm, const void* base, Elem el, int n, int h, int w, int c, int lower_w, int lower_h,
                           int upper_w, int upper_h, int tw, int th, uint32_t pixels,
-                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int cs = 0) {
   const cuuint64_t es = (cuuint64_t)el.size;
+  if (cs == 0) cs = c;
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * es, (cuuint64_t)w * c * es, (cuuint64_t)h * w * c * es};
+  cuuint64_t strides[3] = {(cuuint64_t)cs * es, (cuuint64_t)w * cs * es, (cuuint64_t)h * w * cs * es};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)tw, (cuuint32_t)th, 1};
@@ -128,7 +131,7 @@ static int make_im2col_4d(CUtensorMap* tm, const void* base, Elem el, int n, int
   // descriptor word must be cleared (same workaround CUTLASS applies, cute/atom/copy_traits_sm90_im2col.hpp).
   int drv = 0;
   cudaDriverGetVersion(&drv);
-  if (drv <= 13010 && (uint64_t)n * h * w * c * es < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  if (drv <= 13010 && (uint64_t)n * h * w * cs * es < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
   return 0;
 }
 
@@ -139,6 +142,7 @@ struct OutMap {            // accumulator row m -> element offset of the output 
   float* out;
   int64_t n_stride, h_stride, w_stride, base;  // in elements
   int p_dim, q_dim;        // m = (n*p_dim + i)*q_dim + j
+  int q_valid;             // rows with j >= q_valid are dropped (row-shared A strips index a W-padded grid); 0 = all kept
   int m_total;             // rows that exist
   int n_total;             // valid columns (row length to write)
 };
@@ -182,6 +186,7 @@ struct WgradParams {       // wgrad (MN-major A = dY via tiled TMA, MN-major B =
 __device__ __forceinline__ int64_t out_row_offset(const OutMap& o, int m) {
   if (m >= o.m_total) return -1;
   const int j = m % o.q_dim;
+  if (o.q_valid && j >= o.q_valid) return -1;
   const int t = m / o.q_dim;
   const int i = t % o.p_dim;
   const int n = t / o.p_dim;
@@ -209,16 +214,24 @@ struct FwdParamsMulti {
 // STATS: the epilogue also accumulates the per-channel sum / sum of squares of everything this CTA stores and writes
 // them as one segment of a [gridDim.x / nt][2][n_total] double partial buffer (P.ep.stats); the host then sizes the grid
 // as a multiple of nt, so that every CTA keeps the same N tile for all of its tiles (conv_epilogue.cuh).
-template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16, bool STATS>
+// WT > 1 ("row-shared A strip", the 3x3 / stride-1 layers): the WT filter taps of one filter ROW differ only by a shift of
+// one pixel, so output pixels are indexed over a grid that is padded in W (q_dim = Q + WT - 1 positions per row, the last
+// WT - 1 computed and dropped) and ONE im2col load of kTileM + WT - 1 consecutive positions serves all WT taps: tap j is the
+// same strip read through a UMMA descriptor that starts j rows (j * 128 bytes) later (a 128B-swizzled K-major operand may
+// start at any 128-byte row: profiles/r1_umma_row_shift_probe.txt).  A stage then holds the strip + WT weight tiles and
+// costs one hand-shake per 4*WT MMAs; A traffic from L2 drops from R*S to R loads per tile (the 64 / 128-channel layers are
+// bound by exactly that feed: 97-128 B/clk/SM wanted at full tensor rate against ~100 available).
+template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, bool STATS>
 __global__ void __launch_bounds__((NPROD + 5) * 32, BN <= 64 ? 2 : 1)  // narrow tiles: two CTAs per SM (<= 128 registers)
 igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
   static_assert(NSTAGES % NPROD == 0, "a stage must always be filled by the same producer thread");
   constexpr int kElems = BF16 ? 64 : 32;
-  constexpr uint32_t kABytes = kTileM * 128;
+  constexpr uint32_t kARows = kTileM + WT - 1;
+  constexpr uint32_t kALoadBytes = kARows * 128;                       // what the TMA writes
+  constexpr uint32_t kABytes = (kALoadBytes + 1023u) & ~1023u;         // (weight tiles stay 1024-byte aligned)
   constexpr uint32_t kBBytes = BN * 128;
-  constexpr uint32_t kKbBytes = kABytes + kBBytes;       // one K-block: A tile + B tile
-  constexpr uint32_t kStageBytes = KPS * kKbBytes;       // a pipeline stage (one mbarrier hand-shake) holds KPS K-blocks
+  constexpr uint32_t kStageBytes = kABytes + WT * kBBytes;  // a pipeline stage (one mbarrier hand-shake): strip + WT weight tiles
   constexpr int kAccCols = BN < 32 ? 32 : BN;
   constexpr int kTmemCols = 2 * kAccCols;
 
@@ -282,7 +295,7 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
   if (warp < NPROD) {
     // ===================== TMA producers (whole warp, one elected lane issues) =====================
     const int dbg = PM.p[0].dbg;
-    const uint32_t tx_bytes = ((dbg & 2) ? 0 : kABytes) + ((dbg & 4) ? 0 : kBBytes);
+    const uint32_t tx_bytes = ((dbg & 2) ? 0 : kALoadBytes) + ((dbg & 4) ? 0 : WT * kBBytes);
     uint32_t g = 0;  // stages filled by this CTA so far, counted by every producer; stage-fill g belongs to producer g % NPROD
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
       int cls, m0, n0;
@@ -293,25 +306,25 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
       const int i = tt % P.o.p_dim;
       const int n = tt / P.o.p_dim;
       const int cw = P.base_w + j * P.trav_w, ch = P.base_h + i * P.trav_h;
-      const int num_kb = P.num_taps * P.c_blocks;
-      for (int kb = 0; kb < num_kb; kb += KPS, ++g) {
+      const int num_kb = (P.num_taps / WT) * P.c_blocks;   // stage fills per tile: (tap or tap row) x channel block
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
         if ((int)(g % NPROD) != warp) continue;
         const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
-        const int nvalid = num_kb - kb < KPS ? num_kb - kb : KPS;
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (tr && lane == 0 && g < 1000) tr[2048 + g] = clock64();
         uint8_t* sa = smem + stage * kStageBytes;
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&full_bar[stage], (uint32_t)nvalid * tx_bytes);
+          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          const int tap0 = (kb / P.c_blocks) * WT;
+          const int cb = kb - (kb / P.c_blocks) * P.c_blocks;
+          // (WT > 1: the strip is loaded at the row's smallest W offset, 0; tap j reads it shifted by off_w[tap0 + j] rows)
+          if (!(dbg & 2))
+            ptx::tma_load_im2col_4d(sa, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, WT > 1 ? (uint16_t)0 : P.off_w[tap0],
+                                    P.off_h[tap0]);
+          if (!(dbg & 4)) {
 #pragma unroll
-          for (int u = 0; u < KPS; ++u) {
-            if (u >= nvalid) break;
-            const int tap = (kb + u) / P.c_blocks;
-            const int cb = (kb + u) - tap * P.c_blocks;
-            if (!(dbg & 2))
-              ptx::tma_load_im2col_4d(sa + u * kKbBytes, &P.tmA, &full_bar[stage], cb * kElems, cw, ch, n, P.off_w[tap], P.off_h[tap]);
-            if (!(dbg & 4))
-              ptx::tma_load_2d(sa + u * kKbBytes + kABytes, &P.tmB, &full_bar[stage], P.b_koff[tap] + cb * kElems, n0);
+            for (int u = 0; u < WT; ++u)
+              ptx::tma_load_2d(sa + kABytes + u * kBBytes, &P.tmB, &full_bar[stage], P.b_koff[tap0 + u] + cb * kElems, n0);
           }
         }
         __syncwarp();
@@ -326,26 +339,29 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
     for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++it) {
       int cls, m0, n0;
       decode(t, cls, m0, n0);
-      const int num_kb = PM.p[cls].num_taps * PM.p[cls].c_blocks;
+      const FwdParams& P = PM.p[cls];
+      const int num_kb = (P.num_taps / WT) * P.c_blocks;
       const int buf = it & 1;
       ptx::mbar_wait(&acc_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
       ptx::tc_fence_after();
       if (tr && lane == 0 && it < 250) tr[16 + 2 * it] = clock64();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kAccCols);
-      for (int kb = 0; kb < num_kb; kb += KPS, ++g) {
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
         const uint32_t stage = g % NSTAGES, phase = (g / NSTAGES) & 1u;
-        const int nvalid = num_kb - kb < KPS ? num_kb - kb : KPS;
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (tr && lane == 0 && g < 1000) tr[3072 + g] = clock64();
         const uint32_t s0 = ptx::smem_u32(smem + stage * kStageBytes);
+        const int tap0 = (kb / P.c_blocks) * WT;
+        uint32_t shift[WT];  // A-strip row shift of each tap of this stage (warp-uniform)
+#pragma unroll
+        for (int u = 0; u < WT; ++u) shift[u] = WT > 1 ? (uint32_t)P.off_w[tap0 + u] * 128u : 0u;
         if (ptx::elect_one()) {
           if (!(dbg & 1)) {
             const int nmma = (dbg & 8) ? 1 : (dbg & 16) ? 2 : 4;  // experiment: fewer MMAs per K-block (wrong results)
 #pragma unroll
-            for (int u = 0; u < KPS; ++u) {
-              if (u >= nvalid) break;
-              const uint32_t sa = s0 + u * kKbBytes, sb = sa + kABytes;
+            for (int u = 0; u < WT; ++u) {
+              const uint32_t sa = s0 + shift[u], sb = s0 + kABytes + u * kBBytes;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // one MMA consumes 32 bytes of K per row: 8 tf32 or 16 bf16 elements
                 if (k >= nmma) break;
@@ -763,8 +779,16 @@ static int pick_bn(int64_t m_total, int n_total) {
   return 32;
 }
 
-constexpr size_t persist_smem_bytes(int bn, int nstages, int kps) {
-  return (size_t)nstages * kps * (kTileM * 128 + bn * 128) + kEpilogueStagingBytes + 1024;
+constexpr size_t persist_smem_bytes(int bn, int nstages, int wt) {
+  return (size_t)nstages * ((((kTileM + wt - 1) * 128 + 1023) & ~1023) + wt * bn * 128) + kEpilogueStagingBytes + 1024;
+}
+
+// Taps per pipeline stage along W (the kernel's WT): 3 = the three taps of a filter row share one A strip (3-wide filters,
+// unit stride and dilation in W, 64 / 128-wide tiles - wider tiles are tensor-bound already and have no room for three
+// weight tiles per stage; rows shorter than 8 outputs would waste > 25 % of the MMAs on the dropped positions), else 1.
+static int pick_wt(int taps_w, int stride_w, int dil_w, int bn, int q_out) {
+  if (taps_w != 3 || stride_w != 1 || dil_w != 1 || (bn != 64 && bn != 128) || q_out < 8) return 1;
+  return tuning_knob("TTB_WT", 3) == 3 ? 3 : 1;
 }
 
 // CTAs of a persistent launch: one per SM (two for the narrow tiles whose ring is sized for it), never more than tiles;
@@ -777,13 +801,13 @@ static unsigned persist_grid(int64_t tiles, int nt, size_t smem, bool stats) {
   return (unsigned)grid;
 }
 
-template <int BN, int NSTAGES, int NPROD, int KPS, bool BF16, bool STATS>
+template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, bool STATS>
 static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) {
-  constexpr size_t smem = persist_smem_bytes(BN, NSTAGES, KPS);
+  constexpr size_t smem = persist_smem_bytes(BN, NSTAGES, WT);
   static_assert(smem <= 232448, "shared memory budget of one SM");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16, STATS>,
+    cudaError_t e = cudaFuncSetAttribute(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, WT, BF16, STATS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("igemm: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -797,27 +821,30 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
   // narrow tiles leave room for two CTAs per SM (two independent MMA-issue streams: a 64-column K-block is 128
   // tensor-core cycles but ~300 cycles of issue-side latency per CTA)
   const unsigned grid = persist_grid(tiles, nt, smem, STATS);
-  launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, KPS, BF16, STATS>, grid, (NPROD + 5) * 32, smem, st, PM, count);
+  launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, WT, BF16, STATS>, grid, (NPROD + 5) * 32, smem, st, PM, count);
   return check_launch("igemm_fwd_persist_kernel");
 }
 
-// <BN, stages, producer warps, K-blocks per stage>.  Measured on B200 (TF32): the MMA warp pays ~170 cycles per
+// <BN, stages, producer warps, taps per stage>.  Measured on B200 (TF32): the MMA warp pays ~170 cycles per
 // stage hand-shake + ~30 cycles per MMA issue against 32 / 64 / 128 tensor-core cycles per MMA at N = 64 / 128 / 256,
 // so N = 256 is tensor-bound (512 cycles per K-block), N = 128 nearly (300 vs 256) and N <= 64 issue-bound: narrow
 // tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
-// Two K-blocks per stage (KPS = 2) halve the hand-shakes but the 3-stage ring that fits then hides less latency:
-// measured slower (layer 2: 40.8 vs 38.2 us) and dropped.
-struct PersistCfg { int nstages, nprod, kps; };
-static PersistCfg persist_cfg(int bn) {
+struct PersistCfg { int nstages, nprod; };
+static PersistCfg persist_cfg(int bn, int wt) {
+  if (wt == 3) return bn == 128 ? PersistCfg{3, 3} : PersistCfg{2, 2};
   switch (bn) {
-    case 256: return {4, 2, 1};
-    case 128: return {6, 3, 1};
-    default: return {3, 3, 1};
+    case 256: return {4, 2};
+    case 128: return {6, 3};
+    default: return {3, 3};
   }
 }
 
 template <bool BF16, bool STATS>
-static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, cudaStream_t st) {
+static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, int wt, cudaStream_t st) {
+  if (wt == 3) {
+    if (bn == 128) return launch_persist<128, 3, 3, 3, BF16, STATS>(PM, count, st);
+    return launch_persist<64, 2, 2, 3, BF16, STATS>(PM, count, st);
+  }
   switch (bn) {
     case 256: return launch_persist<256, 4, 2, 1, BF16, STATS>(PM, count, st);
     case 128: return launch_persist<128, 6, 3, 1, BF16, STATS>(PM, count, st);
@@ -826,20 +853,24 @@ static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, cudaS
   }
 }
 
-static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, bool bf16, cudaStream_t st) {
+static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, int wt, bool bf16, cudaStream_t st) {
   const bool stats = count == 1 && PM.p[0].ep.stats != nullptr;
-  if (bf16) return stats ? launch_persist_sel<true, true>(PM, count, bn, st) : launch_persist_sel<true, false>(PM, count, bn, st);
-  return stats ? launch_persist_sel<false, true>(PM, count, bn, st) : launch_persist_sel<false, false>(PM, count, bn, st);
+  if (bf16) return stats ? launch_persist_sel<true, true>(PM, count, bn, wt, st) : launch_persist_sel<true, false>(PM, count, bn, wt, st);
+  return stats ? launch_persist_sel<false, true>(PM, count, bn, wt, st) : launch_persist_sel<false, false>(PM, count, bn, wt, st);
 }
 
 // rows of the [chunks][2][K] statistics partial buffer an fprop launch of this problem writes (Epilogue::stats)
 int igemm_fprop_stats_chunks(const ttb_conv_desc* d) {
-  const int64_t m_total = (int64_t)d->n * d->p * d->q;
-  const int bn = pick_bn(m_total, d->k);
-  const PersistCfg c = persist_cfg(bn);
+  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k);
+  // 256-wide tiles (the deep layers: about one tile per CTA, so the epilogue is not hidden behind a next tile's main loop)
+  // measured +5.8 us with statistics against a ~5 us statistics pass over their small outputs: no statistics there
+  if (bn == 256) return 0;
+  const int wt = pick_wt(d->s, d->stride_w, d->dil_w, bn, d->q);
+  const int64_t m_total = (int64_t)d->n * d->p * (d->q + wt - 1);
+  const PersistCfg c = persist_cfg(bn, wt);
   const int nt = (int)ceil_div(d->k, bn);
   const int64_t tiles = ceil_div(m_total, kTileM) * nt;
-  return (int)(persist_grid(tiles, nt, persist_smem_bytes(bn, c.nstages, c.kps), true) / nt);
+  return (int)(persist_grid(tiles, nt, persist_smem_bytes(bn, c.nstages, wt), true) / nt);
 }
 
 static int wgrad_variant() {  // bring-up / tuning knob (tuning build only): 0 = default
@@ -898,24 +929,29 @@ static int igemm_dbg() {  // timing experiments that produce WRONG results: tuni
   return v;
 }
 
-// x, w: operands in the element type of d->math_mode (fp32 for TF32, bf16 for BF16); y, bias: fp32
-int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, void* /*ws*/,
-                size_t /*ws_bytes*/, cudaStream_t st) {
-  if (load_driver_fns()) return 1;
+// One fprop problem -> kernel parameters.  x, w: operands in the element type of d->math_mode (fp32 for TF32, bf16 for BF16);
+// y, bias: fp32.  x_ctot / y_ctot: channel count of the tensors x / y live in when `d` describes ONE GROUP of a grouped
+// convolution (x, y, ep.* then point at the group's first channel); 0 = dense.
+// wt > 1 (row-shared A strips, see the kernel): the traversal box is widened by wt - 1 positions in W - output rows are
+// indexed over Q + wt - 1 positions, the last wt - 1 dropped - and one load brings kTileM + wt - 1 positions.
+static int fprop_params(FwdParams& P, const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, int bn,
+                        int wt, int x_ctot, int y_ctot) {
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
-  FwdParams P;
   memset(&P, 0, sizeof(P));
-  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
-  if (make_im2col_4d(&P.tmA, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, kTileM))
+  const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w + (wt - 1);
+  if (make_im2col_4d(&P.tmA, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h,
+                     kTileM + wt - 1, CU_TENSOR_MAP_SWIZZLE_128B, x_ctot))
     return 1;
+  const int64_t yk = y_ctot ? y_ctot : d->k;
   P.o.out = y;
-  P.o.n_stride = (int64_t)d->p * d->q * d->k;
-  P.o.h_stride = (int64_t)d->q * d->k;
-  P.o.w_stride = d->k;
+  P.o.n_stride = (int64_t)d->p * d->q * yk;
+  P.o.h_stride = (int64_t)d->q * yk;
+  P.o.w_stride = yk;
   P.o.base = 0;
   P.o.p_dim = d->p;
-  P.o.q_dim = d->q;
-  P.o.m_total = d->n * d->p * d->q;
+  P.o.q_dim = d->q + wt - 1;
+  P.o.q_valid = wt > 1 ? d->q : 0;
+  P.o.m_total = d->n * d->p * (d->q + wt - 1);
   P.o.n_total = d->k;
   P.ep = ep;
   P.ep.relu = (ep.relu ? 1 : 0) | (tuning_knob("TTB_EPI_DBG", 0) << 8);  // (experiment bits: tuning build only)
@@ -935,17 +971,53 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epil
       P.off_h[t] = (uint16_t)(r * d->dil_h);
     }
   // weight matrix [K rows][R*S*C cols]; the TMA box height is the kernel's N tile
-  const int bn = pick_bn(P.o.m_total, P.o.n_total);
-  if (make_tiled_2d(&P.tmB, w, el, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn)) return 1;
+  return make_tiled_2d(&P.tmB, w, el, (uint64_t)d->k, (uint64_t)d->r * d->s * d->c, (uint32_t)bn);
+}
+
+int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epilogue& ep, float* y, void* /*ws*/,
+                size_t /*ws_bytes*/, cudaStream_t st) {
+  if (load_driver_fns()) return 1;
   static thread_local FwdParamsMulti PM1;
-  PM1.p[0] = P;
-  return launch_persist_bn(PM1, 1, bn, el.bf16, st);
+  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k);
+  const int wt = pick_wt(d->s, d->stride_w, d->dil_w, bn, d->q);
+  if (fprop_params(PM1.p[0], d, x, w, ep, y, bn, wt, 0, 0)) return 1;
+  return launch_persist_bn(PM1, 1, bn, wt, d->math_mode == TTB_MATH_BF16, st);
+}
+
+// Grouped convolution: `dg` describes one group (c = C/groups, k = K/groups, groups = 1); group g reads x + g*x_goff (a
+// channel slice of a tensor with x_ctot channels per pixel, or its own dense buffer when x_ctot == 0) and w + g*w_goff and
+// writes channels [g*k, (g+1)*k) of y (y_ctot channels per pixel).  Up to kMaxMulti groups share one persistent launch.
+int igemm_fprop_grouped(const ttb_conv_desc* dg, int groups, const void* x, size_t x_goff_bytes, int x_ctot, const void* w,
+                        size_t w_goff_bytes, const Epilogue& ep, float* y, int y_ctot, cudaStream_t st) {
+  if (load_driver_fns()) return 1;
+  static thread_local FwdParamsMulti PM;
+  const int bn = pick_bn((int64_t)dg->n * dg->p * dg->q * (groups < kMaxMulti ? groups : kMaxMulti), dg->k);
+  const int wt = pick_wt(dg->s, dg->stride_w, dg->dil_w, bn, dg->q);
+  for (int g0 = 0; g0 < groups; g0 += kMaxMulti) {
+    const int cnt = groups - g0 < kMaxMulti ? groups - g0 : kMaxMulti;
+    for (int i = 0; i < cnt; ++i) {
+      const int g = g0 + i;
+      Epilogue e = ep;
+      e.stats = nullptr;
+      if (e.scale) e.scale += (size_t)g * dg->k;
+      if (e.bias) e.bias += (size_t)g * dg->k;
+      if (e.accum) e.accum += (size_t)g * dg->k;
+      if (fprop_params(PM.p[i], dg, reinterpret_cast<const char*>(x) + g * x_goff_bytes,
+                       reinterpret_cast<const char*>(w) + g * w_goff_bytes, e, y + (size_t)g * dg->k, bn, wt, x_ctot, y_ctot))
+        return 1;
+    }
+    if (launch_persist_bn(PM, cnt, bn, wt, dg->math_mode == TTB_MATH_BF16, st)) return 1;
+  }
+  return 0;
 }
 
 // `prepacked` != null: the weights are already in the [C][R][S][K] order (igemm_pack_dgrad_weights), w / ws unused
+// dy_ctot / dx_ctot: channel counts of the tensors dy / dx live in when `d` is ONE GROUP of a grouped convolution (dy, dx,
+// accum point at the group's first channel; the caller zeroes dx where no tap reaches: zero_done); 0 = dense.
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st, const void* prepacked, const float* accum) {
+                cudaStream_t st, const void* prepacked, const float* accum, int dy_ctot, int dx_ctot, bool zero_done) {
   // (`accum`, may be null: added to dx in the epilogue - the gradient already pending for the same tensor)
+  const int64_t xc = dx_ctot ? dx_ctot : d->c;
   if (load_driver_fns()) return 1;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   const size_t wbytes = (size_t)d->k * d->r * d->s * d->c * el.size;
@@ -998,21 +1070,28 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         int lo_h = cls.ro[0], lo_w = cls.so[0];
         for (int i = 0; i < cls.nr; ++i) lo_h = cls.ro[i] < lo_h ? cls.ro[i] : lo_h;
         for (int i = 0; i < cls.ns; ++i) lo_w = cls.so[i] < lo_w ? cls.so[i] : lo_w;
-        const int up_h = ha - d->p + lo_h, up_w = wb - d->q + lo_w;
+        // (a stride-1 dgrad is one class: its N tile is known here, and with it whether the three taps of a filter row
+        // share one strip of dY - see pick_wt / the kernel's WT)
+        const int bn1 = multi ? 0 : pick_bn((int64_t)d->n * ha * wb, d->c);
+        const int wtaps = multi ? 1 : pick_wt(cls.ns, d->stride_w, d->dil_w, bn1, wb);
+        const int up_h = ha - d->p + lo_h, up_w = wb - d->q + lo_w + (wtaps - 1);
         TTB_REQUIRE(in_corner_range(lo_h) && in_corner_range(lo_w) && in_corner_range(up_h) && in_corner_range(up_w),
                     "conv2d_dgrad: traversal box out of TMA range");
         FwdParams Pone;
         FwdParams& P = multi ? PM.p[n_multi] : Pone;
         memset(&P, 0, sizeof(P));
-        if (make_im2col_4d(&P.tmA, dy, el, d->n, d->p, d->q, d->k, lo_w, lo_h, up_w, up_h, 1, 1, kTileM)) return 1;
+        if (make_im2col_4d(&P.tmA, dy, el, d->n, d->p, d->q, d->k, lo_w, lo_h, up_w, up_h, 1, 1, kTileM + wtaps - 1,
+                           CU_TENSOR_MAP_SWIZZLE_128B, dy_ctot))
+          return 1;
         P.o.out = dx;
-        P.o.n_stride = (int64_t)d->h * d->w * d->c;
-        P.o.h_stride = (int64_t)d->stride_h * d->w * d->c;
-        P.o.w_stride = (int64_t)d->stride_w * d->c;
-        P.o.base = ((int64_t)a * d->w + b) * d->c;
+        P.o.n_stride = (int64_t)d->h * d->w * xc;
+        P.o.h_stride = (int64_t)d->stride_h * d->w * xc;
+        P.o.w_stride = (int64_t)d->stride_w * xc;
+        P.o.base = ((int64_t)a * d->w + b) * xc;
         P.o.p_dim = ha;
-        P.o.q_dim = wb;
-        P.o.m_total = d->n * ha * wb;
+        P.o.q_dim = wb + wtaps - 1;
+        P.o.q_valid = wtaps > 1 ? wb : 0;
+        P.o.m_total = d->n * ha * (wb + wtaps - 1);
         P.o.n_total = d->c;
         P.ep = Epilogue{nullptr, nullptr, accum, tuning_knob("TTB_EPI_DBG", 0) << 8, nullptr};
         P.c_blocks = d->k / el.per_row;
@@ -1032,19 +1111,18 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
           ++n_multi;
           continue;
         }
-        const int bn = pick_bn(P.o.m_total, P.o.n_total);
-        if (make_tiled_2d(&P.tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
+        if (make_tiled_2d(&P.tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn1)) return 1;
         static thread_local FwdParamsMulti PM1;
         PM1.p[0] = P;
-        if (launch_persist_bn(PM1, 1, bn, el.bf16, st)) return 1;
+        if (launch_persist_bn(PM1, 1, bn1, wtaps, el.bf16, st)) return 1;
       }
     if (pass == 1 && n_multi > 0) {
       const int bn = pick_bn(m_all, d->c);
       for (int i = 0; i < n_multi; ++i)
         if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
-      if (launch_persist_bn(PM, n_multi, bn, el.bf16, st)) return 1;
+      if (launch_persist_bn(PM, n_multi, bn, 1, el.bf16, st)) return 1;
     }
-    if (pass == 0 && need_zero) {  // input pixels no filter tap reaches: zero (or just the pending gradient)
+    if (pass == 0 && need_zero && !zero_done) {  // input pixels no filter tap reaches: zero (or just the pending gradient)
       const size_t bytes = (size_t)d->n * d->h * d->w * d->c * sizeof(float);
       cudaError_t e = accum ? cudaMemcpyAsync(dx, accum, bytes, cudaMemcpyDeviceToDevice, st) : cudaMemsetAsync(dx, 0, bytes, st);
       if (e != cudaSuccess) {
@@ -1077,9 +1155,12 @@ static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits
 
 // `splits_out` != null: the caller sums the splits (igemm_sum_splits_multi); *splits_out = number of partial buffers
 // [K*R*S*C] at the start of ws (<= 1: dw is already final)
+// x_ctot / dy_ctot: channel counts of the tensors x / dy live in when `d` is ONE GROUP of a grouped convolution (x, dy point
+// at the group's first channel, dw at the group's filters); 0 = dense.
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
-                cudaStream_t st, int* splits_out) {
+                cudaStream_t st, int* splits_out, int x_ctot, int dy_ctot) {
   if (load_driver_fns()) return 1;
+  const uint64_t xc = x_ctot ? x_ctot : d->c, yk = dy_ctot ? dy_ctot : d->k;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   int bn, splits, sps, total;
   const int KP = wgrad_plan(d, &bn, &splits, &sps, &total);
@@ -1129,7 +1210,7 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     const cuuint64_t es = (cuuint64_t)el.size;
     {  // dY viewed as [K/slab][pixels][slab]
       cuuint64_t dims[3] = {(cuuint64_t)slab, (cuuint64_t)m, (cuuint64_t)(d->k / slab)};
-      cuuint64_t strides[2] = {(cuuint64_t)d->k * es, (cuuint64_t)slab * es};
+      cuuint64_t strides[2] = {(cuuint64_t)yk * es, (cuuint64_t)slab * es};
       cuuint32_t box[3] = {(cuuint32_t)slab, (cuuint32_t)KP, (cuuint32_t)(kTileM / slab)};
       cuuint32_t estr[3] = {1, 1, 1};
       if (make_tiled_nd(&P.tmDy, dy, el, 3, dims, strides, box, estr, swz)) return 1;
@@ -1137,7 +1218,7 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     {  // x viewed as [C/slab][N][H][W][slab]; box = one tap's slabs for a (bnimg x bh x bw) block of output pixels
       const int per_box = (d->c < bn ? d->c : bn) / slab;
       cuuint64_t dims[5] = {(cuuint64_t)slab, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n, (cuuint64_t)(d->c / slab)};
-      cuuint64_t strides[4] = {(cuuint64_t)d->c * es, (cuuint64_t)d->w * d->c * es, (cuuint64_t)d->h * d->w * d->c * es,
+      cuuint64_t strides[4] = {(cuuint64_t)xc * es, (cuuint64_t)d->w * xc * es, (cuuint64_t)d->h * d->w * xc * es,
                                (cuuint64_t)slab * es};
       cuuint32_t box[5] = {(cuuint32_t)slab, (cuuint32_t)(bw * d->stride_w), (cuuint32_t)(bh * d->stride_h), (cuuint32_t)bnimg,
                            (cuuint32_t)per_box};
@@ -1146,10 +1227,10 @@ int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw
     }
   } else {
     // dY as a [pixels][K] matrix; box = KP pixel rows x 128 bytes of channels
-    if (make_tiled_2d(&P.tmDy, dy, el, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz)) return 1;
+    if (make_tiled_2d(&P.tmDy, dy, el, (uint64_t)m, (uint64_t)d->k, (uint32_t)KP, swz, dy_ctot)) return 1;
     const int up_h = d->pad_h - (d->r - 1) * d->dil_h, up_w = d->pad_w - (d->s - 1) * d->dil_w;
     if (make_im2col_4d(&P.tmX, x, el, d->n, d->h, d->w, d->c, -d->pad_w, -d->pad_h, up_w, up_h, d->stride_w, d->stride_h, KP,
-                       swz))
+                       swz, x_ctot))
       return 1;
   }
   P.pad_w = d->pad_w;

@@ -140,8 +140,13 @@ def test_tensor_path_planning_is_host_logic():
     assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(d16), i) for i in range(3)] == [1, 1, 1]
     assert lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(d16)) == 0
 
-    dg = desc(8, 64, 16, 64, 3, 1, groups=2)  # grouped convolutions take the exact direct kernels
-    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(dg), i) for i in range(3)] == [0, 0, 0]
+    dg = desc(8, 64, 16, 64, 3, 1, groups=2)  # aligned groups (32 channels each) run in place on the tensor path
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(dg), i) for i in range(3)] == [1, 1, 1]
+    assert lib.ttb_conv2d_dgrad_prepacked_supported(ctypes.byref(dg)) == 0 and lib.ttb_conv2d_fprop_stats_chunks(ctypes.byref(dg)) == 0
+    dn = ops.conv_desc((128, 4, 64, 64), (16, 2, 3, 2), (1, 3), (2, 3), (1, 2), 2)  # the reference notebook's known-answer layer
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(dn), i) for i in range(3)] == [1, 0, 1]  # tap-packed per group
+    dodd = desc(8, 48, 16, 48, 3, 1, groups=2)  # 24 channels per group: neither aligned nor small -> exact direct kernels
+    assert [lib.ttb_conv2d_tensor_path_supported(ctypes.byref(dodd), i) for i in range(3)] == [0, 0, 0]
 
     ops.set_math_mode("fp32")
     df = desc(8, 64, 16, 64, 3, 1)
