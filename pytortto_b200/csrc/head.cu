@@ -68,6 +68,31 @@ __global__ void __launch_bounds__(1024) matmul_kernel(const float* __restrict__ 
   if (row < m && col < n) c[(int64_t)row * n + col] = acc + (bias ? bias[col] : 0.f);
 }
 
+// The same product for FEW outputs and a LONG reduction (the classifier head: 256 x 10 logits over 512 features, the
+// 10 x 512 weight gradient over 256 rows): one WARP per output, lanes stride over k, fixed-order shuffle tree - the tiled
+// kernel above would run 8 - 16 blocks with a serial k loop.
+__global__ void __launch_bounds__(256) matmul_splitk_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            const float* __restrict__ bias, float* __restrict__ c, int m, int n,
+                                                            int k, int64_t sam, int64_t sak, int64_t sbk, int64_t sbn) {
+  pdl_entry();
+  const int lane = threadIdx.x & 31;
+  const int64_t o = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= (int64_t)m * n) return;
+  const int row = (int)(o / n), col = (int)(o % n);
+  const float* pa = a + (int64_t)row * sam;
+  const float* pb = b + (int64_t)col * sbn;
+  float acc0 = 0.f, acc1 = 0.f;
+  int kk = lane;
+  for (; kk + 32 < k; kk += 64) {
+    acc0 = fmaf(pa[(int64_t)kk * sak], pb[(int64_t)kk * sbk], acc0);
+    acc1 = fmaf(pa[(int64_t)(kk + 32) * sak], pb[(int64_t)(kk + 32) * sbk], acc1);
+  }
+  if (kk < k) acc0 = fmaf(pa[(int64_t)kk * sak], pb[(int64_t)kk * sbk], acc0);
+  float acc = acc0 + acc1;
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) c[o] = acc + (bias ? bias[col] : 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LogSoftmax over the last axis of a [rows][cols] matrix: one warp per row
 //   aug = x - max(x);  y = aug - log(sum(exp(aug)))            (grad_nn.py:379-383)
@@ -272,6 +297,11 @@ int ttb_matmul(const float* a, const float* b, const float* bias, float* c, int 
                int64_t sbk, int64_t sbn, void* stream) {
   if (m <= 0 || n <= 0) return 0;
   TTB_REQUIRE(k >= 0 && a && b && c, "matmul: bad arguments");
+  if (k >= 128 && (int64_t)m * n <= 16384) {  // few outputs, long reduction: one warp per output
+    launch_k(matmul_splitk_kernel, (unsigned)(((int64_t)m * n + 7) / 8), 256, 0, as_stream(stream), a, b, bias, c, m, n, k, sam,
+             sak, sbk, sbn);
+    return check_launch("matmul");
+  }
   launch_k(matmul_kernel, dim3((n + 31) / 32, (m + 31) / 32), dim3(32, 32), 0, as_stream(stream), a, b, bias, c, m, n, k, sam,
            sak, sbk, sbn);
   return check_launch("matmul");
