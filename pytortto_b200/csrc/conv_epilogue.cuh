@@ -55,11 +55,36 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, floa
   float4* const out4 = reinterpret_cast<float4*>(out);
   const float4* const accum4 = reinterpret_cast<const float4*>(ep.accum);
   const bool relu = (ep.relu & 1) != 0;
+  // The rows of the tensor that is added (residual / pending gradient) are fetched a whole column block at a time, eight
+  // independent loads per lane, and - for tiles of >= 128 columns (one CTA per SM: registers to spare) - one block AHEAD of
+  // the block being stored, so their HBM latency overlaps the TMEM load, the staging and the stores of the previous block.
+  // Loaded one by one next to the store that consumes them (8 dependent round trips per block) a ResNet-50 dgrad with a
+  // pending gradient ran at 16 TFLOP/s.
+  constexpr bool kAhead = BN >= 128;
+  auto load_accum = [&](float4 (&a)[8], int cb) {
+    const int col0 = n0 + cb * 32;
+    const bool ok = col0 + c4 * 4 < n_total;
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      a[it] = (off4[it] >= 0 && ok) ? ld_f4_stream(reinterpret_cast<const float*>(accum4 + ((int64_t)off4[it] + (col0 >> 2) + c4)))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 acc[8], acc_next[8];
+  if (kAhead && accum4) load_accum(acc_next, 0);
   // (fully unrolled: the statistics live in registers indexed by cb)
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
     const int col0 = n0 + cb * 32;
     if (col0 >= n_total) break;  // warp-uniform
+    if (accum4) {
+      if (kAhead) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) acc[it] = acc_next[it];
+        if (cb + 1 < BN / 32) load_accum(acc_next, cb + 1);  // (columns past n_total are not loaded: see load_accum)
+      } else {
+        load_accum(acc, cb);
+      }
+    }
     uint32_t r[32];
     if (!(dbg & 4)) {
       ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(lane_block * 32) << 16) + (uint32_t)(cb * 32), r);
@@ -95,7 +120,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, floa
       if (off4[it] >= 0 && col_ok) {
         const int64_t o4 = (int64_t)off4[it] + colq;
         if (accum4) {
-          const float4 a = ld_f4_stream(reinterpret_cast<const float*>(accum4 + o4));
+          const float4 a = acc[it];
           v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         }
         if (relu) {
