@@ -22,6 +22,7 @@ int direct_fprop(const ttb_conv_desc* d, const float* x, const float* w, const f
 int direct_dgrad(const ttb_conv_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
 int direct_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, float* dw, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+bool pointwise_narrow(const ttb_conv_desc* d);  // 1 x 1 convolutions with <= 4 filters: HBM-streaming exact kernels
 // conv_igemm.cu (operands in the element type of d->math_mode: fp32 for TF32, bf16 for BF16)
 bool igemm_supported(const ttb_conv_desc* d, int pass);
 int igemm_channel_block(const ttb_conv_desc* d);
@@ -218,7 +219,7 @@ static bool plan_grouped(const ttb_conv_desc* d, int pass, TensorPlan* t) {
 }
 
 static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
-  if (d->math_mode == TTB_MATH_FP32) return false;
+  if (d->math_mode == TTB_MATH_FP32 || pointwise_narrow(d)) return false;
   if (d->groups != 1) return plan_grouped(d, pass, t);
   t->p = *d;
   t->groups = 1;

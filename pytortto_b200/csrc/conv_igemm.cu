@@ -29,6 +29,12 @@
 
 namespace ttb {
 
+// conv_wgrad_halo.cu: haloed-tile wgrad of the narrow stride-1 layers
+bool halo_wgrad_selected(const ttb_conv_desc* d);
+size_t halo_wgrad_workspace(const ttb_conv_desc* d);
+int halo_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes, cudaStream_t st,
+               int* splits_out);
+
 constexpr int kMaxTaps = 64;
 constexpr int kTileM = 128;          // UMMA M (rows of the accumulator = TMEM lanes)
 
@@ -104,6 +110,19 @@ static int make_tiled_nd(CUtensorMap* tm, const void* base, Elem el, int rank, c
     return 1;
   }
   return 0;
+}
+
+// for the other tensor-core translation units (conv_wgrad_halo.cu): a tiled map of rank <= 5 with the swizzle of an MN-major
+// (fp32: 128B span / 32B atom, bf16: 128B) or K-major (128B) operand
+int tma_make_tiled(CUtensorMap* tm, const void* base, bool bf16, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides, bool mn_major) {
+  if (load_driver_fns()) return 1;
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUtensorMapSwizzle swz = (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  return make_tiled_nd(tm, base, elem_of(bf16), rank, d, s, b, e, swz);
 }
 
 // NHWC activation [n][h][w][c] -> im2col map: `pixels` base pixels x 128 bytes of channels per load, traversal strides
@@ -593,6 +612,10 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
   }
 }
 
+void launch_sum_splits(const float* partial, int splits, int64_t n, float* out, cudaStream_t st) {
+  launch_k(sum_splits_kernel, elementwise_grid(n, 256), 256, 0, st, partial, splits, n, out);
+}
+
 // Multi-tensor forms: one launch repacks the dgrad weights / sums the wgrad splits of up to kMaxBatch layers (a training
 // step has ~20 of each, every one a few-microsecond latency-bound launch on its own).  Work is cut into units (tiles
 // for the re-ordering, 1024-element chunks for the sums); start[i] = first unit of tensor i.
@@ -918,7 +941,10 @@ size_t igemm_workspace_size(const ttb_conv_desc* d, int pass) {
   if (pass == 1) return welems * (d->math_mode == TTB_MATH_BF16 ? 2 : 4);  // repacked weights [C][R][S][K]
   int bn, splits, sps, total;
   wgrad_plan(d, &bn, &splits, &sps, &total);
-  return splits > 1 ? (size_t)splits * welems * sizeof(float) : 0;
+  const size_t im2col = splits > 1 ? (size_t)splits * welems * sizeof(float) : 0;
+  // (a group of a grouped convolution always takes the im2col kernel: the larger of the two plans)
+  const size_t halo = halo_wgrad_selected(d) ? halo_wgrad_workspace(d) : 0;
+  return halo > im2col ? halo : im2col;
 }
 
 static long long* g_trace = nullptr;
@@ -1160,6 +1186,7 @@ static int launch_wgrad(const WgradParams& P, int ktiles, int ntiles, int splits
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st, int* splits_out, int x_ctot, int dy_ctot) {
   if (load_driver_fns()) return 1;
+  if (x_ctot == 0 && dy_ctot == 0 && halo_wgrad_selected(d)) return halo_wgrad(d, x, dy, dw, ws, ws_bytes, st, splits_out);
   const uint64_t xc = x_ctot ? x_ctot : d->c, yk = dy_ctot ? dy_ctot : d->k;
   const Elem el = elem_of(d->math_mode == TTB_MATH_BF16);
   int bn, splits, sps, total;

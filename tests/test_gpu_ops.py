@@ -95,6 +95,62 @@ def test_conv2d_tensor_path_vs_oracle(case, mode):
     assert_close("dw", dw, dwo, tol)
 
 
+# stride-1 layers with <= 128 filters: wgrad runs on the haloed-tile kernel (conv_wgrad_halo.cu) - ragged boxes, rows wider
+# than a box, no padding, 2- and 4-wide filters, non-square filters, 1 / 2 channel slabs and 1 / 3 filter rows per CTA
+# (N, Cin, H, W, Cout, kh, kw, ph, pw)
+HALO_CASES = [
+    (3, 64, 12, 20, 32, 3, 3, 1, 1),
+    (2, 32, 9, 24, 64, 3, 2, 0, 0),
+    (2, 64, 70, 70, 64, 3, 3, 1, 1),
+    (2, 128, 16, 16, 128, 3, 3, 1, 1),
+    (2, 64, 10, 16, 128, 5, 3, 2, 1),
+    (2, 96, 9, 11, 64, 1, 4, 0, 2),
+    (2, 192, 8, 16, 64, 3, 3, 1, 1),
+    (5, 64, 33, 8, 64, 3, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", HALO_CASES, ids=[f"n{c[0]}_c{c[1]}_{c[2]}x{c[3]}_k{c[4]}_f{c[5]}x{c[6]}p{c[7]}{c[8]}" for c in HALO_CASES])
+def test_wgrad_haloed_tile_vs_oracle(case, mode):
+    tt = _tt(mode)
+    n, ci, h, w, co, kh, kw, ph, pw = case
+    if mode == "bf16" and (ci % 64 or co % 64):
+        pytest.skip("bf16 operands need 64-channel blocks: this shape runs as TF32 (covered by the tf32 case)")
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, kh, kw)) / np.sqrt(ci * kh * kw)).astype(np.float32)
+    yo = O.conv2d_forward(x, wt, None, (1, 1), (ph, pw), (1, 1))
+    dy = rng.standard_normal(yo.shape).astype(np.float32)
+    dxo, dwo, _ = O.conv2d_backward(x, wt, dy, (1, 1), (ph, pw), (1, 1))
+    y, dx, dw, _ = _run_conv(tt, x, wt, None, dy, (1, 1), (ph, pw), (1, 1), 1)
+    tol = TOL[mode]
+    assert_close("y", y, yo, tol)
+    assert_close("dx", dx, dxo, tol)
+    assert_close("dw", dw, dwo, tol)
+
+
+# 1 x 1 convolutions with <= 4 filters (a segmentation head): HBM-streaming exact-fp32 kernels in every math mode
+@pytest.mark.parametrize("case", [(3, 32, 17, 19, 1, True), (2, 64, 8, 8, 3, False), (2, 8, 5, 7, 4, True), (1, 128, 9, 9, 2, True)],
+                         ids=lambda c: f"n{c[0]}_c{c[1]}_{c[2]}x{c[3]}_k{c[4]}")
+def test_pointwise_conv_with_few_filters(case):
+    tt = _tt("tf32")
+    n, ci, h, w, co, bias = case
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, ci, h, w)).astype(np.float32)
+    wt = (rng.standard_normal((co, ci, 1, 1)) / np.sqrt(ci)).astype(np.float32)
+    b = rng.standard_normal(co).astype(np.float32) if bias else None
+    yo = O.conv2d_forward(x, wt, b, 1, 0, 1)
+    dy = rng.standard_normal(yo.shape).astype(np.float32)
+    dxo, dwo, dbo = O.conv2d_backward(x, wt, dy, 1, 0, 1)
+    y, dx, dw, db = _run_conv(tt, x, wt, b, dy, (1, 1), (0, 0), (1, 1), 1)
+    assert_close("y", y, yo, 2e-5)
+    assert_close("dx", dx, dxo, 2e-5)
+    assert_close("dw", dw, dwo, 2e-5)
+    if bias:
+        assert_close("db", db, dy.sum((0, 2, 3)), 2e-5)
+
+
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
 @pytest.mark.parametrize("name", cases_of(load_golden("conv_transpose2d.npz")))
 def test_conv_transpose2d_golden(name, mode):
