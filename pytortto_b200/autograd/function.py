@@ -9,6 +9,7 @@ difference: the per-op `XBackward` class is created once per Function subclass a
 `type()` on every call (function.py:116) - SURVEY.md §8(f) rank 2 (Python dispatch overhead).
 """
 from .helper import get_data
+from .. import ops as _ops
 
 
 class FunctionBase:
@@ -140,6 +141,10 @@ class Function(FunctionBase):
         grad_fn.requires_grad = requires_grad
         grad_fn.xp = inputs[0].data.__class__ if inputs and inputs[0] is not None else None
 
+        # a deferred convolution (ops.conv2d_fprop_deferred) is launched now, in program order, unless this operator is the
+        # one that can absorb it (Add: decides in its own forward)
+        if _ops._pending[0] is not None and not cls.__dict__.get('_absorbs_deferred_conv', False):
+            _ops.resolve_pending(None, ())
         results = cls.forward(grad_fn, *inputs, **params)
         n_out = 1 if results.__class__ is not tuple else len(results)
         grad_fn.grad = [None] * n_out

@@ -62,6 +62,8 @@ def _unbroadcast(g, shape):
 
 
 class Add(Function):
+    _absorbs_deferred_conv = True
+
     @staticmethod
     def forward(ctx, *inputs, **params):
         xt0, xt1 = inputs
@@ -69,7 +71,13 @@ class Add(Function):
         if xd0.__class__ is not cparray or xd1.__class__ is not cparray:
             raise RuntimeError("add: both operands must be on the CUDA device")
         # (training forward of 4-D operands: the same pass emits the statistics of the sum for the BatchNorm that follows)
-        yd0 = ops.add_arrays(xd0, xd1, stats=is_grad_enabled() and xd0.ndim == 4)
+        want_stats = is_grad_enabled() and xd0.ndim == 4
+        if ops.resolve_pending(Add, (xt0, xt1)):
+            # one operand is a convolution whose launch was deferred: conv + shortcut (+ statistics) is ONE kernel
+            deferred, other = (xd0, xd1) if xd0._thunk is not None else (xd1, xd0)
+            yd0 = ops.conv_add_fused(deferred, other, want_stats)
+        else:
+            yd0 = ops.add_arrays(xd0, xd1, stats=want_stats)
         ctx.params['shapes'] = (xd0.shape, xd1.shape)
         return build_links(yd0, grad_fn=ctx)
 

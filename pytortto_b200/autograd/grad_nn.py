@@ -80,7 +80,8 @@ class Convolution(Function):
         # while a graph is being recorded (training forward) the epilogue also emits the per-channel sum / sum of squares
         # of the output: the BatchNorm that reads it next (grad_nn.py:923-924 of the reference) skips its statistics pass
         want_stats = is_grad_enabled() and ops.conv_fused_info(d)[0]
-        yd0 = ops.conv2d_fprop(xd0, xd1, xd2, d, stats=want_stats)
+        # (the launch waits for the next operator: a residual Add is absorbed into the epilogue, ops.conv2d_fprop_deferred)
+        yd0 = ops.conv2d_fprop_deferred(xd0, xd1, xd2, d, want_stats)
         yt0 = build_links(yd0, grad_fn=ctx)
         ctx.save_for_backward(xt0, xt1)
         ctx.params['desc'] = d

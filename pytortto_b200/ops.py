@@ -191,10 +191,10 @@ def conv_fused_info(d):
     return ent[1], ent[2]
 
 
-def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=False):
+def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=False, out=None):
     """y = conv(x, w) [* scale[k]] [+ bias[k]] [+ residual] [max(., 0)]; `stats`: also emit the BatchNorm statistics
-    partials of y (y._bnstats).  scale / residual / relu / stats need conv_fused_info(d)[0]."""
-    y = new_f32((d.n, d.k, d.p, d.q))
+    partials of y (y._bnstats).  scale / residual / relu / stats need conv_fused_info(d)[0].  `out`: write into this array."""
+    y = new_f32((d.n, d.k, d.p, d.q)) if out is None else out
     if y.size == 0:
         return y
     bf16_direct = d.math_mode == _cabi.TTB_MATH_BF16 and conv_bf16_supported(d, 0) and w.ndim == 4
@@ -226,6 +226,75 @@ def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=Fal
         _cabi.call("ttb_conv2d_fprop", ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(y),
                    None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
     return y
+
+
+# A residual block ends with `conv(...) + shortcut` (reference examples: BasicBlock.forward; tensor.py `Add`).  The conv
+# epilogue can add the shortcut (and emit the next BatchNorm's statistics of the SUM), which removes a full 2R+1W pass - but
+# Convolution.forward does not know what follows it.  So a convolution with a fused epilogue is DEFERRED: its output array
+# exists, the launch is a thunk on the array (`cparray._thunk`, run by the first access to its storage) and `_pending`
+# remembers it.  The very next operator (autograd Function.apply -> resolve_pending) either is the `Add` that consumes it -
+# then ONE launch computes conv + shortcut into the Add's output and the deferred array stays unmaterialised (anything that
+# still touches it later gets the plain convolution) - or it is anything else, and the convolution is launched first, in
+# program order.  Nothing can run between the deferral and that decision except direct array accesses, which materialise.
+_pending = [None]
+_DEFER = os.environ.get("TORTTO_B200_DEFER_CONV", "1") != "0"
+
+
+class _DeferredConv:
+    __slots__ = ("x", "w", "bias", "d", "stats", "vx", "vw")
+
+
+def conv2d_fprop_deferred(x, w, bias, d, stats):
+    """conv2d_fprop whose launch waits for the next operator (see above); falls back to an immediate launch when the problem
+    has no fused epilogue."""
+    if not _DEFER or not conv_fused_info(d)[0] or d.n * d.k * d.p * d.q == 0:
+        return conv2d_fprop(x, w, bias, d, stats=stats)
+    resolve_pending(None, ())
+    y = new_f32((d.n, d.k, d.p, d.q))
+    job = _DeferredConv()
+    job.x, job.w, job.bias, job.d, job.stats = x, w, bias, d, stats
+    job.vx, job.vw = x._version[0], w._version[0]
+
+    def launch(arr, job=job):
+        if _pending[0] is not None and _pending[0]() is arr:
+            _pending[0] = None
+        if job.x._version[0] != job.vx or job.w._version[0] != job.vw:
+            raise RuntimeError("an operand of a convolution was modified in place before its deferred output was read")
+        conv2d_fprop(job.x, job.w, job.bias, job.d, stats=job.stats, out=arr)
+
+    launch.job = job
+    y._thunk = launch
+    _pending[0] = weakref.ref(y)
+    return y
+
+
+def resolve_pending(op_cls, inputs):
+    """Called before every operator's forward (and at the start of backward): launches the deferred convolution unless
+    `op_cls` is the Add that can absorb it.  Returns True when the Add may take the fused path."""
+    ref = _pending[0]
+    if ref is None:
+        return False
+    arr = ref()
+    if arr is None or arr._thunk is None:
+        _pending[0] = None
+        return False
+    if op_cls is not None and getattr(op_cls, "_absorbs_deferred_conv", False) and len(inputs) == 2:
+        a, b = inputs[0].data, inputs[1].data
+        other = b if a is arr else (a if b is arr else None)
+        if (other is not None and other is not arr and other.__class__ is cparray and other.shape == arr.shape
+                and other._t.dtype == torch.float32):
+            return True
+    arr.t  # noqa: B018 - materialises (program order)
+    return False
+
+
+def conv_add_fused(deferred, other, stats):
+    """conv(x, w) (+ bias) + other, the sum's BatchNorm statistics emitted by the same epilogue; `deferred` stays deferred"""
+    job = deferred._thunk.job
+    _pending[0] = None
+    if job.x._version[0] != job.vx or job.w._version[0] != job.vw:
+        raise RuntimeError("an operand of a convolution was modified in place before its deferred output was read")
+    return conv2d_fprop(job.x, job.w, job.bias, job.d, residual=other, stats=stats)
 
 
 def conv2d_bn_eval(x, w, conv_bias, d, mean, var, eps, gamma, beta, relu):
@@ -261,6 +330,7 @@ _prepack_ok = {}
 
 
 def begin_backward_sweep():
+    resolve_pending(None, ())
     _dgrad_pack["sweep"] += 1
     _dgrad_pack["in_sweep"] = True
 

@@ -57,7 +57,22 @@ class cparray:
     """Device array.  `t` is the owning torch tensor (logical shape, canonical physical layout).
     `_h` / `_hver`: optional bf16 shadow of the same values (same physical layout) and the `_version` it was written
     at - co-written by the producing kernel in bf16 math mode so the next convolution reads 2-byte operands."""
-    __slots__ = ("t", "_version", "base", "_h", "_hver", "_bnstats", "__weakref__")
+    __slots__ = ("_t", "_thunk", "_version", "base", "_h", "_hver", "_bnstats", "__weakref__")
+
+    # `t` is a property so that an array can be DEFERRED: its storage (`_t`) exists, but the kernel that fills it
+    # (`_thunk`) has not been launched yet and runs on the first access to `t`.  ops.conv2d_fprop_deferred uses this to let
+    # the residual `Add` that follows a convolution run inside the convolution's epilogue (ops.resolve_pending).
+    @property
+    def t(self):
+        th = self._thunk
+        if th is not None:
+            self._thunk = None
+            th(self)
+        return self._t
+
+    @t.setter
+    def t(self, value):
+        self._t = value
 
     def __init__(self, t, version=None, base=None):
         if t.__class__ is not torch.Tensor:
@@ -66,7 +81,8 @@ class cparray:
             t = t.contiguous(memory_format=torch.channels_last)
         elif t.dim() != 4 and not t.is_contiguous():
             t = t.contiguous()
-        self.t = t
+        self._t = t
+        self._thunk = None
         self._version = [0] if version is None else version
         self.base = base
         self._h = None
@@ -79,7 +95,7 @@ class cparray:
         """an in-place write happened outside the shadow-maintaining kernels"""
         self._h = None
         self._bnstats = None
-        if self.t.dim() == 4:
+        if self._t.dim() == 4:
             mutation_epoch[0] += 1
 
     # ---- construction / transfer --------------------------------------------------------------------------
@@ -114,32 +130,32 @@ class cparray:
     # ---- numpy-style attributes -----------------------------------------------------------------------------
     @property
     def shape(self):
-        return tuple(self.t.shape)
+        return tuple(self._t.shape)
 
     @property
     def ndim(self):
-        return self.t.dim()
+        return self._t.dim()
 
     @property
     def size(self):
-        return self.t.numel()
+        return self._t.numel()
 
     @property
     def dtype(self):
-        return _TORCH_TO_NP[self.t.dtype]
+        return _TORCH_TO_NP[self._t.dtype]
 
     @property
     def itemsize(self):
-        return self.t.element_size()
+        return self._t.element_size()
 
     @property
     def nbytes(self):
-        return self.t.numel() * self.t.element_size()
+        return self._t.numel() * self._t.element_size()
 
     @property
     def strides(self):
-        es = self.t.element_size()
-        return tuple(s * es for s in self.t.stride())
+        es = self._t.element_size()
+        return tuple(s * es for s in self._t.stride())
 
     @property
     def data(self):
@@ -151,14 +167,14 @@ class cparray:
 
     @property
     def device(self):
-        return self.t.device
+        return self._t.device
 
     @property
     def flags(self):
-        return {"C_CONTIGUOUS": self.t.is_contiguous(), "OWNDATA": self.base is None}
+        return {"C_CONTIGUOUS": self._t.is_contiguous(), "OWNDATA": self.base is None}
 
     def __len__(self):
-        return self.t.shape[0]
+        return self._t.shape[0]
 
     def __repr__(self):
         return f"cparray(shape={self.shape}, dtype={self.dtype}, device='{self.device}')"

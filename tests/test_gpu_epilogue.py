@@ -237,3 +237,81 @@ def test_training_step_uses_epilogue_statistics():
     assert_close("y", a[0], b[0], 2e-5)
     assert_close("dx", a[1], b[1], 1e-4)
     assert_close("running_var", a[2], b[2], 2e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
+    """`conv(x) + shortcut` (the end of a residual block): the convolution's launch waits for the next operator, the Add
+    runs inside its epilogue - one conv launch, no add kernel, the statistics of the SUM reach the next BatchNorm - and the
+    result / gradients equal the separate ops; the un-added convolution output is still readable afterwards."""
+    tt = _tt(mode)
+    from pytortto_b200 import _cabi, ops
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((16, 64, 16, 16)).astype(np.float32)
+    s = rng.standard_normal((16, 64, 16, 16)).astype(np.float32)
+    dy = rng.standard_normal((16, 64, 16, 16)).astype(np.float32)
+
+    def run(defer):
+        ops._DEFER = defer
+        names = []
+        orig = _cabi.call
+
+        def spy(name, *a):
+            names.append(name)
+            return orig(name, *a)
+        _cabi.call = spy
+        try:
+            np.random.seed(0)
+            conv = tt.nn.Conv2d(64, 64, 3, 1, 1, bias=False).cuda()
+            bn = tt.nn.BatchNorm2d(64).cuda()
+            xin = tt.nn.Parameter(tt.tensor(x).cuda())
+            sin = tt.nn.Parameter(tt.tensor(s).cuda())
+            c = conv(xin)
+            z = c + sin
+            out = bn(z)
+            out.backward(tt.tensor(dy).cuda())
+            res = (z.data.get(), out.data.get(), xin.grad.get(), sin.grad.get(), conv.weight.grad.get(), c.data.get())
+        finally:
+            _cabi.call = orig
+            ops._DEFER = True
+        return res, names
+
+    (a, names_a), (b, names_b) = run(True), run(False)
+    fwd_a = names_a[:names_a.index("ttb_bn_finalize")]
+    assert not any(n.startswith("ttb_add") for n in fwd_a), fwd_a
+    assert sum(n.startswith("ttb_conv2d_fprop") for n in fwd_a) == 1, fwd_a
+    assert "ttb_bn_stats" not in names_a  # the epilogue emitted the statistics of the sum
+    assert any(n.startswith("ttb_add") for n in names_b[:names_b.index("ttb_bn_finalize")])
+    tol = TOL[mode]
+    for name, u, v in zip(("z", "bn(z)", "dx", "dshortcut", "dw"), a[:5], b[:5]):
+        assert_close(f"{mode} {name}", u, v, 1e-5 if name != "dw" else 1e-4)
+    # the convolution alone (materialised on demand after the fused launch) = z - shortcut
+    assert_close(f"{mode} conv output read after the fusion", a[5], b[5], 1e-6)
+    assert_close(f"{mode} conv vs z - s", a[5], a[0] - s, 10 * tol)
+
+
+def test_deferred_convolution_keeps_program_order():
+    """anything but an absorbing Add launches the deferred convolution first: ReLU / a second use / a backward right after
+    the conv all see the same values as an immediate launch"""
+    tt = _tt("tf32")
+    from pytortto_b200 import ops
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((4, 32, 8, 8)).astype(np.float32)
+
+    def run(defer):
+        ops._DEFER = defer
+        try:
+            np.random.seed(0)
+            conv = tt.nn.Conv2d(32, 32, 3, 1, 1).cuda()
+            xin = tt.nn.Parameter(tt.tensor(x).cuda())
+            c = conv(xin)
+            r = tt.nn.functional.relu(c)       # not an Add: conv launches first
+            z = c + c                           # both operands are the same (already materialised) array
+            w = conv(xin) + 1.0                 # scalar operand: shapes differ, plain path
+            (r.sum() + z.sum() + w.sum()).backward()
+            return r.data.get(), z.data.get(), w.data.get(), xin.grad.get(), conv.weight.grad.get()
+        finally:
+            ops._DEFER = True
+
+    for u, v in zip(run(True), run(False)):
+        assert_close("deferred vs immediate", u, v, 1e-6)
