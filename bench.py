@@ -320,6 +320,9 @@ def profile_families(step, x_dev, y_dev, steps=3):
         elif name == "ttb_bn_apply":        # BN fwd 2R+1W, bwd 4R+1W; fused ReLU credited fwd 1R+1W, bwd 2R+1W (fp32)
             m, c, relu = a[2], a[3], a[7]
             work["hbm_bytes"] += 4.0 * m * c * ((3 + 5) + ((2 + 3) if relu else 0))
+        elif name == "ttb_bn_apply_add":    # bn(x) + identity (+ReLU) in one pass: credited as the three operators it replaces
+            m, c, relu = a[3], a[4], a[8]
+            work["hbm_bytes"] += 4.0 * m * c * ((3 + 5) + 3 + ((2 + 3) if relu else 0))
         elif name == "ttb_relu_fwd":
             work["hbm_bytes"] += 4.0 * a[2] * (2 + 3)
         elif name == "ttb_add":             # residual add / gradient accumulation: 2R + 1W

@@ -184,6 +184,11 @@ int ttb_bn_fold_eval(const float* mean, const float* var, int c, float eps, cons
  * y_bf16 (may be NULL): the same values rounded to bf16, co-written for the bf16 tensor path (ttb_conv2d_*_bf16). */
 int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* mean, const float* scale, const float* beta,
                  int relu, void* y_bf16, void* stream);
+/* y = bn(x) + residual, then max(y, 0) if relu != 0: the tail of a post-activation residual block (BatchNorm.forward
+ * grad_nn.py:942-959 -> `Add` -> Relu.forward :58) as one pass; same arguments as ttb_bn_apply plus `residual` (shape of x);
+ * needs c % 4 == 0 */
+int ttb_bn_apply_add(const float* x, const float* residual, float* y, int64_t m, int c, const float* mean, const float* scale,
+                     const float* beta, int relu, void* y_bf16, void* stream);
 /* partials[chunk][2][C]: sum(dy), sum(dy*(x-mean)).  If relu_out != NULL dy is first masked by (relu_out > 0)
  * (fused ReLU backward, grad_nn.py:64-69).  The mask of a fused BatchNorm+ReLU node comes either from relu_out (the
  * saved ReLU output) or - one read per element cheaper - is recomputed as fmaf(x - mean, relu_scale, relu_shift) > 0

@@ -71,6 +71,7 @@ _PROTOS = {
     "ttb_bn_prepare_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_fold_eval": (c_int, [_F, _F, c_int, c_float, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_apply": (c_int, [_F, _F, c_int64, c_int, _F, _F, _F, c_int, _F, c_void_p]),
+    "ttb_bn_apply_add": (c_int, [_F, _F, _F, c_int64, c_int, _F, _F, _F, c_int, _F, c_void_p]),
     "ttb_bn_bwd_reduce": (c_int, [_F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_int, c_void_p]),
     "ttb_bn_bwd_finalize": (c_int, [_F, c_int, c_int64, c_int, _F, _F, _F, _F, _F, _F, c_void_p]),
     "ttb_bn_bwd_apply": (c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, c_int64, c_int, _F, c_void_p]),

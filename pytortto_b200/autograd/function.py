@@ -141,9 +141,9 @@ class Function(FunctionBase):
         grad_fn.requires_grad = requires_grad
         grad_fn.xp = inputs[0].data.__class__ if inputs and inputs[0] is not None else None
 
-        # a deferred convolution (ops.conv2d_fprop_deferred) is launched now, in program order, unless this operator is the
-        # one that can absorb it (Add: decides in its own forward)
-        if _ops._pending[0] is not None and not cls.__dict__.get('_absorbs_deferred_conv', False):
+        # a deferred producer (ops._defer: a convolution / BatchNorm normalise pass) is launched now, in program order, unless this operator is the
+        # one that can absorb it (Add, ReLU: they decide in their own forward)
+        if _ops._pending[0] is not None and not cls.__dict__.get('_absorbs'):
             _ops.resolve_pending(None, ())
         results = cls.forward(grad_fn, *inputs, **params)
         n_out = 1 if results.__class__ is not tuple else len(results)

@@ -62,7 +62,7 @@ def _unbroadcast(g, shape):
 
 
 class Add(Function):
-    _absorbs_deferred_conv = True
+    _absorbs = ("conv", "bn")
 
     @staticmethod
     def forward(ctx, *inputs, **params):
@@ -72,10 +72,13 @@ class Add(Function):
             raise RuntimeError("add: both operands must be on the CUDA device")
         # (training forward of 4-D operands: the same pass emits the statistics of the sum for the BatchNorm that follows)
         want_stats = is_grad_enabled() and xd0.ndim == 4
-        if ops.resolve_pending(Add, (xt0, xt1)):
-            # one operand is a convolution whose launch was deferred: conv + shortcut (+ statistics) is ONE kernel
-            deferred, other = (xd0, xd1) if xd0._thunk is not None else (xd1, xd0)
-            yd0 = ops.conv_add_fused(deferred, other, want_stats)
+        deferred = ops.resolve_pending(Add, (xt0, xt1))
+        if deferred is not None:
+            other = xd1 if deferred is xd0 else xd0
+            if deferred._thunk.job.kind == "conv":  # conv + shortcut (+ statistics of the sum) is ONE kernel
+                yd0 = ops.conv_add_fused(deferred, other, want_stats)
+            else:  # a BatchNorm normalise pass: the sum stays deferred - a ReLU may follow (post-activation blocks)
+                yd0 = ops.bn_add_deferred(deferred, other)
         else:
             yd0 = ops.add_arrays(xd0, xd1, stats=want_stats)
         ctx.params['shapes'] = (xd0.shape, xd1.shape)

@@ -28,16 +28,23 @@ def _require_cuda(name, *arrays):
 
 class Relu(Function):
     """reference grad_nn.py:33-69: y = maximum(x, 0) (NaN-propagating); saves the OUTPUT; dx = dy * (y > 0)."""
+    _absorbs = ("bn", "bn_add")
 
     @staticmethod
     def forward(ctx, *inputs, **params):
         xt0, = inputs
         xd0 = xt0.data
         _require_cuda('relu', xd0)
+        deferred = ops.resolve_pending(Relu, (xt0,))  # a deferred bn(x) [+ identity]: the ReLU joins its normalise pass
         if params['inplace']:
             inplace_precheck(xt0)
-            ops.relu_fwd(xd0, inplace=True)
+            if deferred is not None:
+                ops.bn_relu_fused(deferred, out=xd0)
+            else:
+                ops.relu_fwd(xd0, inplace=True)
             yt0 = inplace_update(xt0, ctx)
+        elif deferred is not None:
+            yt0 = build_links(ops.bn_relu_fused(deferred), grad_fn=ctx)
         else:
             yt0 = build_links(ops.relu_fwd(xd0), grad_fn=ctx)
         ctx.save_for_backward(yt0)

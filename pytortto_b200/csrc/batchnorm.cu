@@ -412,6 +412,29 @@ __global__ void bn_apply_scalar_kernel(const float* __restrict__ x, float* __res
   }
 }
 
+// y = bn(x) + residual (+ReLU): the tail of a post-activation residual block (BatchNorm -> `out += identity` -> ReLU,
+// reference examples/resnet/resnet50_finetune: Bottleneck.forward) as ONE 2R+1W pass instead of the three passes
+// (1R+1W, 2R+1W, 1R+1W) of the separate operators.
+template <bool RELU, bool SHADOW>
+__global__ void __launch_bounds__(256)
+bn_apply_add_kernel(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
+                    __nv_bfloat16* __restrict__ yh, int64_t n4, int cq, const float* __restrict__ mean,
+                    const float* __restrict__ scale, const float* __restrict__ beta) {
+  pdl_entry();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 r = ld_f4_stream(res + 4 * i);
+    float4 a = bn_apply4<false>(ld_f4_stream(x + 4 * i), mean, scale, beta, (int)(i % cq));
+    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+    if (RELU) {
+      a.x = a.x < 0.f ? 0.f : a.x; a.y = a.y < 0.f ? 0.f : a.y;
+      a.z = a.z < 0.f ? 0.f : a.z; a.w = a.w < 0.f ? 0.f : a.w;
+    }
+    st_f4(y + 4 * i, a);
+    if (SHADOW) st_bf16x4(yh + 4 * i, a);
+  }
+}
+
 // dx = c1*(g - c2 - (x-mean)*c3) [+ accum], g = dy (masked by relu_out > 0 when given).  `accum`: a gradient that already
 // reached the same tensor through another branch (the residual shortcut) - added here instead of by a separate kernel.
 // MASK: 0 none, 1 read the ReLU output, 2 recompute it from x (fmaf(x - mean, rscale, rbeta), see col_reduce_kernel).
@@ -613,6 +636,26 @@ int ttb_bn_apply(const float* x, float* y, int64_t m, int c, const float* mean, 
     else launch_k(bn_apply_scalar_kernel<false>, grid, 256, 0, st, x, y, yh, n, c, mean, scale, beta);
   }
   return check_launch("bn_apply");
+}
+
+int ttb_bn_apply_add(const float* x, const float* residual, float* y, int64_t m, int c, const float* mean, const float* scale,
+                     const float* beta, int relu, void* y_bf16, void* stream) {
+  int64_t n = m * c;
+  if (n <= 0) return 0;
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+  TTB_REQUIRE(c % 4 == 0 && a16(x) && a16(residual) && a16(y) && a16(mean) && a16(scale) && a16(beta) &&
+                  (reinterpret_cast<uintptr_t>(yh) & 7) == 0,
+              "bn_apply_add: needs a multiple of 4 channels and 16-byte aligned buffers");
+  cudaStream_t st = as_stream(stream);
+  const int grid = elementwise_grid(n / 4, 256);
+  if (relu) {
+    if (yh) launch_k(bn_apply_add_kernel<true, true>, grid, 256, 0, st, x, residual, y, yh, n / 4, c / 4, mean, scale, beta);
+    else launch_k(bn_apply_add_kernel<true, false>, grid, 256, 0, st, x, residual, y, yh, n / 4, c / 4, mean, scale, beta);
+  } else {
+    if (yh) launch_k(bn_apply_add_kernel<false, true>, grid, 256, 0, st, x, residual, y, yh, n / 4, c / 4, mean, scale, beta);
+    else launch_k(bn_apply_add_kernel<false, false>, grid, 256, 0, st, x, residual, y, yh, n / 4, c / 4, mean, scale, beta);
+  }
+  return check_launch("bn_apply_add");
 }
 
 int ttb_bn_bwd_reduce(const float* dy, const float* x, const float* mean, const float* relu_out, const float* relu_scale,

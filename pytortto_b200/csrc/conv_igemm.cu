@@ -886,8 +886,10 @@ static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, int wt
 int igemm_fprop_stats_chunks(const ttb_conv_desc* d) {
   const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k);
   // 256-wide tiles (the deep layers: about one tile per CTA, so the epilogue is not hidden behind a next tile's main loop)
-  // measured +5.8 us with statistics against a ~5 us statistics pass over their small outputs: no statistics there
-  if (bn == 256) return 0;
+  // measured +5.8 us with statistics against a ~5 us statistics pass over their small outputs: no statistics there -
+  // unless the output is large (the 1 x 1 expansions of ResNet-50: 100-800 MB, several tiles per CTA), where the separate
+  // pass is a full HBM read of the tensor (38 of that network's 53 BatchNorms ran one: 3.8 ms of a 56 ms step)
+  if (bn == 256 && (int64_t)d->n * d->p * d->q * d->k < tuning_knob("TTB_STATS256_MIN_MELEMS", 8) * (int64_t)(1 << 20)) return 0;
   const int wt = pick_wt(d->s, d->stride_w, d->dil_w, bn, d->q);
   const int64_t m_total = (int64_t)d->n * d->p * (d->q + wt - 1);
   const PersistCfg c = persist_cfg(bn, wt);

@@ -228,39 +228,47 @@ def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=Fal
     return y
 
 
-# A residual block ends with `conv(...) + shortcut` (reference examples: BasicBlock.forward; tensor.py `Add`).  The conv
-# epilogue can add the shortcut (and emit the next BatchNorm's statistics of the SUM), which removes a full 2R+1W pass - but
-# Convolution.forward does not know what follows it.  So a convolution with a fused epilogue is DEFERRED: its output array
-# exists, the launch is a thunk on the array (`cparray._thunk`, run by the first access to its storage) and `_pending`
-# remembers it.  The very next operator (autograd Function.apply -> resolve_pending) either is the `Add` that consumes it -
-# then ONE launch computes conv + shortcut into the Add's output and the deferred array stays unmaterialised (anything that
-# still touches it later gets the plain convolution) - or it is anything else, and the convolution is launched first, in
-# program order.  Nothing can run between the deferral and that decision except direct array accesses, which materialise.
+# Deferred producers ("the next operator decides the epilogue").
+# A residual block ends with `conv(...) + shortcut` (pre-activation: reference examples' BasicBlock.forward) or with
+# `relu(bn(conv(...)) + identity)` (post-activation: Bottleneck.forward of the ResNet-50 notebook).  The conv epilogue can
+# add the shortcut (and emit the next BatchNorm's statistics of the SUM), and BatchNorm's normalise pass can add the
+# identity and apply the ReLU - each fusion removes full HBM passes - but an operator's forward does not know what follows
+# it.  So such a producer is DEFERRED: its output array exists, the launch is a thunk on the array (`cparray._thunk`, run by
+# the first access to its storage) and `_pending` remembers it.  The very next operator (autograd Function.apply ->
+# resolve_pending) either ABSORBS it -
+#     Add  <- deferred convolution      : ONE launch conv + shortcut (+ statistics) into the Add's output
+#     Add  <- deferred BatchNorm apply  : the sum is itself deferred ("bn_add": y = bn(x) + other)
+#     ReLU <- deferred bn_add / bn      : ONE normalise pass y = max(bn(x) [+ other], 0) into the ReLU's output
+# and the absorbed array stays unmaterialised (anything that still touches it later gets the plain producer) - or it is
+# anything else, and the producer is launched first, in program order.  Nothing can run between the deferral and that
+# decision except direct array accesses, which materialise.  Gradients are unaffected: none of the absorbed intermediate
+# values is saved for backward (Convolution saves its input and weight, BatchNorm its input, Add nothing, ReLU its output).
 _pending = [None]
 _DEFER = os.environ.get("TORTTO_B200_DEFER_CONV", "1") != "0"
 
 
-class _DeferredConv:
-    __slots__ = ("x", "w", "bias", "d", "stats", "vx", "vw")
+class _Job:
+    """what a deferred launch needs; `versions`: (array, version) pairs that must be unchanged when it finally runs"""
+    __slots__ = ("kind", "args", "versions")
+
+    def check(self):
+        for arr, ver in self.versions:
+            if arr._version[0] != ver:
+                raise RuntimeError("an operand of a deferred convolution / batch-norm was modified in place before its output was read")
 
 
-def conv2d_fprop_deferred(x, w, bias, d, stats):
-    """conv2d_fprop whose launch waits for the next operator (see above); falls back to an immediate launch when the problem
-    has no fused epilogue."""
-    if not _DEFER or not conv_fused_info(d)[0] or d.n * d.k * d.p * d.q == 0:
-        return conv2d_fprop(x, w, bias, d, stats=stats)
+def _defer(y, kind, args, operands, run):
+    """mark `y` as produced by `run(y, *args)` later; returns y"""
     resolve_pending(None, ())
-    y = new_f32((d.n, d.k, d.p, d.q))
-    job = _DeferredConv()
-    job.x, job.w, job.bias, job.d, job.stats = x, w, bias, d, stats
-    job.vx, job.vw = x._version[0], w._version[0]
+    job = _Job()
+    job.kind, job.args = kind, args
+    job.versions = tuple((a, a._version[0]) for a in operands if a is not None)
 
-    def launch(arr, job=job):
+    def launch(arr, job=job, run=run):
         if _pending[0] is not None and _pending[0]() is arr:
             _pending[0] = None
-        if job.x._version[0] != job.vx or job.w._version[0] != job.vw:
-            raise RuntimeError("an operand of a convolution was modified in place before its deferred output was read")
-        conv2d_fprop(job.x, job.w, job.bias, job.d, stats=job.stats, out=arr)
+        job.check()
+        run(arr, *job.args)
 
     launch.job = job
     y._thunk = launch
@@ -268,33 +276,102 @@ def conv2d_fprop_deferred(x, w, bias, d, stats):
     return y
 
 
-def resolve_pending(op_cls, inputs):
-    """Called before every operator's forward (and at the start of backward): launches the deferred convolution unless
-    `op_cls` is the Add that can absorb it.  Returns True when the Add may take the fused path."""
+def pending_array():
     ref = _pending[0]
     if ref is None:
-        return False
+        return None
     arr = ref()
     if arr is None or arr._thunk is None:
         _pending[0] = None
-        return False
-    if op_cls is not None and getattr(op_cls, "_absorbs_deferred_conv", False) and len(inputs) == 2:
-        a, b = inputs[0].data, inputs[1].data
-        other = b if a is arr else (a if b is arr else None)
-        if (other is not None and other is not arr and other.__class__ is cparray and other.shape == arr.shape
-                and other._t.dtype == torch.float32):
-            return True
+        return None
+    return arr
+
+
+def resolve_pending(op_cls, inputs):
+    """Called before every operator's forward (and at the start of backward).  Returns the deferred array if `op_cls`
+    (a Function class with `_absorbs` = kinds it can take) consumes it as one of `inputs` and can absorb it; otherwise
+    launches the deferred producer (program order) and returns None."""
+    arr = pending_array()
+    if arr is None:
+        return None
+    kinds = getattr(op_cls, "_absorbs", ()) if op_cls is not None else ()
+    if arr._thunk.job.kind in kinds:
+        datas = [i.data for i in inputs if i is not None]
+        if any(d is arr for d in datas):
+            others = [d for d in datas if d is not arr]
+            if all(o.__class__ is cparray and o._thunk is None and o.shape == arr.shape and o._t.dtype == torch.float32
+                   for o in others):
+                return arr
     arr.t  # noqa: B018 - materialises (program order)
-    return False
+    return None
+
+
+def conv2d_fprop_deferred(x, w, bias, d, stats):
+    """conv2d_fprop whose launch waits for the next operator (see above); an immediate launch when the problem has no fused
+    epilogue."""
+    if not _DEFER or not conv_fused_info(d)[0] or d.n * d.k * d.p * d.q == 0:
+        return conv2d_fprop(x, w, bias, d, stats=stats)
+    y = new_f32((d.n, d.k, d.p, d.q))
+    return _defer(y, "conv", (x, w, bias, d, stats), (x, w, bias),
+                  lambda arr, x, w, bias, d, stats: conv2d_fprop(x, w, bias, d, stats=stats, out=arr))
 
 
 def conv_add_fused(deferred, other, stats):
     """conv(x, w) (+ bias) + other, the sum's BatchNorm statistics emitted by the same epilogue; `deferred` stays deferred"""
     job = deferred._thunk.job
     _pending[0] = None
-    if job.x._version[0] != job.vx or job.w._version[0] != job.vw:
-        raise RuntimeError("an operand of a convolution was modified in place before its deferred output was read")
-    return conv2d_fprop(job.x, job.w, job.bias, job.d, residual=other, stats=stats)
+    job.check()
+    x, w, bias, d, _ = job.args
+    return conv2d_fprop(x, w, bias, d, residual=other, stats=stats)
+
+
+def _bn_apply_launch(y, x, other, m, c, stats_rows, relu):
+    """y = bn(x) [+ other] [max(., 0)] with the statistics block `stats_rows` ([5][C]: mean, var+eps, sd, scale, shift)"""
+    base = stats_rows.t.data_ptr()
+    row = c * 4
+    yh = _new_shadow(y).data_ptr() if _shadow_wanted(y) else None
+    if other is None:
+        _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu), yh,
+                   current_stream_ptr())
+    else:
+        _cabi.call("ttb_bn_apply_add", _ptr(x), _ptr(other), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu),
+                   yh, current_stream_ptr())
+
+
+def bn_apply_deferred(x, m, c, stats_rows, relu):
+    """the normalise pass of a BatchNorm: deferred when a following Add / ReLU could absorb it (4-D, no fused ReLU)"""
+    y = cparray(empty_device(x.shape))
+    if relu or not _DEFER or x.ndim != 4 or c % 4 != 0 or x.size == 0:
+        _bn_apply_launch(y, x, None, m, c, stats_rows, relu)
+        return y
+    return _defer(y, "bn", (x, None, m, c, stats_rows, False), (x,), _bn_apply_launch)
+
+
+def bn_add_deferred(deferred, other):
+    """Add absorbing a deferred BatchNorm apply: the sum bn(x) + other, itself deferred (a ReLU may follow)"""
+    job = deferred._thunk.job
+    _pending[0] = None
+    job.check()
+    x, _, m, c, stats_rows, _ = job.args
+    y = cparray(empty_device(x.shape))
+    return _defer(y, "bn_add", (x, other, m, c, stats_rows, False), (x, other), _bn_apply_launch)
+
+
+def bn_relu_fused(deferred, out=None):
+    """ReLU absorbing a deferred bn / bn_add: y = max(bn(x) [+ other], 0) in one pass.  `out`: write in place into the
+    deferred array itself (ReLU(inplace=True))."""
+    job = deferred._thunk.job
+    _pending[0] = None
+    job.check()
+    x, other, m, c, stats_rows, _ = job.args
+    if out is not None:
+        out._thunk = None
+        y = out
+        y._h = None
+    else:
+        y = cparray(empty_device(x.shape))
+    _bn_apply_launch(y, x, other, m, c, stats_rows, True)
+    return y
 
 
 def conv2d_bn_eval(x, w, conv_bias, d, mean, var, eps, gamma, beta, relu):
@@ -675,9 +752,7 @@ def bn_forward_train(x, gamma, beta, running_mean, running_var, momentum, eps, r
         _cabi.call("ttb_bn_finalize", sums.data_ptr(), nchunks, count, c, eps, 0.0 if momentum is None else momentum,
                    _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var), base, base + row, base + 2 * row,
                    base + 3 * row, base + 4 * row, st)
-    y = cparray(empty_device(x.shape))
-    yh = _new_shadow(y).data_ptr() if _shadow_wanted(x) else None
-    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu), yh, st)
+    y = bn_apply_deferred(x, m, c, stats, relu)
     return y, stats, count
 
 
@@ -689,9 +764,7 @@ def bn_forward_eval(x, gamma, beta, mean, var, eps, relu=False):
     st = current_stream_ptr()
     _cabi.call("ttb_bn_prepare_eval", _ptr(mean), _ptr(var), c, eps, _ptr(gamma), _ptr(beta), base, base + row,
                base + 2 * row, base + 3 * row, base + 4 * row, st)
-    y = cparray(empty_device(x.shape))
-    yh = _new_shadow(y).data_ptr() if _shadow_wanted(x) else None
-    _cabi.call("ttb_bn_apply", _ptr(x), _ptr(y), m, c, base, base + 3 * row, base + 4 * row, int(relu), yh, st)
+    y = bn_apply_deferred(x, m, c, stats, relu)
     return y, stats, m
 
 

@@ -315,3 +315,56 @@ def test_deferred_convolution_keeps_program_order():
 
     for u, v in zip(run(True), run(False)):
         assert_close("deferred vs immediate", u, v, 1e-6)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_post_activation_block_tail_is_one_pass(mode, inplace):
+    """relu(bn(x) + identity) (the end of a ResNet-50 Bottleneck): the BatchNorm's normalise pass is deferred, the Add and the
+    ReLU join it - one ttb_bn_apply_add launch instead of bn_apply + add + relu - with the same values and gradients as the
+    separate operators; the absorbed intermediates are still readable afterwards."""
+    tt = _tt(mode)
+    from pytortto_b200 import _cabi, ops
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((8, 64, 12, 12)).astype(np.float32)
+    ident = rng.standard_normal((8, 64, 12, 12)).astype(np.float32)
+    dy = rng.standard_normal((8, 64, 12, 12)).astype(np.float32)
+
+    def run(defer):
+        ops._DEFER = defer
+        names = []
+        orig = _cabi.call
+
+        def spy(name, *a):
+            names.append(name)
+            return orig(name, *a)
+        _cabi.call = spy
+        try:
+            np.random.seed(0)
+            bn = tt.nn.BatchNorm2d(64).cuda()
+            bn.weight.data[...] = rng.standard_normal(64).astype(np.float32) * 0 + np.linspace(0.5, 1.5, 64, dtype=np.float32)
+            relu = tt.nn.ReLU(inplace=inplace)
+            xin = tt.nn.Parameter(tt.tensor(x).cuda())
+            iin = tt.nn.Parameter(tt.tensor(ident).cuda())
+            b = bn(xin)
+            z = b + iin
+            y = relu(z)
+            y.backward(tt.tensor(dy).cuda())
+            res = [y.data.get(), xin.grad.get(), iin.grad.get(), bn.weight.grad.get(), bn.bias.grad.get(), b.data.get()]
+            if not inplace:
+                res.append(z.data.get())
+        finally:
+            _cabi.call = orig
+            ops._DEFER = True
+        return res, names
+
+    (a, names_a), (b_, names_b) = run(True), run(False)
+    fwd_a = names_a[:names_a.index("ttb_bn_bwd_reduce")] if "ttb_bn_bwd_reduce" in names_a else names_a
+    fwd_a = [n for n in fwd_a if n.startswith(("ttb_bn_apply", "ttb_add", "ttb_relu_fwd"))]
+    first_backward = fwd_a.index("ttb_bn_apply_add")
+    assert fwd_a[:first_backward + 1] == ["ttb_bn_apply_add"], fwd_a  # (later entries: materialisation for the reads below)
+    assert "ttb_bn_apply_add" not in names_b
+    for name, u, v in zip(("y", "dx", "didentity", "dgamma", "dbeta", "bn(x) read afterwards", "sum read afterwards"), a, b_):
+        assert_close(f"{mode} {name}", u, v, 1e-5)
+    yo = np.maximum(a[5] + ident, 0)
+    assert_close(f"{mode} y vs max(bn + identity, 0)", a[0], yo, 1e-6)
