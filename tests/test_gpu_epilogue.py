@@ -39,6 +39,12 @@ def _gpu():
     require_gpu()
 
 
+def _skip_unless_deferral_is_on():
+    from pytortto_b200 import ops
+    if not ops._DEFER:
+        pytest.skip("deferred producers are switched off in this build (TORTTO_B200_DEFER=1 enables them)")
+
+
 def _tt(mode):
     import pytortto_b200 as tt
     tt.set_math_mode(mode)
@@ -244,6 +250,7 @@ def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
     """`conv(x) + shortcut` (the end of a residual block): the convolution's launch waits for the next operator, the Add
     runs inside its epilogue - one conv launch, no add kernel, the statistics of the SUM reach the next BatchNorm - and the
     result / gradients equal the separate ops; the un-added convolution output is still readable afterwards."""
+    _skip_unless_deferral_is_on()
     tt = _tt(mode)
     from pytortto_b200 import _cabi, ops
     rng = np.random.default_rng(5)
@@ -252,7 +259,7 @@ def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
     dy = rng.standard_normal((16, 64, 16, 16)).astype(np.float32)
 
     def run(defer):
-        ops._DEFER = defer
+        prev, ops._DEFER = ops._DEFER, defer
         names = []
         orig = _cabi.call
 
@@ -273,7 +280,7 @@ def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
             res = (z.data.get(), out.data.get(), xin.grad.get(), sin.grad.get(), conv.weight.grad.get(), c.data.get())
         finally:
             _cabi.call = orig
-            ops._DEFER = True
+            ops._DEFER = prev
         return res, names
 
     (a, names_a), (b, names_b) = run(True), run(False)
@@ -293,13 +300,14 @@ def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
 def test_deferred_convolution_keeps_program_order():
     """anything but an absorbing Add launches the deferred convolution first: ReLU / a second use / a backward right after
     the conv all see the same values as an immediate launch"""
+    _skip_unless_deferral_is_on()
     tt = _tt("tf32")
     from pytortto_b200 import ops
     rng = np.random.default_rng(6)
     x = rng.standard_normal((4, 32, 8, 8)).astype(np.float32)
 
     def run(defer):
-        ops._DEFER = defer
+        prev, ops._DEFER = ops._DEFER, defer
         try:
             np.random.seed(0)
             conv = tt.nn.Conv2d(32, 32, 3, 1, 1).cuda()
@@ -311,7 +319,7 @@ def test_deferred_convolution_keeps_program_order():
             (r.sum() + z.sum() + w.sum()).backward()
             return r.data.get(), z.data.get(), w.data.get(), xin.grad.get(), conv.weight.grad.get()
         finally:
-            ops._DEFER = True
+            ops._DEFER = prev
 
     for u, v in zip(run(True), run(False)):
         assert_close("deferred vs immediate", u, v, 1e-6)
@@ -323,6 +331,7 @@ def test_post_activation_block_tail_is_one_pass(mode, inplace):
     """relu(bn(x) + identity) (the end of a ResNet-50 Bottleneck): the BatchNorm's normalise pass is deferred, the Add and the
     ReLU join it - one ttb_bn_apply_add launch instead of bn_apply + add + relu - with the same values and gradients as the
     separate operators; the absorbed intermediates are still readable afterwards."""
+    _skip_unless_deferral_is_on()
     tt = _tt(mode)
     from pytortto_b200 import _cabi, ops
     rng = np.random.default_rng(8)
@@ -331,7 +340,7 @@ def test_post_activation_block_tail_is_one_pass(mode, inplace):
     dy = rng.standard_normal((8, 64, 12, 12)).astype(np.float32)
 
     def run(defer):
-        ops._DEFER = defer
+        prev, ops._DEFER = ops._DEFER, defer
         names = []
         orig = _cabi.call
 
@@ -355,7 +364,7 @@ def test_post_activation_block_tail_is_one_pass(mode, inplace):
                 res.append(z.data.get())
         finally:
             _cabi.call = orig
-            ops._DEFER = True
+            ops._DEFER = prev
         return res, names
 
     (a, names_a), (b_, names_b) = run(True), run(False)
