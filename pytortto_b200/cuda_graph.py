@@ -17,6 +17,7 @@ hyper-parameters baked at capture time (call `recapture()` after changing the le
 """
 import torch
 
+from . import ops as _ops
 from .tensor import Tensor
 
 
@@ -56,6 +57,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             out = self.fn(*self.static_inputs)
+            _ops.resolve_pending(None, ())  # a producer whose launch is still deferred (ops._defer) belongs to the graph
         self.outputs, self._multi = _flatten_outputs(out)
         for bn in self._bn_modules():  # the recorded execution did not run: take back its host-side step count
             if getattr(bn, "_nbt", None) is not None:

@@ -414,6 +414,11 @@ def begin_backward_sweep():
 
 def end_backward_sweep():
     _dgrad_pack["in_sweep"] = False
+    _dgrad_pack["registry"].clear()  # (weights registered by a forward whose dgrad never ran must not be kept alive)
+    packed = _dgrad_pack["packed"]
+    if len(packed) > 64:  # drop the packed copies of weights that no longer exist (models rebuilt in one process)
+        for ptr in [p_ for p_, e in packed.items() if e[2]() is None]:
+            del packed[ptr]
     join_wgrad()  # weight gradients computed on the second stream are complete for whoever runs next
 
 
@@ -440,8 +445,8 @@ def _flush_dgrad_pack():
     for i, (w, d) in enumerate(items):
         ptr = w.t.data_ptr()
         ent = _dgrad_pack["packed"].get(ptr)
-        if ent is None or ent[0].numel() != w.t.numel():
-            ent = [torch.empty(w.t.numel(), dtype=torch.float32, device=w.t.device), -1]
+        if ent is None or ent[0].numel() != w.t.numel() or ent[2]() is not w:
+            ent = [torch.empty(w.t.numel(), dtype=torch.float32, device=w.t.device), -1, weakref.ref(w)]
             _dgrad_pack["packed"][ptr] = ent
         ent[1] = _dgrad_pack["sweep"]
         descs[i] = ctypes.pointer(d)
