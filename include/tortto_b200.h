@@ -273,7 +273,8 @@ int ttb_comm_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);
 int ttb_comm_open(const unsigned char* handle, void** peer_ptr);
 int ttb_comm_close(void* peer_ptr);
 int ttb_comm_free(void* dev_ptr);
-/* bytes of one slot holding up to max_values doubles (header + data) */
+/* bytes of one slot holding up to max_values <= 8192 doubles: header + two data buffers used alternately (parity of the
+ * slot's exchange count), so a rank that runs ahead never overwrites words a slower peer is still reading; 0 if too large */
 size_t ttb_comm_slot_bytes(int max_values);
 /* out[i] = sum over ranks (rank order) of sum over chunks of that rank's partials[chunk][i], exchanged through the
  * slot at `slot_offset` of every rank's buffer.  peers_dev: DEVICE array of `world` mapped buffer bases (own buffer at

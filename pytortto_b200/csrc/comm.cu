@@ -9,8 +9,11 @@
 // own slot as self-validating 8-byte words {sequence | 32 data bits}, poll the same words of every peer over NVLink
 // (peer loads bypass L1) and add them IN RANK ORDER (bit-identical result on every rank) into a local [n] buffer that
 // the ordinary bn finalize kernels consume.
-// Why reuse of a slot is safe: a rank reaches the same call site again only after every peer has passed all the
-// call sites in between, each of which needed this rank's later exchanges, which are stream-ordered after this one.
+// Why reuse of a slot is safe: the data area is DOUBLE-BUFFERED by the parity of the exchange's sequence number.  Rank A
+// can start exchange s+1 (other buffer) while a slow peer B is still reading A's words of exchange s, but A cannot finish
+// s+1 - and so cannot reach s+2, which overwrites the buffer of s - before B has published its s+1 value, which B does
+// only after its own exchange s (all reads of A's buffer s) has completed.  This holds even when one call site is the only
+// synchronisation point of the program (one BatchNorm layer, forward only).
 #include <string.h>
 
 #include "bn_finalize.cuh"
@@ -24,6 +27,9 @@ struct SlotHeader {
   unsigned int pad[2];
 };
 constexpr size_t kSlotHeaderBytes = 16;
+constexpr int kCommMaxValues = 8192;                            // values per exchange (2C doubles, C <= 4096)
+constexpr size_t kParityStride = (size_t)kCommMaxValues * 16;   // bytes between the two data buffers of a slot
+__device__ __forceinline__ size_t slot_data_offset(unsigned int seq) { return kSlotHeaderBytes + (seq & 1u) * kParityStride; }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -76,7 +82,7 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
     mine_sm[threadIdx.x] = mine;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
     const unsigned long long tag = (unsigned long long)seq << 32;
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + kSlotHeaderBytes) + 2 * (size_t)i;
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + slot_data_offset(seq)) + 2 * (size_t)i;
     st_volatile_u64(w, tag | (bits & 0xffffffffull));
     st_volatile_u64(w + 1, tag | (bits >> 32));
   }
@@ -91,7 +97,7 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
       v = mine_sm[threadIdx.x];
     } else {
       const unsigned long long* pw =
-          reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes) + 2 * (size_t)i;
+          reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + slot_data_offset(seq)) + 2 * (size_t)i;
       unsigned long long a, b, spins = 0;
       for (;;) {
         a = ld_volatile_u64(pw);
@@ -166,7 +172,7 @@ comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int
     const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
     const unsigned long long tag = (unsigned long long)seq << 32;
     const size_t v = threadIdx.y == 0 ? (size_t)i : (size_t)c + i;
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + kSlotHeaderBytes) + 2 * v;
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + slot_data_offset(seq)) + 2 * v;
     st_volatile_u64(w, tag | (bits & 0xffffffffull));
     st_volatile_u64(w + 1, tag | (bits >> 32));
   }
@@ -179,7 +185,7 @@ comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int
       v0 = mine_sm[0][threadIdx.x];
       v1 = mine_sm[1][threadIdx.x];
     } else {
-      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + kSlotHeaderBytes);
+      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + slot_data_offset(seq));
       const unsigned long long* p0 = base + 2 * (size_t)i;
       const unsigned long long* p1 = base + 2 * ((size_t)c + i);
       unsigned long long w0, w1, w2, w3, spins = 0;
@@ -279,11 +285,14 @@ int ttb_comm_free(void* dev_ptr) {
   return 0;
 }
 
-size_t ttb_comm_slot_bytes(int max_values) { return kSlotHeaderBytes + (size_t)max_values * 16; }
+size_t ttb_comm_slot_bytes(int max_values) {  // header + two data buffers (exchange parity); max_values <= 8192
+  if (max_values < 0 || max_values > kCommMaxValues) return 0;
+  return kSlotHeaderBytes + kParityStride + (size_t)max_values * 16;
+}
 
 int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,
                        size_t slot_offset, double* out, void* stream) {
-  TTB_REQUIRE(partials && peers_dev && out && n > 0 && num_chunks > 0, "comm_allreduce: bad arguments");
+  TTB_REQUIRE(partials && peers_dev && out && n > 0 && n <= kCommMaxValues && num_chunks > 0, "comm_allreduce: bad arguments");
   TTB_REQUIRE(world > 0 && world <= kMaxWorld && rank >= 0 && rank < world, "comm_allreduce: world size %d not in 1..%d", world,
               kMaxWorld);
   // about a minute of polling before a missing peer is declared lost
@@ -293,7 +302,7 @@ int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* cons
 }
 
 static int comm_check(const void* partials, const void* peers_dev, int c, int num_chunks, int world, int rank, const char* what) {
-  TTB_REQUIRE(partials && peers_dev && c > 0 && num_chunks > 0, "%s: bad arguments", what);
+  TTB_REQUIRE(partials && peers_dev && c > 0 && 2 * c <= kCommMaxValues && num_chunks > 0, "%s: bad arguments", what);
   TTB_REQUIRE(world > 0 && world <= kMaxWorld && rank >= 0 && rank < world, "%s: world size %d not in 1..%d", what, world, kMaxWorld);
   return 0;
 }

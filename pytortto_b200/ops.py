@@ -244,7 +244,7 @@ def conv2d_fprop(x, w, bias, d, scale=None, residual=None, relu=False, stats=Fal
 # decision except direct array accesses, which materialise.  Gradients are unaffected: none of the absorbed intermediate
 # values is saved for backward (Convolution saves its input and weight, BatchNorm its input, Add nothing, ReLU its output).
 _pending = [None]
-_DEFER = os.environ.get("TORTTO_B200_DEFER", "0") != "0"  # (off until validated on hardware; the GPU tests switch it on)
+_DEFER = os.environ.get("TORTTO_B200_DEFER", "1") != "0"  # (TORTTO_B200_DEFER=0: every producer launches immediately)
 
 
 class _Job:

@@ -290,8 +290,13 @@ def test_residual_add_is_absorbed_by_the_deferred_convolution(mode):
     assert "ttb_bn_stats" not in names_a  # the epilogue emitted the statistics of the sum
     assert any(n.startswith("ttb_add") for n in names_b[:names_b.index("ttb_bn_finalize")])
     tol = TOL[mode]
+    # z, bn(z) and the gradient of the shortcut never pass through a rounded operand: 1e-5.  dx / dw do: the statistics the
+    # epilogue emits differ from the separate pass's in the last bits (summation order), so the BatchNorm gradient that the
+    # dgrad / wgrad kernels read as a bf16 (tf32) operand differs by an ulp here and there and ROUNDS the other way in a few
+    # elements (2^-9 relative each in bf16; measured on B200: dx 3.7e-5 in bf16 mode, < 1e-5 in tf32 mode)
+    grad_tol = {"tf32": {"dx": 1e-5, "dw": 1e-4}, "bf16": {"dx": 2e-4, "dw": 5e-4}}[mode]
     for name, u, v in zip(("z", "bn(z)", "dx", "dshortcut", "dw"), a[:5], b[:5]):
-        assert_close(f"{mode} {name}", u, v, 1e-5 if name != "dw" else 1e-4)
+        assert_close(f"{mode} {name}", u, v, grad_tol.get(name, 1e-5))
     # the convolution alone (materialised on demand after the fused launch) = z - shortcut
     assert_close(f"{mode} conv output read after the fusion", a[5], b[5], 1e-6)
     assert_close(f"{mode} conv vs z - s", a[5], a[0] - s, 10 * tol)
