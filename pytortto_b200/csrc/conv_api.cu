@@ -177,6 +177,10 @@ struct TensorPlan {
   bool bf16;        // operands are staged as bf16
   bool stage_ops;   // operands need a staged copy (conversion and / or channel padding)
   bool packed;      // tap-packed staging: `p` is the 1 x 1 convolution over [N][P][Q][round_up(R*S*C)] (fprop / wgrad)
+  bool pack_rows;   // ... or, for tall filters (the 7 x 7 / stride-2 ImageNet stem), only the S*C taps of a filter ROW are
+                    // packed: `p` is the R x 1 convolution (stride / padding / dilation in H kept) over [N][H][Q][round_up(S*C)]
+                    // and `pk` the problem handed to the packing kernel (rows = (n, h, q)); weights [K][R][S*C] -> [K*R][kp]
+  ttb_conv_desc pk;
   int groups;       // > 1: `p` is ONE GROUP (c = C/groups, k = K/groups) of a grouped convolution; the groups run either in
                     // place on channel slices of the caller's tensors (aligned channel counts) or tap-packed (<= 4 channels
                     // per group)
@@ -193,7 +197,7 @@ static bool plan_grouped(const ttb_conv_desc* d, int pass, TensorPlan* t) {
   const int G = d->groups, cg = d->c / G, kg = d->k / G;
   ttb_conv_desc q = *d;
   q.groups = 1; q.c = cg; q.k = kg;
-  t->bf16 = false; t->groups = G; t->packed = false; t->stage_ops = false;
+  t->bf16 = false; t->groups = G; t->packed = false; t->pack_rows = false; t->stage_ops = false;
   t->a_bytes = t->b_bytes = t->c_bytes = 0;
   const size_t yrows = (size_t)d->n * d->p * d->q;
   if (pass != 1 && cg <= 4 && kg % 8 == 0 && d->r * d->s * cg <= kPackMaxCols - 64 && tuning_knob("TTB_TAP_PACK", 1)) {
@@ -225,10 +229,34 @@ static bool plan_tensor(const ttb_conv_desc* d, int pass, TensorPlan* t) {
   t->groups = 1;
   t->bf16 = d->math_mode == TTB_MATH_BF16;
   t->packed = false;
+  t->pack_rows = false;
   const int blk = igemm_channel_block(d);
   if (pass != 1 && d->c <= 4 && d->r * d->s > 1 && d->r * d->s * d->c <= kPackMaxCols - 64 && tuning_knob("TTB_TAP_PACK", 1)) {
-    // tap-packed: the layer as a 1 x 1 convolution over the staged [N][P][Q][kp] tensor
     const int kp = (d->r * d->s * d->c + blk - 1) / blk * blk;
+    // Row-packed when that stages fewer bytes: the staged tensor of the full packing is P*Q*kp per image - for the 7x7x3
+    // stride-2 stem 160 columns per OUTPUT pixel, 2 GB at 256 x 224 x 224, and the layer ran at 36 TFLOP/s bound by writing
+    // and re-reading it - against H*Q*kpr with kpr = round_up(S*C) = 32: 2.5x fewer bytes, R K-blocks per tile instead of 5.
+    const int kpr = (d->s * d->c + blk - 1) / blk * blk;
+    if (d->r > 1 && (int64_t)d->h * kpr * 4 <= (int64_t)d->p * kp * 3 && tuning_knob("TTB_ROW_PACK", 1)) {
+      ttb_conv_desc q = *d;
+      q.c = kpr; q.w = d->q; q.s = 1;
+      q.stride_w = q.dil_w = 1;
+      q.pad_w = 0;
+      if (igemm_supported(&q, pass)) {
+        t->p = q;
+        t->pk = *d;
+        t->pk.r = 1; t->pk.stride_h = t->pk.dil_h = 1; t->pk.pad_h = 0; t->pk.p = d->h;
+        t->packed = t->pack_rows = t->stage_ops = true;
+        const size_t es = t->bf16 ? 2 : 4;
+        const size_t xrows = (size_t)d->n * d->h * d->q, yrows = (size_t)d->n * d->p * d->q;
+        t->a_bytes = align256(xrows * kpr * es);
+        t->b_bytes = pass == 0 ? align256((size_t)d->k * d->r * kpr * es) : (t->bf16 ? align256(yrows * d->k * es) : 0);
+        t->c_bytes = pass == 2 ? align256((size_t)d->k * d->r * kpr * sizeof(float)) : 0;
+        t->inner = align256(igemm_workspace_size(&t->p, pass));
+        return true;
+      }
+    }
+    // tap-packed: the layer as a 1 x 1 convolution over the staged [N][P][Q][kp] tensor
     ttb_conv_desc q = *d;
     q.c = kp; q.h = d->p; q.w = d->q; q.r = q.s = 1;
     q.stride_h = q.stride_w = q.dil_h = q.dil_w = 1;
@@ -341,9 +369,11 @@ static int fprop_tensor(const ttb_conv_desc* d, const TensorPlan& t, const float
                                (size_t)t.p.k * t.p.c * 4, ep, y, d->k, st);
   }
   if (!t.stage_ops && flat_fprop_supported(&t.p)) return flat_fprop(&t.p, x, w, ep, y, st);
-  if (t.packed) {  // w [K][R*S*C] -> [K][kp] (zero tail), x -> xcol
-    if (pack_taps(d, x, ws, t.p.c, t.bf16, st)) return 1;
-    if (stage(w, ws + t.a_bytes, d->k, d->r * d->s * d->c, t.p.c, t.bf16, st)) return 1;
+  if (t.packed) {  // w [K][R*S*C] -> [K][kp] (zero tail; row-packed: [K*R][S*C] -> [K*R][kp]), x -> xcol
+    if (pack_taps(t.pack_rows ? &t.pk : d, x, ws, t.p.c, t.bf16, st)) return 1;
+    if (t.pack_rows ? stage(w, ws + t.a_bytes, (int64_t)d->k * d->r, d->s * d->c, t.p.c, t.bf16, st)
+                    : stage(w, ws + t.a_bytes, d->k, d->r * d->s * d->c, t.p.c, t.bf16, st))
+      return 1;
     xa = ws;
     wa = ws + t.a_bytes;
   } else if (t.stage_ops) {
@@ -472,7 +502,8 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
     return check_launch("unpad_channels");
   }
   if (t.stage_ops) {
-    if (t.packed ? pack_taps(d, x, ws, t.p.c, t.bf16, st) : stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st))
+    if (t.packed ? pack_taps(t.pack_rows ? &t.pk : d, x, ws, t.p.c, t.bf16, st)
+                 : stage(x, ws, (int64_t)d->n * d->h * d->w, d->c, t.p.c, t.bf16, st))
       return 1;
     xa = ws;
     if (t.bf16) {
@@ -483,8 +514,8 @@ int ttb_conv2d_wgrad(const ttb_conv_desc* d, const float* x, const float* dy, fl
   }
   if (int rc = igemm_wgrad(&t.p, xa, dya, dwa, ws ? ws + t.a_bytes + t.b_bytes + t.c_bytes : nullptr, t.inner, st)) return rc;
   if (t.c_bytes) {  // crop the padded reduction columns: [K][kp] -> [K][R*S*C] (tap-packed) / [K*R*S][cp] -> [K*R*S][C]
-    const int64_t wrows = t.packed ? d->k : (int64_t)d->k * d->r * d->s;
-    const int wc = t.packed ? d->r * d->s * d->c : d->c;
+    const int64_t wrows = t.pack_rows ? (int64_t)d->k * d->r : (t.packed ? d->k : (int64_t)d->k * d->r * d->s);
+    const int wc = t.pack_rows ? d->s * d->c : (t.packed ? d->r * d->s * d->c : d->c);
     launch_k(unpad_channels_kernel, elementwise_grid(wrows * wc, 256), 256, 0, st, dwa, dw, wrows, wc, t.p.c);
     return check_launch("unpad_channels");
   }

@@ -785,13 +785,7 @@ bool igemm_supported(const ttb_conv_desc* d, int pass) {
 }
 
 // Widest N tile that still gives every SM a CTA; narrow channel counts get a matching narrow tile.
-static int pick_bn(int64_t m_total, int n_total) {
-  if (const int v = tuning_knob("TTB_FORCE_BN", 0)) {  // experiment switch (tuning build only)
-    if (v == 256 && n_total > 128) return 256;
-    if (v >= 128 && n_total > 64) return 128;
-    if (v >= 64 && n_total > 32) return 64;
-    if (v == 32) return 32;
-  }
+static int pick_bn_wide(int64_t m_total, int n_total) {
   const int64_t mtiles = ceil_div(m_total, kTileM);
   const int sms = sm_count();
   // 256-wide tiles are the only tensor-bound TF32 configuration (see launch_persist_bn): take them as soon as they
@@ -800,6 +794,29 @@ static int pick_bn(int64_t m_total, int n_total) {
   if (n_total > 64 && (mtiles * ceil_div(n_total, 128) >= sms || n_total > 128)) return 128;
   if (n_total > 32) return 64;
   return 32;
+}
+
+// `nkb`: K-blocks (stage fills of one tap) a tile's main loop runs = taps x reduction channels / 32 (64 in bf16).  A SHALLOW
+// reduction - the 1 x 1 convolutions of a bottleneck network, the 1 x 1 stride-2 shortcuts, the few-tap classes of a
+// strided dgrad - spends 4 nkb MMAs (<= 2-4 k cycles) per tile against 2.4 / 4.5 / 9 k cycles of epilogue for 64 / 128 / 256
+// columns on the CTA's four epilogue warps: the kernel is bound by the epilogue, not by the tensor pipe.  Narrow tiles
+// run TWO CTAs per SM, i.e. eight epilogue warps storing, and halve the epilogue of a tile.  Measured on B200
+// (profiles/r2_force_bn_*.txt, per-layer device time of a step): ResNet-50 1x1 layers with <= 8 K-blocks 1.3-1.6x faster on
+// 64-wide tiles (64->256 at 56x56: 410 -> 289 us, the 256->64 dgrad with its pending gradient: 601 -> 403 us), 16-32
+// K-blocks 1.1-1.4x on 128-wide instead of 256-wide tiles; the 3 x 3 layers (>= 18 K-blocks) keep the wide tiles.
+static int pick_bn(int64_t m_total, int n_total, int nkb) {
+  if (const int v = tuning_knob("TTB_FORCE_BN", 0)) {  // experiment switch (tuning build only)
+    if (v == 256 && n_total > 128) return 256;
+    if (v >= 128 && n_total > 64) return 128;
+    if (v >= 64 && n_total > 32) return 64;
+    if (v == 32) return 32;
+  }
+  int bn = pick_bn_wide(m_total, n_total);
+  if (tuning_knob("TTB_SHALLOW_BN", 1)) {
+    if (nkb <= 8 && bn > 64) bn = 64;
+    else if (nkb <= 32 && bn > 128) bn = 128;
+  }
+  return bn;
 }
 
 constexpr size_t persist_smem_bytes(int bn, int nstages, int wt) {
@@ -884,7 +901,7 @@ static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, int wt
 
 // rows of the [chunks][2][K] statistics partial buffer an fprop launch of this problem writes (Epilogue::stats)
 int igemm_fprop_stats_chunks(const ttb_conv_desc* d) {
-  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k);
+  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k, d->r * d->s * (d->c / igemm_channel_block(d)));
   // 256-wide tiles (the deep layers: about one tile per CTA, so the epilogue is not hidden behind a next tile's main loop)
   // measured +5.8 us with statistics against a ~5 us statistics pass over their small outputs: no statistics there -
   // unless the output is large (the 1 x 1 expansions of ResNet-50: 100-800 MB, several tiles per CTA), where the separate
@@ -1006,7 +1023,7 @@ int igemm_fprop(const ttb_conv_desc* d, const void* x, const void* w, const Epil
                 size_t /*ws_bytes*/, cudaStream_t st) {
   if (load_driver_fns()) return 1;
   static thread_local FwdParamsMulti PM1;
-  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k);
+  const int bn = pick_bn((int64_t)d->n * d->p * d->q, d->k, d->r * d->s * (d->c / igemm_channel_block(d)));
   const int wt = pick_wt(d->s, d->stride_w, d->dil_w, bn, d->q);
   if (fprop_params(PM1.p[0], d, x, w, ep, y, bn, wt, 0, 0)) return 1;
   return launch_persist_bn(PM1, 1, bn, wt, d->math_mode == TTB_MATH_BF16, st);
@@ -1019,7 +1036,8 @@ int igemm_fprop_grouped(const ttb_conv_desc* dg, int groups, const void* x, size
                         size_t w_goff_bytes, const Epilogue& ep, float* y, int y_ctot, cudaStream_t st) {
   if (load_driver_fns()) return 1;
   static thread_local FwdParamsMulti PM;
-  const int bn = pick_bn((int64_t)dg->n * dg->p * dg->q * (groups < kMaxMulti ? groups : kMaxMulti), dg->k);
+  const int bn = pick_bn((int64_t)dg->n * dg->p * dg->q * (groups < kMaxMulti ? groups : kMaxMulti), dg->k,
+                         dg->r * dg->s * (dg->c / igemm_channel_block(dg)));
   const int wt = pick_wt(dg->s, dg->stride_w, dg->dil_w, bn, dg->q);
   for (int g0 = 0; g0 < groups; g0 += kMaxMulti) {
     const int cnt = groups - g0 < kMaxMulti ? groups - g0 : kMaxMulti;
@@ -1069,7 +1087,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
   struct Cls { int a, b, nr, ns; int rr[kMaxTaps], ro[kMaxTaps], ss[kMaxTaps], so[kMaxTaps]; };
   static thread_local Cls cls;
   static thread_local FwdParamsMulti PM;
-  int n_multi = 0;
+  int n_multi = 0, nkb_max = 0;
   int64_t m_all = 0;
   const bool multi = d->stride_h * d->stride_w > 1 && d->stride_h * d->stride_w <= kMaxMulti;
   for (int pass = 0; pass < 2; ++pass) {
@@ -1100,7 +1118,9 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         for (int i = 0; i < cls.ns; ++i) lo_w = cls.so[i] < lo_w ? cls.so[i] : lo_w;
         // (a stride-1 dgrad is one class: its N tile is known here, and with it whether the three taps of a filter row
         // share one strip of dY - see pick_wt / the kernel's WT)
-        const int bn1 = multi ? 0 : pick_bn((int64_t)d->n * ha * wb, d->c);
+        const int nkb = cls.nr * cls.ns * (d->k / el.per_row);
+        if (nkb > nkb_max) nkb_max = nkb;
+        const int bn1 = multi ? 0 : pick_bn((int64_t)d->n * ha * wb, d->c, nkb);
         const int wtaps = multi ? 1 : pick_wt(cls.ns, d->stride_w, d->dil_w, bn1, wb);
         const int up_h = ha - d->p + lo_h, up_w = wb - d->q + lo_w + (wtaps - 1);
         TTB_REQUIRE(in_corner_range(lo_h) && in_corner_range(lo_w) && in_corner_range(up_h) && in_corner_range(up_w),
@@ -1145,7 +1165,7 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         if (launch_persist_bn(PM1, 1, bn1, wtaps, el.bf16, st)) return 1;
       }
     if (pass == 1 && n_multi > 0) {
-      const int bn = pick_bn(m_all, d->c);
+      const int bn = pick_bn(m_all, d->c, nkb_max);  // (the deepest class decides: the others only get shorter)
       for (int i = 0; i < n_multi; ++i)
         if (make_tiled_2d(&PM.p[i].tmB, wt, el, (uint64_t)d->c, (uint64_t)T * d->k, (uint32_t)bn)) return 1;
       if (launch_persist_bn(PM, n_multi, bn, 1, el.bf16, st)) return 1;
