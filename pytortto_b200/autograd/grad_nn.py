@@ -102,8 +102,9 @@ class Convolution(Function):
         xd0, xd1 = ctx.saved_tensors
         d = ctx.params['desc']
         grad0, grad1, grad2 = None, None, None
-        if ctx.needs_input_grad[2]:
-            grad2 = ops.bias_grad(gd0, out=grad_slot(ctx, 2))
+        if ctx.needs_input_grad[2]:  # (on the wgrad stream when it feeds a leaf: see the weight gradient below)
+            grad2 = ops.bias_grad(gd0, out=grad_slot(ctx, 2),
+                                  overlap=ctx.next_functions[2][0].__class__ is AccumulateGrad)
         # wgrad forks to a second stream (joined at the end of backward), dgrad stays on the critical path.  Measured on
         # B200 (preact_resnet18, batch 256, graph replay): 3.81 ms/step in this order, 3.89 with dgrad queued first,
         # 3.92 without the fork - the two tensor-bound kernels cannot share an SM (shared memory) and an HBM-bound

@@ -178,6 +178,47 @@ maxpool_bwd4_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t
     const int n = (int)(t2 / d.h);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned done = 0;  // bit j: channel j already has its (last-writer) value
+    if constexpr (KH > 0) {
+      // Compile-time geometry: an input element is covered by at most NR x NS windows (2 x 2 for 3x3 / stride 2).  Their
+      // index words and gradients are ALL loaded first (independent loads; dy is re-read from L1 / L2, a quarter of dx's
+      // size) and the last-writer selection runs on registers afterwards: the walk that loaded an index, tested it and
+      // only then loaded the gradient was a chain of up to 8 dependent loads per thread (0.95 ms on the ResNet-50 stem pool
+      // at batch 256, 0.18 of the HBM roofline).
+      constexpr int NR = (KH + SH - 1) / SH, NS = (KW + SW - 1) / SW;
+      const int r0 = (h + d.pad_h) % SH, s0 = (w + d.pad_w) % SW;
+      uint32_t ib[NR * NS], code[NR * NS];
+      float4 g[NR * NS];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int r = r0 + i * SH, hp = h + d.pad_h - r;
+        const int pp = hp / SH;
+        const bool okr = r < KH && hp >= 0 && pp < d.p;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const int sx = s0 + j * SW, wq = w + d.pad_w - sx;
+          const int qq = wq / SW;
+          const bool ok = okr && sx < KW && wq >= 0 && qq < d.q;
+          const int64_t o = ok ? (((int64_t)n * d.p + pp) * d.q + qq) * d.c + c0 : 0;
+          ib[i * NS + j] = ok ? *reinterpret_cast<const uint32_t*>(idx + o) : 0xFFFFFFFFu;  // (0xFF is never a tap code)
+          g[i * NS + j] = ok ? ld_f4_stream(dy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          code[i * NS + j] = (uint32_t)(r * KW + sx);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < NR * NS; ++e) {  // r ascending, then s ascending: the first hit is the last writer in raster order
+        unsigned hit = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hit |= (((ib[e] >> (8 * j)) & 0xFFu) == code[e]) ? (1u << j) : 0u;
+        if (!ACCUM) hit &= ~done;
+        const float gv[4] = {g[e].x, g[e].y, g[e].z, g[e].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (hit & (1u << j)) acc[j] = ACCUM ? acc[j] + gv[j] : gv[j];
+        done |= hit;
+      }
+      st_f4(dx + 4 * t, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      continue;
+    }
     for (int r = 0; r < d.kh && done != 0xFu; ++r) {
       int hp = h + d.pad_h - r * d.dil_h;
       if (hp < 0) break;

@@ -573,11 +573,20 @@ def conv2d_wgrad(x, dy, d, overlap=False, out=None):
     return dw
 
 
-def bias_grad(dy, out=None):
-    """dy (N,K,P,Q) -> (K,)   (gd0.sum((0,2,3)), reference grad_nn.py:727-728)"""
+def bias_grad(dy, out=None, overlap=False):
+    """dy (N,K,P,Q) -> (K,)   (gd0.sum((0,2,3)), reference grad_nn.py:727-728).  `overlap`: the result goes straight to a
+    leaf, so - like the weight gradient - this full HBM read of dy leaves the critical path and runs on the wgrad stream
+    (UNet at 8 x 512 x 512: 23 biased convolutions, 0.8 ms of bias gradients per step)."""
     n, k, p, q = dy.shape
     db = out if out is not None else new_f32((k,))
-    _cabi.call("ttb_bias_grad", _ptr(dy), _ptr(db), n * p * q, k, current_stream_ptr())
+    st = current_stream_ptr()
+    if overlap and _overlap["enabled"] and db.size:
+        side = _side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        st = side.cuda_stream
+        _overlap["keep"].append((dy, db))
+        _overlap["dirty"] = True
+    _cabi.call("ttb_bias_grad", _ptr(dy), _ptr(db), n * p * q, k, st)
     return db
 
 

@@ -560,6 +560,8 @@ STEM_CASES = [  # (N, Cin, H, W, Cout, kh, kw, stride, pad)
     (2, 3, 33, 29, 32, 3, 3, 1, 1),      # UNet's first layer, ragged
     (3, 1, 28, 28, 16, 5, 5, 1, 2),
     (2, 4, 17, 17, 24, 3, 2, 2, 1),
+    (2, 4, 30, 26, 16, 7, 5, 2, 3),      # tall filter, stride 2: ROW-packed staging (7 K-blocks of round_up(5*4) columns)
+    (3, 3, 21, 40, 32, 7, 7, 2, 3),      # the stem again on a ragged, non-square image (odd H: the last filter rows hang over)
 ]
 
 
