@@ -149,6 +149,26 @@ int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const voi
                           float* dx, void* stream);
 int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,
                           size_t workspace_bytes, void* stream);
+
+/* dgrad fused with the statistics pass of the BatchNorm backward that consumes its output.  In a network
+ * conv(relu(bn(x))) the gradient dgrad produces is what BatchNorm.backward (reference autograd/grad_nn.py:967-989) reduces
+ * next: sum(g) and sum(g * (x - mean)) per channel, g = dx masked by the ReLU (recomputed as fmaf(x - mean, rscale, rshift)
+ * > 0, the expression forward evaluated).  The dgrad epilogue emits those sums of what it stores, so ttb_bn_bwd_reduce (two
+ * full reads) is not run; ttb_bn_bwd_finalize / ttb_comm_bn_bwd_finalize take `partials` as they take ttb_bn_bwd_reduce's.
+ *   ttb_conv2d_dgrad_bn_stats_chunks   rows of `partials` ([chunks][2][C] doubles) this problem writes; 0 = not available
+ *                                      (strided / grouped / staged problems, small outputs on 256-wide tiles)
+ *   ttb_conv2d_dgrad_bn                dy, w_packed: fp32 ([C][R][S][K] from ttb_conv2d_dgrad_pack_weights) for TF32 math,
+ *                                      bf16 (ttb_conv2d_pack_weights_bf16) for BF16 math; accum as in ttb_conv2d_dgrad_prepacked */
+typedef struct ttb_dgrad_bn_stats {
+  const float* x;       /* the BatchNorm's input [N,H,W,C]: same shape and layout as dx                              */
+  const float* mean;    /* [C] batch mean saved by forward                                                           */
+  const float* rscale;  /* [C] or NULL: scale / shift forward normalised with, when a ReLU follows the BatchNorm     */
+  const float* rshift;
+  double* partials;     /* [ttb_conv2d_dgrad_bn_stats_chunks(d)][2][C]                                               */
+} ttb_dgrad_bn_stats;
+int ttb_conv2d_dgrad_bn_stats_chunks(const ttb_conv_desc* d);
+int ttb_conv2d_dgrad_bn(const ttb_conv_desc* d, const void* dy, const void* w_packed, const float* accum, float* dx,
+                        const ttb_dgrad_bn_stats* bn, void* stream);
 int ttb_conv2d_pack_weights_bf16(int count, const ttb_conv_desc* const* descs, const float* const* w, void* const* w_bf16,
                                  void* const* wt_bf16, void* stream);
 int ttb_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -33,6 +33,11 @@ class ConvEpilogue(ctypes.Structure):
     _fields_ = [("scale", c_void_p), ("bias", c_void_p), ("residual", c_void_p), ("relu", c_int32), ("stats", c_void_p)]
 
 
+class DgradBnStats(ctypes.Structure):
+    """struct ttb_dgrad_bn_stats"""
+    _fields_ = [("x", c_void_p), ("mean", c_void_p), ("rscale", c_void_p), ("rshift", c_void_p), ("partials", c_void_p)]
+
+
 _F = c_void_p  # device pointers travel as plain integers
 _PROTOS = {
     "ttb_last_error": (c_char_p, []),
@@ -60,6 +65,8 @@ _PROTOS = {
     "ttb_conv2d_fprop_bf16": (c_int, [POINTER(ConvDesc), _F, _F, POINTER(ConvEpilogue), _F, c_void_p]),
     "ttb_conv2d_dgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_void_p]),
     "ttb_conv2d_wgrad_bf16": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, c_size_t, c_void_p]),
+    "ttb_conv2d_dgrad_bn_stats_chunks": (c_int, [POINTER(ConvDesc)]),
+    "ttb_conv2d_dgrad_bn": (c_int, [POINTER(ConvDesc), _F, _F, _F, _F, POINTER(DgradBnStats), c_void_p]),
     "ttb_conv2d_pack_weights_bf16": (c_int, [c_int, POINTER(POINTER(ConvDesc)), POINTER(c_void_p), POINTER(c_void_p),
                                              POINTER(c_void_p), c_void_p]),
     "ttb_to_bf16": (c_int, [_F, _F, c_int64, c_void_p]),

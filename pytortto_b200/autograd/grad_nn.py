@@ -120,7 +120,13 @@ class Convolution(Function):
         # the engine hands it over (Tensor._sweep) and the dgrad epilogue adds it instead of a separate add kernel
         accum = ctx.params.pop('_accum0', None)
         if ctx.needs_input_grad[0]:
-            grad0 = ops.conv2d_dgrad(gd0, xd1, d, accum=accum)
+            # the input came out of a BatchNorm(+ReLU) node: its backward runs next on this gradient and can take the dgrad
+            # launch over, with the epilogue that emits its two reductions (ops.conv2d_dgrad_for_batchnorm)
+            fn0 = ctx.next_functions[0][0]
+            if fn0 is not None and getattr(getattr(fn0, '_forward_cls', None), '_absorbs_dgrad', False):
+                grad0 = ops.conv2d_dgrad_for_batchnorm(gd0, xd1, d, accum=accum)
+            else:
+                grad0 = ops.conv2d_dgrad(gd0, xd1, d, accum=accum)
         return grad0, grad1, grad2
 
 
@@ -308,6 +314,7 @@ class _BatchNormBase(Function):
 
 # its backward can fold the pending gradient of input 0 into dx (TORTTO_B200_FOLD_ACCUM=0: separate add kernel)
 _BatchNormBase._accumulates_input0 = os.environ.get("TORTTO_B200_FOLD_ACCUM", "1") != "0"
+_BatchNormBase._absorbs_dgrad = os.environ.get("TORTTO_B200_DGRAD_BN", "1") != "0"  # (see Convolution.backward)
 
 
 class BatchNormRelu(_BatchNormBase):

@@ -85,12 +85,20 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 //   v += accum[same element]       (accum may be null)      - a residual / a gradient already pending for the same tensor
 //   v = max(v, 0)                  (relu != 0)
 //   stats (may be null): per-chunk partial sums [chunks][2][K] (double) of v and v*v for the BatchNorm that follows
+//   bn_x != null: `stats` receives instead the two sums a BatchNorm BACKWARD needs over the stored values v (a dgrad whose
+//   output is the gradient that BatchNorm(+ReLU) node reads next): sum(g) and sum(g * (x - mean[k])) with g = v, or
+//   g = v where fmaf(x - mean, rscale, rshift) > 0 else 0 (the ReLU mask recomputed exactly as forward computed it);
+//   bn_x = the BatchNorm's input, same shape / layout as the output
 struct Epilogue {
   const float* scale;
   const float* bias;
   const float* accum;
   int relu;
   double* stats;
+  const float* bn_x;
+  const float* bn_mean;
+  const float* bn_rscale;  // may be null (no ReLU behind the BatchNorm): then bn_rshift is unused
+  const float* bn_rshift;
 };
 inline Epilogue bias_epilogue(const float* bias) { return Epilogue{nullptr, bias, nullptr, 0, nullptr}; }
 

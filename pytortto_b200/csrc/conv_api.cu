@@ -35,7 +35,8 @@ int igemm_fprop_grouped(const ttb_conv_desc* dg, int groups, const void* x, size
                         size_t w_goff_bytes, const Epilogue& ep, float* y, int y_ctot, cudaStream_t st);
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
                 cudaStream_t st, const void* prepacked = nullptr, const float* accum = nullptr, int dy_ctot = 0, int dx_ctot = 0,
-                bool zero_done = false);
+                bool zero_done = false, const Epilogue* bn = nullptr);
+int igemm_dgrad_stats_chunks(const ttb_conv_desc* d);
 int igemm_wgrad(const ttb_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                 cudaStream_t st, int* splits_out = nullptr, int x_ctot = 0, int dy_ctot = 0);
 // conv_flat.cu: "flat-shift halo tile" fprop / dgrad with shared-memory-resident weights (the 64-channel 3x3 layers)
@@ -603,6 +604,33 @@ int ttb_conv2d_dgrad_bf16(const ttb_conv_desc* d, const void* dy_bf16, const voi
   if (int rc = validate(d, "conv2d_dgrad_bf16")) return rc;
   TTB_REQUIRE(ttb_conv2d_bf16_supported(d, 1), "conv2d_dgrad_bf16: problem needs the staged path (ttb_conv2d_dgrad)");
   return igemm_dgrad(d, dy_bf16, nullptr, dx, nullptr, 0, as_stream(stream), w_packed_bf16, accum);
+}
+
+/* ---- dgrad whose epilogue also emits the sums of the BatchNorm backward that reads dx next ----------------------------- */
+
+static bool dgrad_bn_plan(const ttb_conv_desc* d, bool* bf16) {
+  *bf16 = d->math_mode == TTB_MATH_BF16;
+  if (*bf16) return ttb_conv2d_bf16_supported(d, 1) != 0;
+  TensorPlan t;
+  return plan_tensor(d, 1, &t) && !t.stage_ops && t.groups == 1 && !flat_dgrad_supported(&t.p);
+}
+
+int ttb_conv2d_dgrad_bn_stats_chunks(const ttb_conv_desc* d) {
+  bool bf16;
+  if (!d || validate(d, "conv2d_dgrad_bn_stats_chunks") || !dgrad_bn_plan(d, &bf16)) return 0;
+  return igemm_dgrad_stats_chunks(d);
+}
+
+int ttb_conv2d_dgrad_bn(const ttb_conv_desc* d, const void* dy, const void* w_packed, const float* accum, float* dx,
+                        const ttb_dgrad_bn_stats* bn, void* stream) {
+  if (int rc = validate(d, "conv2d_dgrad_bn")) return rc;
+  bool bf16;
+  TTB_REQUIRE(bn && bn->x && bn->mean && bn->partials && (!bn->rscale == !bn->rshift), "conv2d_dgrad_bn: bad statistics arguments");
+  TTB_REQUIRE(dgrad_bn_plan(d, &bf16) && igemm_dgrad_stats_chunks(d) > 0,
+              "conv2d_dgrad_bn: not available for this problem (ttb_conv2d_dgrad_bn_stats_chunks)");
+  Epilogue e = Epilogue{nullptr, nullptr, nullptr, 0, bn->partials};
+  e.bn_x = bn->x; e.bn_mean = bn->mean; e.bn_rscale = bn->rscale; e.bn_rshift = bn->rshift;
+  return igemm_dgrad(d, dy, nullptr, dx, nullptr, 0, as_stream(stream), w_packed, accum, 0, 0, false, &e);
 }
 
 int ttb_conv2d_wgrad_bf16(const ttb_conv_desc* d, const void* x_bf16, const void* dy_bf16, float* dw, void* workspace,

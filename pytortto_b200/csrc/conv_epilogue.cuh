@@ -31,12 +31,13 @@ struct EpiStats {
 
 // One tile.  `my_off`: element offset of the output row this thread's accumulator row maps to (< 0: the row does not
 // exist / is dropped); `st`: this warp's 32 x kStagePitch staging floats; `lane_block` = TMEM lane block (warp_id % 4).
-template <int BN, bool STATS>
+// STATS: 0 none, 1 sum / sum of squares of the stored values (forward statistics), 2 the BatchNorm-backward sums (Epilogue::bn_x)
+template <int BN, int STATS>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, float* __restrict__ out, int64_t my_off, int n0,
                                               int n_total, const Epilogue& ep, int lane_block, EpiStats<BN>& es) {
   const int lane = threadIdx.x & 31;
   const int sub = lane >> 3, c4 = lane & 7;
-  const bool fresh = STATS && es.cnt == 0;
+  const bool fresh = STATS == 1 && es.cnt == 0;
   int tile_rows = 0;
   // output offsets (in float4 units; every row offset is a multiple of 4 elements) of the 8 rows this lane stores, fetched
   // from their owner lanes once per tile instead of once per column block
@@ -71,6 +72,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, floa
   };
   float4 acc[8], acc_next[8];
   if (kAhead && accum4) load_accum(acc_next, 0);
+  // BatchNorm-backward sums (Epilogue::bn_x): the BatchNorm's input at the positions this lane stores, eight independent
+  // loads per column block issued before the TMEM load, and the lane's four per-channel constants
+  constexpr bool bwd = STATS == 2;
+  const float4* const bnx4 = reinterpret_cast<const float4*>(ep.bn_x);
   // (fully unrolled: the statistics live in registers indexed by cb)
 #pragma unroll
   for (int cb = 0; cb < BN / 32; ++cb) {
@@ -83,6 +88,22 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, floa
         if (cb + 1 < BN / 32) load_accum(acc_next, cb + 1);  // (columns past n_total are not loaded: see load_accum)
       } else {
         load_accum(acc, cb);
+      }
+    }
+    float4 xs[8];
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rsc = mu, rsh = mu;
+    if (STATS && bwd) {
+      const bool okc = col0 + c4 * 4 < n_total;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        xs[it] = (off4[it] >= 0 && okc) ? ld_f4_stream(reinterpret_cast<const float*>(bnx4 + ((int64_t)off4[it] + (col0 >> 2) + c4)))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (okc) {
+        mu = ld_f4(ep.bn_mean + col0 + c4 * 4);
+        if (ep.bn_rscale) {
+          rsc = ld_f4(ep.bn_rscale + col0 + c4 * 4);
+          rsh = ld_f4(ep.bn_rshift + col0 + c4 * 4);
+        }
       }
     }
     uint32_t r[32];
@@ -128,7 +149,18 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_acc, float* st, floa
           v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
         }
         if (!(dbg & 1)) out4[o4] = v;
-        if (STATS) {
+        if (STATS && bwd) {  // (es.k stays 0: the flush then passes s0 / s1 through unchanged)
+          const float4 xv = xs[it];
+          const float cx = xv.x - mu.x, cy = xv.y - mu.y, cz = xv.z - mu.z, cw = xv.w - mu.w;
+          float4 g = v;
+          if (ep.bn_rscale) {  // exactly forward's expression (bn_apply4): bit-identical mask decisions
+            g.x = fmaf(cx, rsc.x, rsh.x) > 0.f ? g.x : 0.f; g.y = fmaf(cy, rsc.y, rsh.y) > 0.f ? g.y : 0.f;
+            g.z = fmaf(cz, rsc.z, rsh.z) > 0.f ? g.z : 0.f; g.w = fmaf(cw, rsc.w, rsh.w) > 0.f ? g.w : 0.f;
+          }
+          es.s0[cb][0] += g.x; es.s0[cb][1] += g.y; es.s0[cb][2] += g.z; es.s0[cb][3] += g.w;
+          es.s1[cb][0] = fmaf(g.x, cx, es.s1[cb][0]); es.s1[cb][1] = fmaf(g.y, cy, es.s1[cb][1]);
+          es.s1[cb][2] = fmaf(g.z, cz, es.s1[cb][2]); es.s1[cb][3] = fmaf(g.w, cw, es.s1[cb][3]);
+        } else if (STATS) {
           if (fresh && !seen) { es.k[cb][0] = v.x; es.k[cb][1] = v.y; es.k[cb][2] = v.z; es.k[cb][3] = v.w; }
           seen = true;
           const float dx = v.x - es.k[cb][0], dy = v.y - es.k[cb][1], dz = v.z - es.k[cb][2], dw = v.w - es.k[cb][3];

@@ -240,7 +240,7 @@ struct FwdParamsMulti {
 // start at any 128-byte row: profiles/r1_umma_row_shift_probe.txt).  A stage then holds the strip + WT weight tiles and
 // costs one hand-shake per 4*WT MMAs; A traffic from L2 drops from R*S to R loads per tile (the 64 / 128-channel layers are
 // bound by exactly that feed: 97-128 B/clk/SM wanted at full tensor rate against ~100 available).
-template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, bool STATS>
+template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, int STATS>
 __global__ void __launch_bounds__((NPROD + 5) * 32, BN <= 64 ? 2 : 1)  // narrow tiles: two CTAs per SM (<= 128 registers)
 igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int count) {
   pdl_launch_dependents();  // (the matching pdl_wait() follows the prologue below)
@@ -411,11 +411,23 @@ igemm_fwd_persist_kernel(const __grid_constant__ FwdParamsMulti PM, const int co
       decode(t, cls, m0, n0);
       const FwdParams& P = PM.p[cls];
       const int buf = it & 1;
+      const int64_t my_off = out_row_offset(P.o, m0 + (warp & 3) * 32 + lane);
+      // While this warp waits for the tile's MMAs, the rows of the tensors its epilogue will READ at the output positions
+      // (the pending gradient / residual, the BatchNorm input of the backward sums) are pulled into L2: their loads inside
+      // the epilogue are dependent round trips per 32-column block, ~4x shorter from L2 than from HBM.
+      if ((STATS == 2 || P.ep.accum != nullptr) && my_off >= 0) {
+#pragma unroll
+        for (int cb = 0; cb < BN / 32; ++cb) {
+          if (n0 + cb * 32 >= P.o.n_total) break;
+          if (P.ep.accum != nullptr) ptx::prefetch_l2(P.ep.accum + my_off + n0 + cb * 32);
+          if (STATS == 2) ptx::prefetch_l2(P.ep.bn_x + my_off + n0 + cb * 32);
+        }
+      }
       ptx::mbar_wait(&acc_full[buf], ((uint32_t)it >> 1) & 1u);
       ptx::tc_fence_after();
       if (tr && ew == 0 && lane == 0 && it < 250) tr[528 + 2 * it] = clock64();
-      epilogue_tile<BN, STATS>(tmem_base + (uint32_t)(buf * kAccCols), my_stage, P.o.out,
-                               out_row_offset(P.o, m0 + (warp & 3) * 32 + lane), n0, P.o.n_total, P.ep, warp & 3, es);
+      epilogue_tile<BN, STATS>(tmem_base + (uint32_t)(buf * kAccCols), my_stage, P.o.out, my_off, n0, P.o.n_total, P.ep,
+                               warp & 3, es);
       n0_last = n0;
       ptx::tc_fence_before();
       __syncwarp();
@@ -841,7 +853,7 @@ static unsigned persist_grid(int64_t tiles, int nt, size_t smem, bool stats) {
   return (unsigned)grid;
 }
 
-template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, bool STATS>
+template <int BN, int NSTAGES, int NPROD, int WT, bool BF16, int STATS>
 static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) {
   constexpr size_t smem = persist_smem_bytes(BN, NSTAGES, WT);
   static_assert(smem <= 232448, "shared memory budget of one SM");
@@ -860,7 +872,7 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
   for (int i = 0; i < count; ++i) tiles += (int64_t)ceil_div(PM.p[i].o.m_total, kTileM) * nt;
   // narrow tiles leave room for two CTAs per SM (two independent MMA-issue streams: a 64-column K-block is 128
   // tensor-core cycles but ~300 cycles of issue-side latency per CTA)
-  const unsigned grid = persist_grid(tiles, nt, smem, STATS);
+  const unsigned grid = persist_grid(tiles, nt, smem, STATS != 0);
   launch_k(igemm_fwd_persist_kernel<BN, NSTAGES, NPROD, WT, BF16, STATS>, grid, (NPROD + 5) * 32, smem, st, PM, count);
   return check_launch("igemm_fwd_persist_kernel");
 }
@@ -879,7 +891,7 @@ static PersistCfg persist_cfg(int bn, int wt) {
   }
 }
 
-template <bool BF16, bool STATS>
+template <bool BF16, int STATS>
 static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, int wt, cudaStream_t st) {
   if (wt == 3) {
     if (bn == 128) return launch_persist<128, 3, 3, 3, BF16, STATS>(PM, count, st);
@@ -894,9 +906,14 @@ static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, int w
 }
 
 static int launch_persist_bn(const FwdParamsMulti& PM, int count, int bn, int wt, bool bf16, cudaStream_t st) {
-  const bool stats = count == 1 && PM.p[0].ep.stats != nullptr;
-  if (bf16) return stats ? launch_persist_sel<true, true>(PM, count, bn, wt, st) : launch_persist_sel<true, false>(PM, count, bn, wt, st);
-  return stats ? launch_persist_sel<false, true>(PM, count, bn, wt, st) : launch_persist_sel<false, false>(PM, count, bn, wt, st);
+  // 0 none, 1 forward statistics of the stored values, 2 BatchNorm-backward sums against Epilogue::bn_x (conv_epilogue.cuh)
+  const int stats = (count == 1 && PM.p[0].ep.stats != nullptr) ? (PM.p[0].ep.bn_x != nullptr ? 2 : 1) : 0;
+  if (bf16) {
+    if (stats == 2) return launch_persist_sel<true, 2>(PM, count, bn, wt, st);
+    return stats ? launch_persist_sel<true, 1>(PM, count, bn, wt, st) : launch_persist_sel<true, 0>(PM, count, bn, wt, st);
+  }
+  if (stats == 2) return launch_persist_sel<false, 2>(PM, count, bn, wt, st);
+  return stats ? launch_persist_sel<false, 1>(PM, count, bn, wt, st) : launch_persist_sel<false, 0>(PM, count, bn, wt, st);
 }
 
 // rows of the [chunks][2][K] statistics partial buffer an fprop launch of this problem writes (Epilogue::stats)
@@ -911,6 +928,22 @@ int igemm_fprop_stats_chunks(const ttb_conv_desc* d) {
   const int64_t m_total = (int64_t)d->n * d->p * (d->q + wt - 1);
   const PersistCfg c = persist_cfg(bn, wt);
   const int nt = (int)ceil_div(d->k, bn);
+  const int64_t tiles = ceil_div(m_total, kTileM) * nt;
+  return (int)(persist_grid(tiles, nt, persist_smem_bytes(bn, c.nstages, wt), true) / nt);
+}
+
+// rows of the [chunks][2][C] partial buffer a stride-1 dgrad of this problem writes when its epilogue emits the sums of a
+// BatchNorm backward over dx (Epilogue::bn_x); 0 = not available.  Mirrors igemm_dgrad's single-class tile choice.
+int igemm_dgrad_stats_chunks(const ttb_conv_desc* d) {
+  if (d->stride_h != 1 || d->stride_w != 1 || d->groups != 1 || !igemm_supported(d, 1)) return 0;
+  const int nkb = d->r * d->s * (d->k / igemm_channel_block(d));
+  const int bn = pick_bn((int64_t)d->n * d->h * d->w, d->c, nkb);
+  // (256-wide tiles on small outputs: about one tile per CTA, the longer epilogue would not be hidden - as in fprop)
+  if (bn == 256 && (int64_t)d->n * d->h * d->w * d->c < tuning_knob("TTB_STATS256_MIN_MELEMS", 8) * (int64_t)(1 << 20)) return 0;
+  const int wt = pick_wt(d->s, 1, d->dil_w, bn, d->w);
+  const int64_t m_total = (int64_t)d->n * d->h * (d->w + wt - 1);
+  const PersistCfg c = persist_cfg(bn, wt);
+  const int nt = (int)ceil_div(d->c, bn);
   const int64_t tiles = ceil_div(m_total, kTileM) * nt;
   return (int)(persist_grid(tiles, nt, persist_smem_bytes(bn, c.nstages, wt), true) / nt);
 }
@@ -1060,8 +1093,11 @@ int igemm_fprop_grouped(const ttb_conv_desc* dg, int groups, const void* x, size
 // `prepacked` != null: the weights are already in the [C][R][S][K] order (igemm_pack_dgrad_weights), w / ws unused
 // dy_ctot / dx_ctot: channel counts of the tensors dy / dx live in when `d` is ONE GROUP of a grouped convolution (dy, dx,
 // accum point at the group's first channel; the caller zeroes dx where no tap reaches: zero_done); 0 = dense.
+// `bn` (may be null; stride-1 problems only, see igemm_dgrad_stats_chunks): stats + bn_* fields of an Epilogue - the epilogue
+// also emits the BatchNorm-backward sums of dx against the BatchNorm input bn->bn_x.
 int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx, void* ws, size_t ws_bytes,
-                cudaStream_t st, const void* prepacked, const float* accum, int dy_ctot, int dx_ctot, bool zero_done) {
+                cudaStream_t st, const void* prepacked, const float* accum, int dy_ctot, int dx_ctot, bool zero_done,
+                const Epilogue* bn) {
   // (`accum`, may be null: added to dx in the epilogue - the gradient already pending for the same tensor)
   const int64_t xc = dx_ctot ? dx_ctot : d->c;
   if (load_driver_fns()) return 1;
@@ -1090,6 +1126,8 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
   int n_multi = 0, nkb_max = 0;
   int64_t m_all = 0;
   const bool multi = d->stride_h * d->stride_w > 1 && d->stride_h * d->stride_w <= kMaxMulti;
+  TTB_REQUIRE(!bn || (d->stride_h == 1 && d->stride_w == 1 && !dy_ctot && !dx_ctot),
+              "conv2d_dgrad: BatchNorm-backward statistics need a dense stride-1 problem");
   for (int pass = 0; pass < 2; ++pass) {
     for (int a = 0; a < d->stride_h; ++a)
       for (int b = 0; b < d->stride_w; ++b) {
@@ -1142,6 +1180,10 @@ int igemm_dgrad(const ttb_conv_desc* d, const void* dy, const void* w, float* dx
         P.o.m_total = d->n * ha * (wb + wtaps - 1);
         P.o.n_total = d->c;
         P.ep = Epilogue{nullptr, nullptr, accum, tuning_knob("TTB_EPI_DBG", 0) << 8, nullptr};
+        if (bn) {
+          P.ep.stats = bn->stats;
+          P.ep.bn_x = bn->bn_x; P.ep.bn_mean = bn->bn_mean; P.ep.bn_rscale = bn->bn_rscale; P.ep.bn_rshift = bn->bn_rshift;
+        }
         P.c_blocks = d->k / el.per_row;
         P.num_taps = cls.nr * cls.ns;
         P.base_w = lo_w;

@@ -413,6 +413,7 @@ def begin_backward_sweep():
 
 
 def end_backward_sweep():
+    resolve_pending(None, ())  # a dgrad whose launch was deferred for a BatchNorm backward that never came
     _dgrad_pack["in_sweep"] = False
     _dgrad_pack["registry"].clear()  # (weights registered by a forward whose dgrad never ran must not be kept alive)
     packed = _dgrad_pack["packed"]
@@ -455,31 +456,104 @@ def _flush_dgrad_pack():
     _cabi.call("ttb_conv2d_dgrad_pack_weights", n, descs, src, dst, current_stream_ptr())
 
 
-def conv2d_dgrad(dy, w, d, accum=None):
-    """`accum`: a gradient already pending for the same tensor (the engine's `grad += new`): added in the dgrad epilogue
-    where the kernel can (pre-packed TF32 / bf16 tensor path), by a separate add otherwise."""
-    dx = new_f32((d.n, d.c, d.h, d.w))
-    if dx.size == 0:
-        return dx if accum is None else accum
-    if accum is not None and (accum.shape != dx.shape or accum.t.dtype != torch.float32):
-        return add_arrays(conv2d_dgrad(dy, w, d), accum)
+_dgrad_bn_chunks = {}  # id(descriptor) -> rows of the partial buffer a dgrad + BatchNorm-backward-statistics launch writes
+# Measured on B200 (profiles/r2_dgrad_bn_ab.txt): the fused launch saves the statistics pass (preact_resnet18: 0.29 -> 0.11
+# ms of ttb_bn_bwd_reduce per step) but its longer epilogue costs the dgrad kernels about as much (0.77 -> 0.95 ms); net
+# 3.098 -> 3.075 ms per step in TF32 mode (fewer launches), 2.636 -> 2.670 ms in bf16 mode, where the shorter main loop no
+# longer hides the epilogue - so bf16 problems take it only on request (TORTTO_B200_DGRAD_BN_BF16=1).
+_DGRAD_BN_BF16 = [os.environ.get("TORTTO_B200_DGRAD_BN_BF16", "0") != "0"]
+
+
+def _dgrad_tensor_operands(dy, w, d):
+    """(dy pointer, packed weight pointer) when this dgrad runs on the tensor path from ready-made operands - bf16 shadows,
+    or fp32 with the weights pre-packed for this backward sweep - else None"""
     if d.math_mode == _cabi.TTB_MATH_BF16:
         if conv_bf16_supported(d, 1) and w.ndim == 4:
-            _cabi.call("ttb_conv2d_dgrad_bf16", ctypes.byref(d), bf16_of(dy).data_ptr(), _weight_bf16(w, True).data_ptr(),
-                       _ptr(accum), _ptr(dx), current_stream_ptr())
-            return dx
-        d = _tf32_twin(d)
+            return bf16_of(dy).data_ptr(), _weight_bf16(w, True).data_ptr()
+        return None
     if _dgrad_pack["enabled"] and _dgrad_pack["in_sweep"]:  # (a dgrad outside backward = ConvTranspose2d forward)
         _flush_dgrad_pack()
         ent = _dgrad_pack["packed"].get(w.t.data_ptr())
         if ent is not None and ent[1] == _dgrad_pack["sweep"] and _prepack_ok.get(id(d)):
-            _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), _ptr(dy), ent[0].data_ptr(), _ptr(accum), _ptr(dx),
+            return _ptr(dy), ent[0].data_ptr()
+    return None
+
+
+def conv2d_dgrad_for_batchnorm(dy, w, d, accum=None):
+    """conv2d_dgrad whose consumer is a BatchNorm(+ReLU) backward node: the launch is deferred (see `_defer`) so that
+    `bn_backward` can run it with the epilogue that also emits the two sums of the BatchNorm backward over dx
+    (ttb_conv2d_dgrad_bn) - the statistics pass (two full reads) disappears.  Anything else that touches the array first
+    gets the plain dgrad."""
+    dx_shape = (d.n, d.c, d.h, d.w)
+    if not _DEFER or not _dgrad_pack["in_sweep"] or d.n * d.c * d.h * d.w == 0 or \
+            (d.math_mode == _cabi.TTB_MATH_BF16 and not _DGRAD_BN_BF16[0]) or \
+            (accum is not None and (accum.shape != dx_shape or accum.t.dtype != torch.float32 or accum._thunk is not None)):
+        return conv2d_dgrad(dy, w, d, accum)
+    chunks = _dgrad_bn_chunks.get(id(d))
+    if chunks is None:
+        chunks = _dgrad_bn_chunks[id(d)] = int(_cabi.load().ttb_conv2d_dgrad_bn_stats_chunks(ctypes.byref(d)))
+    if chunks <= 0 or (d.math_mode != _cabi.TTB_MATH_BF16 and not (_dgrad_pack["enabled"] and _prepack_ok.get(id(d)))):
+        return conv2d_dgrad(dy, w, d, accum)
+    if _dgrad_tensor_operands(dy, w, d) is None:  # (the operands the fused launch needs exist now, hence also later)
+        return conv2d_dgrad(dy, w, d, accum)
+    dx = new_f32(dx_shape)
+    return _defer(dx, "dgrad", (dy, w, d, accum), (dy, w, accum),
+                  lambda arr, dy, w, d, accum: conv2d_dgrad(dy, w, d, accum, out=arr))
+
+
+def dgrad_bn_fused(deferred, x, mean_ptr, rscale_ptr, rshift_ptr):
+    """BatchNorm backward absorbing the deferred dgrad that produces its incoming gradient: ONE conv launch writes
+    `deferred` and the [chunks][2][C] partial sums; returns (partials, chunks) or None (then the caller materialises)."""
+    job = deferred._thunk.job
+    dy, w, d, accum = job.args
+    if tuple(x.shape) != tuple(deferred.shape) or x.__class__ is not cparray or x.t.dtype != torch.float32:
+        return None
+    ops_ptrs = _dgrad_tensor_operands(dy, w, d)
+    if ops_ptrs is None:
+        return None
+    _pending[0] = None
+    job.check()
+    chunks = _dgrad_bn_chunks[id(d)]
+    partials = torch.empty((chunks, 2, d.c), dtype=torch.float64, device=x.t.device)
+    bn = _cabi.DgradBnStats(_ptr(x), mean_ptr, rscale_ptr, rshift_ptr, partials.data_ptr())
+    deferred._thunk = None
+    deferred._h = None
+    _cabi.call("ttb_conv2d_dgrad_bn", ctypes.byref(d), ops_ptrs[0], ops_ptrs[1], _ptr(accum), deferred._t.data_ptr(),
+               ctypes.byref(bn), current_stream_ptr())
+    return partials, chunks
+
+
+def conv2d_dgrad(dy, w, d, accum=None, out=None):
+    """`accum`: a gradient already pending for the same tensor (the engine's `grad += new`): added in the dgrad epilogue
+    where the kernel can (pre-packed TF32 / bf16 tensor path), by a separate add otherwise.  `out`: the array to fill (a
+    deferred launch finally running)."""
+    dx = out if out is not None else new_f32((d.n, d.c, d.h, d.w))
+    if dx.size == 0:
+        return dx if accum is None else accum
+    if accum is not None and (accum.shape != dx.shape or accum.t.dtype != torch.float32):
+        return add_arrays(conv2d_dgrad(dy, w, d), accum)
+    ops_ptrs = _dgrad_tensor_operands(dy, w, d)
+    if ops_ptrs is not None:
+        _cabi.call("ttb_conv2d_dgrad_bf16" if d.math_mode == _cabi.TTB_MATH_BF16 else "ttb_conv2d_dgrad_prepacked",
+                   ctypes.byref(d), ops_ptrs[0], ops_ptrs[1], _ptr(accum), _ptr(dx), current_stream_ptr())
+        return dx
+    if d.math_mode == _cabi.TTB_MATH_BF16:
+        d = _tf32_twin(d)
+        ops_ptrs = _dgrad_tensor_operands(dy, w, d)
+        if ops_ptrs is not None:
+            _cabi.call("ttb_conv2d_dgrad_prepacked", ctypes.byref(d), ops_ptrs[0], ops_ptrs[1], _ptr(accum), _ptr(dx),
                        current_stream_ptr())
             return dx
     ws, nb = _workspace(_cabi.load().ttb_conv2d_workspace_size(ctypes.byref(d), 1))
     _cabi.call("ttb_conv2d_dgrad", ctypes.byref(d), _ptr(dy), _ptr(w), _ptr(dx),
                None if ws is None else ws.data_ptr(), nb, current_stream_ptr())
-    return dx if accum is None else add_arrays(dx, accum)
+    if accum is None:
+        return dx
+    res = add_arrays(dx, accum)
+    if out is not None:  # (a deferred launch must fill the array it was deferred on)
+        out.t.copy_(res.t)
+        return out
+    return res
 
 
 # Weight gradients are leaves of the backward pass: nothing downstream of a conv's backward needs dW before the
@@ -795,12 +869,20 @@ def bn_backward(dy, x, gamma, stats, count, relu_out=None, need_dx=True, need_dg
     base = stats.t.data_ptr()
     row = c * 4
     st = current_stream_ptr()
-    chunks = _cabi.load().ttb_bn_num_chunks(m, c)
-    partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
     rsc = rsh = None
     if fused_relu and _RECOMPUTE_RELU_MASK:
         relu_out, rsc, rsh = None, base + 3 * row, base + 4 * row
-    _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, m, c, partials.data_ptr(), chunks, st)
+    partials = None
+    if relu_out is None and dy.__class__ is cparray and dy._thunk is not None and x.ndim == 4 and \
+            getattr(getattr(dy._thunk, "job", None), "kind", None) == "dgrad":
+        # the gradient is a dgrad whose launch is still deferred: ONE conv launch writes it AND the two sums over it
+        fusedp = dgrad_bn_fused(dy, x, base, rsc, rsh)
+        if fusedp is not None:
+            partials, chunks = fusedp
+    if partials is None:
+        chunks = _cabi.load().ttb_bn_num_chunks(m, c)
+        partials = torch.empty((chunks, 2, c), dtype=torch.float64, device=x.t.device)
+        _cabi.call("ttb_bn_bwd_reduce", _ptr(dy), _ptr(x), base, _ptr(relu_out), rsc, rsh, m, c, partials.data_ptr(), chunks, st)
     dgamma = (out_dgamma if out_dgamma is not None else new_f32((c,))) if need_dgamma else None
     dbeta = (out_dbeta if out_dbeta is not None else new_f32((c,))) if need_dbeta else None
     coef = new_f32((3, c))

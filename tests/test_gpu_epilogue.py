@@ -382,3 +382,62 @@ def test_post_activation_block_tail_is_one_pass(mode, inplace):
         assert_close(f"{mode} {name}", u, v, 1e-5)
     yo = np.maximum(a[5] + ident, 0)
     assert_close(f"{mode} y vs max(bn + identity, 0)", a[0], yo, 1e-6)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", [(8, 64, 16, 16, 64), (4, 128, 12, 12, 128), (3, 64, 9, 11, 96)],
+                         ids=["c64_16x16", "c128_12x12", "c64_9x11_k96"])
+def test_dgrad_emits_the_batchnorm_backward_sums(mode, relu, shape):
+    """conv(relu?(bn(x))): the gradient the conv's dgrad produces is what BatchNorm.backward reduces next (sum g,
+    sum g (x - mean), g masked by the ReLU).  The dgrad launch is deferred, the BatchNorm backward node takes it over with
+    the epilogue that emits those sums (ttb_conv2d_dgrad_bn) - no ttb_bn_bwd_reduce pass - and every gradient equals the
+    separate kernels' (same dgrad values; the sums differ only by summation order)."""
+    _skip_unless_deferral_is_on()
+    tt = _tt(mode)
+    from pytortto_b200 import _cabi
+    from pytortto_b200.autograd import grad_nn
+    n, c, h, w, k = shape
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    res = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    dy = rng.standard_normal((n, k, h, w)).astype(np.float32)
+
+    def run(fuse):
+        from pytortto_b200 import ops
+        prev, prev16 = grad_nn._BatchNormBase._absorbs_dgrad, ops._DGRAD_BN_BF16[0]
+        grad_nn._BatchNormBase._absorbs_dgrad = fuse
+        ops._DGRAD_BN_BF16[0] = True  # (bf16 problems take the fused launch only on request: measured slower there)
+        names = []
+        orig = _cabi.call
+
+        def spy(name, *a):
+            names.append(name)
+            return orig(name, *a)
+        _cabi.call = spy
+        try:
+            np.random.seed(0)
+            bn = tt.nn.BatchNorm2d(c).cuda()
+            bn.weight.data[...] = np.linspace(0.5, 1.5, c, dtype=np.float32)
+            bn.bias.data[...] = np.linspace(-0.3, 0.3, c, dtype=np.float32)
+            body = tt.nn.Sequential(bn, tt.nn.ReLU()) if relu else bn
+            conv = tt.nn.Conv2d(c, k, 3, 1, 1, bias=False).cuda()
+            xin = tt.nn.Parameter(tt.tensor(x).cuda())
+            rin = tt.nn.Parameter(tt.tensor(res).cuda())
+            a = body(xin)
+            # (a second consumer of the BatchNorm output: a gradient may already be pending for it when the dgrad runs)
+            loss = (conv(a) * tt.tensor(dy).cuda()).sum() + (a * rin).sum()
+            loss.backward()
+            out = (xin.grad.get(), bn.weight.grad.get(), bn.bias.grad.get(), conv.weight.grad.get(), rin.grad.get())
+        finally:
+            _cabi.call = orig
+            grad_nn._BatchNormBase._absorbs_dgrad = prev
+            ops._DGRAD_BN_BF16[0] = prev16
+        return out, names
+
+    (a, names_a), (b, names_b) = run(True), run(False)
+    if not (mode == "bf16" and k % 64):  # (96 filters: no bf16 dgrad - the layer falls back to TF32 and stays unfused there)
+        assert "ttb_conv2d_dgrad_bn" in names_a and "ttb_bn_bwd_reduce" not in names_a, names_a
+    assert "ttb_conv2d_dgrad_bn" not in names_b and "ttb_bn_bwd_reduce" in names_b
+    for name, u, v in zip(("dx", "dgamma", "dbeta", "dw", "dres"), a, b):
+        assert_close(f"{mode} relu={relu} {name}", u, v, 2e-5 if name in ("dx", "dgamma", "dbeta") else 1e-6)
