@@ -314,7 +314,10 @@ class _BatchNormBase(Function):
 
 # its backward can fold the pending gradient of input 0 into dx (TORTTO_B200_FOLD_ACCUM=0: separate add kernel)
 _BatchNormBase._accumulates_input0 = os.environ.get("TORTTO_B200_FOLD_ACCUM", "1") != "0"
-_BatchNormBase._absorbs_dgrad = os.environ.get("TORTTO_B200_DGRAD_BN", "1") != "0"  # (see Convolution.backward)
+# (see Convolution.backward.)  Off by default: on B200 the fused launch is a wash - the statistics pass it removes
+# (preact_resnet18: 0.29 -> 0.11 ms per step) comes back as a longer dgrad epilogue (0.77 -> 0.95 ms), the step gains 0.75 %
+# in TF32 mode and loses 1.3 % in bf16 mode (profiles/r2_dgrad_bn_ab.txt).  TORTTO_B200_DGRAD_BN=1 switches it on.
+_BatchNormBase._absorbs_dgrad = os.environ.get("TORTTO_B200_DGRAD_BN", "0") != "0"
 
 
 class BatchNormRelu(_BatchNormBase):

@@ -460,7 +460,8 @@ _dgrad_bn_chunks = {}  # id(descriptor) -> rows of the partial buffer a dgrad + 
 # Measured on B200 (profiles/r2_dgrad_bn_ab.txt): the fused launch saves the statistics pass (preact_resnet18: 0.29 -> 0.11
 # ms of ttb_bn_bwd_reduce per step) but its longer epilogue costs the dgrad kernels about as much (0.77 -> 0.95 ms); net
 # 3.098 -> 3.075 ms per step in TF32 mode (fewer launches), 2.636 -> 2.670 ms in bf16 mode, where the shorter main loop no
-# longer hides the epilogue - so bf16 problems take it only on request (TORTTO_B200_DGRAD_BN_BF16=1).
+# longer hides the epilogue.  The whole fusion is therefore opt-in (TORTTO_B200_DGRAD_BN=1, grad_nn._BatchNormBase), and
+# bf16 problems additionally need TORTTO_B200_DGRAD_BN_BF16=1.
 _DGRAD_BN_BF16 = [os.environ.get("TORTTO_B200_DGRAD_BN_BF16", "0") != "0"]
 
 
