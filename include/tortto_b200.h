@@ -293,12 +293,14 @@ int ttb_comm_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);
 int ttb_comm_open(const unsigned char* handle, void** peer_ptr);
 int ttb_comm_close(void* peer_ptr);
 int ttb_comm_free(void* dev_ptr);
-/* bytes of one slot holding up to max_values <= 8192 doubles: header + two data buffers used alternately (parity of the
- * slot's exchange count), so a rank that runs ahead never overwrites words a slower peer is still reading; 0 if too large */
+/* bytes of one slot for exchanges of up to max_values <= 4096 doubles among <= 8 ranks: header + two buffers used alternately
+ * (parity of the slot's exchange count, so a rank that runs ahead never overwrites words a slower peer is still reading),
+ * each with one area per SOURCE rank - peers push their values into it and the owner polls its own memory; 0 if too large */
 size_t ttb_comm_slot_bytes(int max_values);
 /* out[i] = sum over ranks (rank order) of sum over chunks of that rank's partials[chunk][i], exchanged through the
  * slot at `slot_offset` of every rank's buffer.  peers_dev: DEVICE array of `world` mapped buffer bases (own buffer at
- * index `rank`).  One kernel, one NVLink round trip; every rank must call it for the same slot the same number of times. */
+ * index `rank`).  One kernel, one one-way NVLink latency (values are pushed, polling is local); every rank must call it for
+ * the same slot the same number of times. */
 int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,
                        size_t slot_offset, double* out, void* stream);
 /* The same exchange fused with the BatchNorm finalisation that follows it - one kernel per BatchNorm layer and

@@ -5,10 +5,12 @@
 // stream.  Here every rank owns a communication buffer (cudaMalloc + CUDA IPC, mapped into every peer) made of
 // fixed "slots" {flag, arrive counter, data[]}; a call site (one BatchNorm layer, forward or backward) always uses
 // the same slot, so nothing but device memory changes between steps (CUDA-graph safe).
-// One kernel per exchange (comm_allreduce_kernel below): sum this rank's per-chunk partials, write the result into its
-// own slot as self-validating 8-byte words {sequence | 32 data bits}, poll the same words of every peer over NVLink
-// (peer loads bypass L1) and add them IN RANK ORDER (bit-identical result on every rank) into a local [n] buffer that
-// the ordinary bn finalize kernels consume.
+// One kernel per exchange (comm_allreduce_kernel below): sum this rank's per-chunk partials, PUSH the result into the
+// slot of every peer (remote stores over NVLink into the area reserved for this rank) as self-validating 8-byte words
+// {sequence | 32 data bits}, poll the areas of the own slot that the peers fill - LOCAL memory, so a value is seen one
+// one-way NVLink latency after it was sent instead of after 1-2 round trips of remote polling - and add the values IN RANK
+// ORDER (bit-identical result on every rank) into a local [n] buffer that the ordinary bn finalize kernels consume.
+// Slot layout: header | parity 0: [world][kCommMaxValues] word pairs | parity 1: the same.
 // Why reuse of a slot is safe: the data area is DOUBLE-BUFFERED by the parity of the exchange's sequence number.  Rank A
 // can start exchange s+1 (other buffer) while a slow peer B is still reading A's words of exchange s, but A cannot finish
 // s+1 - and so cannot reach s+2, which overwrites the buffer of s - before B has published its s+1 value, which B does
@@ -27,9 +29,12 @@ struct SlotHeader {
   unsigned int pad[2];
 };
 constexpr size_t kSlotHeaderBytes = 16;
-constexpr int kCommMaxValues = 8192;                            // values per exchange (2C doubles, C <= 4096)
-constexpr size_t kParityStride = (size_t)kCommMaxValues * 16;   // bytes between the two data buffers of a slot
-__device__ __forceinline__ size_t slot_data_offset(unsigned int seq) { return kSlotHeaderBytes + (seq & 1u) * kParityStride; }
+constexpr int kCommMaxValues = 4096;                          // values per exchange (2C doubles, C <= 2048)
+constexpr size_t kRankStride = (size_t)kCommMaxValues * 16;   // bytes of the area one source rank writes
+// area of a slot that source rank `src` fills in the exchange with sequence number `seq` (two buffers, by parity)
+__device__ __forceinline__ size_t slot_area_offset(unsigned int seq, int world, int src) {
+  return kSlotHeaderBytes + ((size_t)(seq & 1u) * world + src) * kRankStride;
+}
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -45,7 +50,7 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
   return v;
 }
 
-constexpr int kMaxWorld = 16;
+constexpr int kMaxWorld = 8;  // one NVSwitch box (CUDA IPC does not leave the node)
 
 // ONE kernel per exchange, one NVLink round trip ("LL" style: every 8-byte word carries its own sequence number, so
 // the data is its own flag and no fence / separate flag write is needed; aligned 8-byte accesses are atomic).
@@ -80,15 +85,11 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
     double mine = 0.0;
     for (int j = 0; j < 32; ++j) mine += sm[j][threadIdx.x];
     mine_sm[threadIdx.x] = mine;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
-    const unsigned long long tag = (unsigned long long)seq << 32;
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + slot_data_offset(seq)) + 2 * (size_t)i;
-    st_volatile_u64(w, tag | (bits & 0xffffffffull));
-    st_volatile_u64(w + 1, tag | (bits >> 32));
   }
   __syncthreads();  // sm[][] is reused below: row r = the value of rank r
-  // thread (x = value, y = peer rank) polls ONE peer, so the NVLink round trips of all peers overlap (polled one after
-  // the other by a single thread, an exchange took ~1.5 us per peer); rank order is restored by the sum below
+  // thread (x = value, y = peer rank) serves ONE peer: it pushes this rank's value into that peer's slot and then polls
+  // the area of the own slot that the peer fills, so the transfers of all peers overlap; rank order is restored by the
+  // sum below
   bool failed = false;
   const int r = threadIdx.y;
   if (r < world && i < n) {
@@ -96,8 +97,14 @@ comm_allreduce_kernel(const double* __restrict__ partials, int num_chunks, int n
     if (r == rank) {
       v = mine_sm[threadIdx.x];
     } else {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(mine_sm[threadIdx.x]);
+      const unsigned long long tag = (unsigned long long)seq << 32;
+      unsigned long long* w =
+          reinterpret_cast<unsigned long long*>(peers[r] + slot_offset + slot_area_offset(seq, world, rank)) + 2 * (size_t)i;
+      st_volatile_u64(w, tag | (bits & 0xffffffffull));
+      st_volatile_u64(w + 1, tag | (bits >> 32));
       const unsigned long long* pw =
-          reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + slot_data_offset(seq)) + 2 * (size_t)i;
+          reinterpret_cast<const unsigned long long*>(own + slot_area_offset(seq, world, r)) + 2 * (size_t)i;
       unsigned long long a, b, spins = 0;
       for (;;) {
         a = ld_volatile_u64(pw);
@@ -164,17 +171,11 @@ comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int
   sm0[threadIdx.y][threadIdx.x] = a0 + a1;
   sm1[threadIdx.y][threadIdx.x] = b0 + b1;
   __syncthreads();
-  if (threadIdx.y < 2 && i < c) {  // y = 0 publishes value i, y = 1 value c + i
+  if (threadIdx.y < 2 && i < c) {  // y = 0 sums value i, y = 1 value c + i
     double (*sm)[33] = threadIdx.y == 0 ? sm0 : sm1;
     double mine = 0.0;
     for (int j = 0; j < 32; ++j) mine += sm[j][threadIdx.x];
     mine_sm[threadIdx.y][threadIdx.x] = mine;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
-    const unsigned long long tag = (unsigned long long)seq << 32;
-    const size_t v = threadIdx.y == 0 ? (size_t)i : (size_t)c + i;
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(own + slot_data_offset(seq)) + 2 * v;
-    st_volatile_u64(w, tag | (bits & 0xffffffffull));
-    st_volatile_u64(w + 1, tag | (bits >> 32));
   }
   __syncthreads();  // sm0 / sm1 are reused: row r = the two values of rank r
   bool failed = false;
@@ -185,7 +186,17 @@ comm_bn_finalize_kernel(const double* __restrict__ partials, int num_chunks, int
       v0 = mine_sm[0][threadIdx.x];
       v1 = mine_sm[1][threadIdx.x];
     } else {
-      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peers[r] + slot_offset + slot_data_offset(seq));
+      // push both values of channel i into peer r's slot (the area reserved for this rank), then poll what peer r pushes here
+      const unsigned long long tag = (unsigned long long)seq << 32;
+      const unsigned long long b0 = (unsigned long long)__double_as_longlong(mine_sm[0][threadIdx.x]);
+      const unsigned long long b1 = (unsigned long long)__double_as_longlong(mine_sm[1][threadIdx.x]);
+      unsigned long long* wbase =
+          reinterpret_cast<unsigned long long*>(peers[r] + slot_offset + slot_area_offset(seq, world, rank));
+      st_volatile_u64(wbase + 2 * (size_t)i, tag | (b0 & 0xffffffffull));
+      st_volatile_u64(wbase + 2 * (size_t)i + 1, tag | (b0 >> 32));
+      st_volatile_u64(wbase + 2 * ((size_t)c + i), tag | (b1 & 0xffffffffull));
+      st_volatile_u64(wbase + 2 * ((size_t)c + i) + 1, tag | (b1 >> 32));
+      const unsigned long long* base = reinterpret_cast<const unsigned long long*>(own + slot_area_offset(seq, world, r));
       const unsigned long long* p0 = base + 2 * (size_t)i;
       const unsigned long long* p1 = base + 2 * ((size_t)c + i);
       unsigned long long w0, w1, w2, w3, spins = 0;
@@ -285,9 +296,9 @@ int ttb_comm_free(void* dev_ptr) {
   return 0;
 }
 
-size_t ttb_comm_slot_bytes(int max_values) {  // header + two data buffers (exchange parity); max_values <= 8192
+size_t ttb_comm_slot_bytes(int max_values) {  // header + 2 parities x kMaxWorld source areas; max_values <= 4096
   if (max_values < 0 || max_values > kCommMaxValues) return 0;
-  return kSlotHeaderBytes + kParityStride + (size_t)max_values * 16;
+  return kSlotHeaderBytes + 2 * (size_t)kMaxWorld * kRankStride;
 }
 
 int ttb_comm_allreduce(const double* partials, int num_chunks, int n, void* const* peers_dev, int world, int rank,

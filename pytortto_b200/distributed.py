@@ -54,7 +54,8 @@ def init_process_group(backend=None, sync_bn=True):
         dist.init_process_group(backend=backend)
     _state.update(initialized=True, world=dist.get_world_size(), rank=dist.get_rank(), sync_bn=bool(sync_bn),
                   backend=backend, peer_comm=None)
-    if backend == "nccl" and sync_bn and _state["world"] > 1 and os.environ.get("TORTTO_B200_PEER_COMM", "1") != "0":
+    if backend == "nccl" and sync_bn and 1 < _state["world"] <= PeerComm.MAX_WORLD and \
+            os.environ.get("TORTTO_B200_PEER_COMM", "1") != "0":
         try:
             enable_peer_comm()
         except RuntimeError as e:  # CUDA IPC not permitted between these processes: keep the NCCL path
@@ -102,7 +103,8 @@ class PeerComm:
     """Small-message all-reduce over NVLink peer memory (csrc/comm.cu): every rank owns a cudaMalloc'ed buffer of
     fixed slots, exported through CUDA IPC and mapped by every peer.  A call site (BatchNorm layer x direction) owns
     one slot for the life of the process, so replays of a captured CUDA graph keep working."""
-    MAX_VALUES = 2 * 4096   # 2C doubles, C <= 4096
+    MAX_VALUES = 2 * 2048   # 2C doubles, C <= 2048 (wider layers take the library all-reduce)
+    MAX_WORLD = 8           # one NVSwitch box: every rank's slot has an area per source rank (csrc/comm.cu)
     SLOTS = 256
 
     def __init__(self):
