@@ -5,20 +5,23 @@ NVLink 5 / NVSwitch through `torch.distributed` (gloo for the CPU host-logic tes
 by rank (`shard_batch`); two exchange steps make a k-GPU run equal the reference's single-process run on the
 concatenated batch:
 
-1. Parameter gradients.  Every rank back-propagates the mean loss of ITS shard.  `DistributedDataParallel` hooks
-   `AccumulateGrad` (the leaf node of the autograd graph, reference autograd/function.py:70-93): as soon as a
-   parameter's gradient is final it is appended to the current bucket (reverse parameter order = the order
-   backward produces them); a full bucket (~10 MB) is flattened and all-reduced (SUM) asynchronously on NCCL's own
-   stream while the rest of backward keeps the compute stream busy.  `reduce_gradients()` (called between
-   `loss.backward()` and `optimizer.step()`) waits for the outstanding buckets, scales by 1/world - the mean over
-   ranks of local-mean gradients IS the global-batch mean gradient - and scatters the result back into `p.grad`.
+1. Parameter gradients.  Every rank back-propagates the mean loss of ITS shard.  The parameters are laid out once in
+   static flat buckets (~10 MB, reverse parameter order = the order backward produces them); the wgrad / BatchNorm
+   backward kernels write each gradient straight into its slot of the bucket (`p._grad_slot`), and
+   `DistributedDataParallel`'s hook on `AccumulateGrad` (the leaf node of the autograd graph, reference
+   autograd/function.py:70-93) launches NCCL's all-reduce (AVG) IN PLACE on a bucket as soon as its last gradient is
+   final - from the wgrad stream, so it overlaps the rest of backward; no pack / unpack passes.  `reduce_gradients()`
+   (between `loss.backward()` and `optimizer.step()`) waits for the outstanding buckets; the mean over ranks of
+   local-mean gradients IS the global-batch mean gradient.
 
 2. BatchNorm statistics (SyncBN).  BatchNorm.forward all-reduces the per-channel double sums [sum x, sum x^2]
    (2C values) and uses count = world * local count, so normalisation and the running statistics (unbiased variance
    with the GLOBAL N/(N-1), reference autograd/grad_nn.py:923-930) are those of the global batch; BatchNorm.backward
    all-reduces [sum dy, sum dy*(x-mean)] so dx follows the reference formula (:984-988) with global sums.
    dgamma / dbeta computed from those all-reduced sums are identical on every rank and equal the SUM over ranks of
-   the local-loss gradients, so they skip the bucket all-reduce and only receive the 1/world scaling.
+   the local-loss gradients, so they skip the bucket all-reduce and only receive the 1/world scaling (decided per step:
+   only for layers that really ran synced).  On one NVSwitch box (<= 8 ranks) the exchange does not go through NCCL:
+   `PeerComm` / csrc/comm.cu is a one-kernel all-reduce over NVLink peer memory, fused with the BatchNorm finalisation.
 """
 import os
 
