@@ -604,7 +604,16 @@ class _BatchNorm(Module):
             if getattr(self, '_nbt', None) is None:
                 self._nbt = float(self.num_batches_tracked.item())
             self._nbt += 1.0
-            factor = 1.0 / self._nbt if self.momentum is None else self.momentum
+            if self.momentum is None:
+                # cumulative moving average: the factor 1/n changes every step and is a HOST scalar - a CUDA-graph replay
+                # would keep applying the factor of the captured step, silently diverging from eager execution
+                import torch
+                if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("BatchNorm with momentum=None (cumulative moving average) cannot be captured in a "
+                                       "CUDA graph: its averaging factor 1/num_batches_tracked changes every step")
+                factor = 1.0 / self._nbt
+            else:
+                factor = self.momentum
         else:
             factor = None
         bn_training = True if self.training else (self.running_mean is None and self.running_var is None)

@@ -77,3 +77,22 @@ def test_device_prefetcher_yields_batches_in_order():
         np.testing.assert_array_equal(yb.data.get(), ys[i].numpy())
         seen += 1
     assert seen == 5
+
+
+def test_cumulative_average_batchnorm_refuses_graph_capture():
+    """BatchNorm2d(momentum=None) averages its running statistics with the HOST factor 1/num_batches_tracked, which changes
+    every step: a graph replay would keep the captured step's factor.  Capturing such a step fails loudly instead."""
+    require_gpu()
+    import torch
+    import pytortto_b200 as tt
+    tt.set_math_mode("tf32")
+    bn = tt.nn.BatchNorm2d(8, momentum=None).cuda()
+    x = tt.tensor(np.random.default_rng(0).standard_normal((4, 8, 6, 6)).astype(np.float32)).cuda()
+
+    def step(inp):
+        return bn(inp).sum()
+
+    with pytest.raises(RuntimeError, match="cumulative moving average"):
+        tt.cuda_graph.GraphedStep(step, (x,), modules=[bn], warmup=1)
+    torch.cuda.synchronize()
+    bn(x)  # eager execution is unaffected
