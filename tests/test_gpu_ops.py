@@ -583,3 +583,22 @@ def test_stem_conv2d_tap_packed_vs_oracle(case, mode):
     assert_close("dx", dx, dxo, tol)
     assert_close("dw", dw, dwo, tol)
     assert_close("db", db, dbo, 2e-5)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "fp32"])
+def test_empty_batch_flows_through_conv_relu_pool(mode):
+    """A batch of zero images (the last, short batch of a data loader can be empty after filtering): shapes follow the
+    reference's formulas (numpy on zero-size arrays), nothing is launched on zero elements, and the weight / bias
+    gradients of the convolution are zeros of the parameter's shape."""
+    tt = _tt(mode)
+    np.random.seed(0)
+    conv = tt.nn.Conv2d(8, 16, 3, 2, 1).cuda()
+    x = tt.nn.Parameter(tt.tensor(np.zeros((0, 8, 12, 10), np.float32)).cuda())
+    y = tt.nn.MaxPool2d(2, 2)(tt.nn.ReLU()(conv(x)))
+    assert tuple(y.shape) == (0, 16, 3, 2)
+    yo = O.conv2d_forward(np.zeros((0, 8, 12, 10), np.float32), conv.weight.data.get(), conv.bias.data.get(), 2, 1, 1)
+    assert yo.shape == (0, 16, 6, 5)
+    y.sum().backward()
+    assert tuple(x.grad.shape) == (0, 8, 12, 10)
+    np.testing.assert_array_equal(conv.weight.grad.get(), np.zeros((16, 8, 3, 3), np.float32))
+    np.testing.assert_array_equal(conv.bias.grad.get(), np.zeros(16, np.float32))
