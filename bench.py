@@ -112,7 +112,23 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the numpy oracle (port of the reference's im2col+GEMM algorithm) on host cores
 # ---------------------------------------------------------------------------------------------------------------
+def _all_host_threads():
+    """The CPU arm uses every host core BLAS can use.  torchrun exports OMP_NUM_THREADS=1 to its workers by default, which
+    would time the reference single-threaded at N > 1: lift the limit for the numpy legs (threadpoolctl)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def oracle_images_per_sec(model, sample_batch, steps, warmup, seed=0):
+    with _all_host_threads():
+        return _oracle_images_per_sec(model, sample_batch, steps, warmup, seed)
+
+
+def _oracle_images_per_sec(model, sample_batch, steps, warmup, seed=0):
     from oracle.resnet_oracle import StepOracle, init_params
     cfg = MODELS[model]
     oc = cfg["oracle"]
@@ -138,9 +154,11 @@ def cpu_sample_batch(model, batch, budget_s, steps):
 
 
 def blas_threads():
+    """threads the numpy legs ran on (inside _all_host_threads)"""
     try:
         from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+        with _all_host_threads():
+            return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
     except Exception:
         return os.cpu_count() or 1
 
