@@ -836,10 +836,10 @@ constexpr size_t persist_smem_bytes(int bn, int nstages, int wt) {
 }
 
 // Taps per pipeline stage along W (the kernel's WT): 3 = the three taps of a filter row share one A strip (3-wide filters,
-// unit stride and dilation in W, 64 / 128-wide tiles - wider tiles are tensor-bound already and have no room for three
+// unit stride and dilation in W, 32 / 64 / 128-wide tiles - wider tiles are tensor-bound already and have no room for three
 // weight tiles per stage; rows shorter than 8 outputs would waste > 25 % of the MMAs on the dropped positions), else 1.
 static int pick_wt(int taps_w, int stride_w, int dil_w, int bn, int q_out) {
-  if (taps_w != 3 || stride_w != 1 || dil_w != 1 || (bn != 64 && bn != 128) || q_out < 8) return 1;
+  if (taps_w != 3 || stride_w != 1 || dil_w != 1 || (bn != 32 && bn != 64 && bn != 128) || q_out < 8) return 1;
   return tuning_knob("TTB_WT", 3) == 3 ? 3 : 1;
 }
 
@@ -883,7 +883,7 @@ static int launch_persist(const FwdParamsMulti& PM, int count, cudaStream_t st) 
 // tiles run two CTAs per SM (two independent issue streams; their ring is sized to let two fit).
 struct PersistCfg { int nstages, nprod; };
 static PersistCfg persist_cfg(int bn, int wt) {
-  if (wt == 3) return bn == 128 ? PersistCfg{3, 3} : PersistCfg{2, 2};
+  if (wt == 3) return bn == 64 ? PersistCfg{2, 2} : PersistCfg{3, 3};
   switch (bn) {
     case 256: return {4, 2};
     case 128: return {6, 3};
@@ -895,6 +895,7 @@ template <bool BF16, int STATS>
 static int launch_persist_sel(const FwdParamsMulti& PM, int count, int bn, int wt, cudaStream_t st) {
   if (wt == 3) {
     if (bn == 128) return launch_persist<128, 3, 3, 3, BF16, STATS>(PM, count, st);
+    if (bn == 32) return launch_persist<32, 3, 3, 3, BF16, STATS>(PM, count, st);  // (32-filter layers: UNet level 1)
     return launch_persist<64, 2, 2, 3, BF16, STATS>(PM, count, st);
   }
   switch (bn) {
