@@ -164,3 +164,38 @@ def test_bad_arguments_fail_loudly_without_a_gpu():
     assert lib.ttb_comm_bn_finalize(None, 0, None, 2, 0, 0, 1, 8, 1e-5, 0.1, None, None, None, None, None, None, None, None,
                                     None, None) != 0
     assert b"comm_bn_finalize" in lib.ttb_last_error()
+
+
+def test_round2_planning_entry_points_are_host_logic():
+    """Host-side decisions added in round 2, callable without a GPU: row-packed staging of tall-filter stems (workspace
+    size), availability of the dgrad + BatchNorm-backward-statistics epilogue, geometry of a SyncBN peer slot."""
+    from pytortto_b200 import _cabi, ops
+    lib = _cabi.load()
+    ops.set_math_mode("tf32")
+    a256 = lambda b: (b + 255) // 256 * 256
+
+    # 7x7x3 / stride 2 / pad 3 stem at 224^2: ROW-packed - one staged row per (n, h, q) with round_up(7*3, 32) = 32 columns -
+    # instead of round_up(7*7*3, 32) = 160 columns per output pixel
+    n, h, k = 4, 224, 64
+    d = ops.conv_desc((n, 3, h, h), (k, 3, 7, 7), (2, 2), (3, 3), (1, 1), 1)
+    ws = lib.ttb_conv2d_workspace_size(ctypes.byref(d), 0)
+    row_packed = a256(n * h * 112 * 32 * 4) + a256(k * 7 * 32 * 4)
+    full_packed = a256(n * 112 * 112 * 160 * 4) + a256(k * 160 * 4)
+    assert row_packed <= ws < full_packed, (ws, row_packed, full_packed)
+    # the 3x3x3 CIFAR stem keeps the full packing (27 taps -> ONE 32-column K-block per output pixel)
+    d3 = ops.conv_desc((n, 3, 32, 32), (k, 3, 3, 3), (1, 1), (1, 1), (1, 1), 1)
+    assert lib.ttb_conv2d_workspace_size(ctypes.byref(d3), 0) == a256(n * 32 * 32 * 32 * 4) + a256(k * 32 * 4)
+
+    # dgrad + BatchNorm-backward sums: dense stride-1 problems with ready-made operands only
+    s1 = ops.conv_desc((8, 64, 16, 16), (64, 64, 3, 3), (1, 1), (1, 1), (1, 1), 1)
+    s2 = ops.conv_desc((8, 64, 16, 16), (64, 64, 3, 3), (2, 2), (1, 1), (1, 1), 1)
+    g2 = ops.conv_desc((8, 64, 16, 16), (64, 32, 3, 3), (1, 1), (1, 1), (1, 1), 2)
+    c3 = ops.conv_desc((8, 3, 16, 16), (64, 3, 3, 3), (1, 1), (1, 1), (1, 1), 1)
+    assert lib.ttb_conv2d_dgrad_bn_stats_chunks(ctypes.byref(s1)) > 0
+    assert lib.ttb_conv2d_dgrad_bn_stats_chunks(ctypes.byref(s2)) == 0
+    assert lib.ttb_conv2d_dgrad_bn_stats_chunks(ctypes.byref(g2)) == 0
+    assert lib.ttb_conv2d_dgrad_bn_stats_chunks(ctypes.byref(c3)) == 0   # staged operands (padded channels)
+
+    # SyncBN peer slot: header + 2 parities x 8 source-rank areas of 4096 word pairs; larger exchanges are refused
+    assert lib.ttb_comm_slot_bytes(4096) == 16 + 2 * 8 * 4096 * 16
+    assert lib.ttb_comm_slot_bytes(4097) == 0
