@@ -255,6 +255,79 @@ maxpool_bwd4_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t
   }
 }
 
+// 3 x 3 / stride 2 (the ResNet stem pool): one thread = a 2 x 2 block of input pixels x 4 channels.  With u = h + pad, the
+// rows u = 2a+1 (covered by window p = a through tap r = 1) and u = 2a+2 (p = a+1 through r = 0, p = a through r = 2) see only
+// the windows p in {a, a+1}, and likewise for the columns: the block's four pixels read the SAME four windows, whose index
+// words and gradients are loaded once (4 + 4 loads for 4 outputs; the per-pixel gather loads 9 + 9).  The candidates of a
+// pixel are visited r ascending, then s ascending - the first hit is the last writer in raster order (reference
+// grad_nn.py:820), exactly as maxpool_bwd4_kernel does.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_k3s2_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx,
+                        int a_lo, int na, int b_lo, int nb) {
+  pdl_entry();
+  const int cq = d.c / 4;
+  const int64_t total = (int64_t)d.n * na * nb * cq;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int c0 = (int)(t % cq) * 4;
+    int64_t rest = t / cq;
+    const int b = b_lo + (int)(rest % nb);
+    rest /= nb;
+    const int a = a_lo + (int)(rest % na);
+    const int n = (int)(rest / na);
+    // the four windows (p, q) in {a, a+1} x {b, b+1}: index word and gradient, 0xFFFFFFFF / 0 when the window does not exist
+    uint32_t ib[2][2];
+    float4 g[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int p = a + i, q = b + j;
+        const bool ok = p >= 0 && p < d.p && q >= 0 && q < d.q;
+        const int64_t o = ok ? (((int64_t)n * d.p + p) * d.q + q) * d.c + c0 : 0;
+        ib[i][j] = ok ? *reinterpret_cast<const uint32_t*>(idx + o) : 0xFFFFFFFFu;
+        g[i][j] = ok ? ld_f4_stream(dy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    // pixel (hi, wi) of the block: hi = 0 -> u odd (tap r = 1 of window a), hi = 1 -> u even (r = 0 of a+1, then r = 2 of a)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int h = 2 * a + 1 + hi - d.pad_h;
+      if (h < 0 || h >= d.h) continue;
+#pragma unroll
+      for (int wi = 0; wi < 2; ++wi) {
+        const int w = 2 * b + 1 + wi - d.pad_w;
+        if (w < 0 || w >= d.w) continue;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned done = 0;
+        // candidate list in (r ascending, s ascending) order: (window row offset i, tap r), (window column offset j, tap s)
+        const int nr = hi ? 2 : 1, ns = wi ? 2 : 1;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (e >= nr) break;
+          const int i = hi ? 1 - e : 0, r = hi ? 2 * e : 1;
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            if (f >= ns) break;
+            const int j = wi ? 1 - f : 0, sx = wi ? 2 * f : 1;
+            const uint32_t code = (uint32_t)(r * 3 + sx), word = ib[i][j];
+            unsigned hit = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hit |= (((word >> (8 * k)) & 0xFFu) == code) ? (1u << k) : 0u;
+            if (!ACCUM) hit &= ~done;
+            const float gv[4] = {g[i][j].x, g[i][j].y, g[i][j].z, g[i][j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (hit & (1u << k)) acc[k] = ACCUM ? acc[k] + gv[k] : gv[k];
+            done |= hit;
+          }
+        }
+        st_f4(dx + ((((int64_t)n * d.h + h) * d.w + w) * d.c + c0), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      }
+    }
+  }
+}
+
 }  // namespace ttb
 
 using namespace ttb;
@@ -299,8 +372,16 @@ int ttb_maxpool2d_bwd(const ttb_pool_desc* d, const float* dy, const uint8_t* id
     if (accumulate) launch_k(maxpool_bwd4_kernel<true, KH, KW, SH, SW>, grid4, 256, 0, st, *d, dy, idx, dx, total / 4);  \
     else launch_k(maxpool_bwd4_kernel<false, KH, KW, SH, SW>, grid4, 256, 0, st, *d, dy, idx, dx, total / 4);   \
   } while (0)
-    if (unit_dil && d->kh == 3 && d->kw == 3 && d->stride_h == 2 && d->stride_w == 2) TTB_POOL_BWD(3, 3, 2, 2);
-    else if (unit_dil && d->kh == 2 && d->kw == 2 && d->stride_h == 2 && d->stride_w == 2) TTB_POOL_BWD(2, 2, 2, 2);
+    if (unit_dil && d->kh == 3 && d->kw == 3 && d->stride_h == 2 && d->stride_w == 2) {
+      // blocks of 2 x 2 input pixels: u = h + pad in {2a+1, 2a+2}, a = floor((u - 1) / 2) over u in [pad, H - 1 + pad]
+      auto fl = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };  // floor(v / 2)
+      const int a_lo = fl(d->pad_h - 1), a_hi = fl(d->h + d->pad_h - 2);
+      const int b_lo = fl(d->pad_w - 1), b_hi = fl(d->w + d->pad_w - 2);
+      const int na = a_hi - a_lo + 1, nb = b_hi - b_lo + 1;
+      const int grid = elementwise_grid((int64_t)d->n * na * nb * (d->c / 4), 256);
+      if (accumulate) launch_k(maxpool_bwd_k3s2_kernel<true>, grid, 256, 0, st, *d, dy, idx, dx, a_lo, na, b_lo, nb);
+      else launch_k(maxpool_bwd_k3s2_kernel<false>, grid, 256, 0, st, *d, dy, idx, dx, a_lo, na, b_lo, nb);
+    } else if (unit_dil && d->kh == 2 && d->kw == 2 && d->stride_h == 2 && d->stride_w == 2) TTB_POOL_BWD(2, 2, 2, 2);
     else TTB_POOL_BWD(0, 0, 0, 0);
 #undef TTB_POOL_BWD
     return check_launch("maxpool2d_bwd");
