@@ -12,8 +12,12 @@ call; inputs are copied into the captured input buffers first, outputs are read 
     loss.item()
 
 Constraints (checked or documented): fixed shapes; no host synchronisation inside the step (`.item()`, `.get()`);
-hyper-parameters baked at capture time (call `recapture()` after changing the learning rate); BatchNorm's host-side
-`num_batches_tracked` counter is advanced on every replay for the modules passed in `modules`.
+host-side hyper-parameters are baked at capture time (call `recapture()` after changing the learning rate; Adam's step
+count and bias corrections live on the device and advance inside the graph; BatchNorm with `momentum=None` - a host-side
+1/n averaging factor - refuses to be captured); BatchNorm's host-side `num_batches_tracked` counter is advanced on every
+replay for the modules passed in `modules`.  Side effect to know about: the `warmup` eager executions are REAL training
+steps on the example inputs (parameters, momentum buffers and running statistics move); the recorded execution itself does
+not run.
 """
 import torch
 
