@@ -328,6 +328,46 @@ maxpool_bwd_k3s2_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uin
   }
 }
 
+// 2 x 2 / stride 2 (UNet's pools): windows do not overlap, so the 2 x 2 block of input pixels u = h + pad in {2a, 2a+1} x
+// {2b, 2b+1} belongs to window (a, b) alone - one index word and one gradient load serve its four pixels (tap r*2 + s).
+// ACCUM and last-writer-wins coincide (one candidate per pixel).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_k2s2_kernel(ttb_pool_desc d, const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx,
+                        int a_lo, int na, int b_lo, int nb) {
+  pdl_entry();
+  const int cq = d.c / 4;
+  const int64_t total = (int64_t)d.n * na * nb * cq;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int c0 = (int)(t % cq) * 4;
+    int64_t rest = t / cq;
+    const int b = b_lo + (int)(rest % nb);
+    rest /= nb;
+    const int a = a_lo + (int)(rest % na);
+    const int n = (int)(rest / na);
+    const bool ok = a >= 0 && a < d.p && b >= 0 && b < d.q;
+    const int64_t o = ok ? (((int64_t)n * d.p + a) * d.q + b) * d.c + c0 : 0;
+    const uint32_t word = ok ? *reinterpret_cast<const uint32_t*>(idx + o) : 0xFFFFFFFFu;
+    const float4 g = ok ? ld_f4_stream(dy + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int h = 2 * a + r - d.pad_h;
+      if (h < 0 || h >= d.h) continue;
+#pragma unroll
+      for (int sx = 0; sx < 2; ++sx) {
+        const int w = 2 * b + sx - d.pad_w;
+        if (w < 0 || w >= d.w) continue;
+        const uint32_t code = (uint32_t)(r * 2 + sx);
+        float acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = (((word >> (8 * k)) & 0xFFu) == code) ? gv[k] : 0.f;
+        st_f4(dx + ((((int64_t)n * d.h + h) * d.w + w) * d.c + c0), make_float4(acc[0], acc[1], acc[2], acc[3]));
+      }
+    }
+  }
+}
+
 }  // namespace ttb
 
 using namespace ttb;
@@ -381,7 +421,13 @@ int ttb_maxpool2d_bwd(const ttb_pool_desc* d, const float* dy, const uint8_t* id
       const int grid = elementwise_grid((int64_t)d->n * na * nb * (d->c / 4), 256);
       if (accumulate) launch_k(maxpool_bwd_k3s2_kernel<true>, grid, 256, 0, st, *d, dy, idx, dx, a_lo, na, b_lo, nb);
       else launch_k(maxpool_bwd_k3s2_kernel<false>, grid, 256, 0, st, *d, dy, idx, dx, a_lo, na, b_lo, nb);
-    } else if (unit_dil && d->kh == 2 && d->kw == 2 && d->stride_h == 2 && d->stride_w == 2) TTB_POOL_BWD(2, 2, 2, 2);
+    } else if (unit_dil && d->kh == 2 && d->kw == 2 && d->stride_h == 2 && d->stride_w == 2) {
+      auto fl = [](int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); };  // floor(v / 2)
+      const int a_lo = fl(d->pad_h), a_hi = fl(d->h - 1 + d->pad_h), b_lo = fl(d->pad_w), b_hi = fl(d->w - 1 + d->pad_w);
+      const int na = a_hi - a_lo + 1, nb = b_hi - b_lo + 1;
+      const int grid = elementwise_grid((int64_t)d->n * na * nb * (d->c / 4), 256);
+      launch_k(maxpool_bwd_k2s2_kernel, grid, 256, 0, st, *d, dy, idx, dx, a_lo, na, b_lo, nb);
+    }
     else TTB_POOL_BWD(0, 0, 0, 0);
 #undef TTB_POOL_BWD
     return check_launch("maxpool2d_bwd");
